@@ -1,0 +1,143 @@
+/*
+ * pn2_api.h — C ABI of libpn2_b200.so: the PointNet++ set-abstraction / feature-propagation
+ * geometry ops as hand-written sm_100a CUDA kernels.
+ *
+ * This is the drop-in boundary for charlesq34/pointnet2's tf_ops/{sampling,grouping,
+ * 3d_interpolation}.  Every entry point replaces one of the free "Launcher"/"_cpu" functions the
+ * reference's TensorFlow OpKernels call (cited per function, paths relative to the reference
+ * root) and keeps that function's scalar/pointer argument order, with a trailing CUDA stream.
+ *
+ * Conventions (all entry points):
+ *   - plain C, no torch/TF types: sizes are `int`, tensors are raw pointers, `stream` is a
+ *     cudaStream_t passed as void* (NULL = legacy default stream, as the reference uses).
+ *   - device entry points (pn2_*): every pointer is a DEVICE pointer to a dense row-major
+ *     float32 / int32 tensor.  The library allocates nothing, frees nothing and never
+ *     synchronises; launches are asynchronous on `stream`.  Stateless and re-entrant.
+ *   - gradients accumulate with float atomics into a buffer the CALLER has zero-filled, exactly
+ *     like the reference (tf_sampling.cpp:174, tf_grouping.cpp:204, tf_interpolate.cpp:258).
+ *   - return value: 0 on success, otherwise a cudaError_t (argument errors return
+ *     cudaErrorInvalidValue = 1).  pn2_error_string() translates.
+ *   - limits: every tensor must have fewer than 2^31 elements per batch entry; n, m < 2^31.
+ */
+#ifndef PN2_API_H_
+#define PN2_API_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PN2_API_VERSION 1
+
+/* ---- sampling (replaces tf_ops/sampling/tf_sampling_g.cu launchers) ---------------------- */
+
+/* farthestpointsamplingLauncher(b,n,m,inp,temp,out), tf_sampling_g.cu:203-205.
+ * inp (b,n,3) f32; out (b,m) i32.  out[:,0] = 0; selection order and tie-break identical to the
+ * reference kernel (:105-170): argmax of the running min squared distance under
+ * (value desc, k mod 512 asc, k asc).  `temp` is the reference's (32,n) scratch: unused here
+ * (the running minimum lives in registers), may be NULL. */
+int pn2_fps(int b, int n, int m, const float* inp, float* temp, int* out, void* stream);
+
+/* Same, also emitting new_xyz (b,m,3) = inp gathered at out (FPS + gather_point in one launch;
+ * the pair sample_and_group always issues, utils/pointnet_util.py:40). new_xyz may be NULL. */
+int pn2_fps_gather(int b, int n, int m, const float* inp, int* out, float* new_xyz, void* stream);
+
+/* gatherpointLauncher(b,n,m,inp,idx,out), tf_sampling_g.cu:206-208. out (b,m,3). */
+int pn2_gather_point(int b, int n, int m, const float* inp, const int* idx, float* out, void* stream);
+
+/* scatteraddpointLauncher(b,n,m,out_g,idx,inp_g), tf_sampling_g.cu:209-211.
+ * inp_g (b,n,3) must be zero-filled by the caller. */
+int pn2_gather_point_grad(int b, int n, int m, const float* out_g, const int* idx, float* inp_g, void* stream);
+
+/* ---- grouping (replaces tf_ops/grouping/tf_grouping_g.cu launchers) ----------------------- */
+
+/* queryBallPointLauncher(b,n,m,radius,nsample,xyz1,xyz2,idx,pts_cnt), tf_grouping_g.cu:125-128.
+ * xyz1 (b,n,3) data, xyz2 (b,m,3) queries; idx (b,m,nsample) i32, pts_cnt (b,m) i32.
+ * First nsample hits in ascending index order, row padded with the first hit.  Rows with no hit
+ * (undefined in the reference) are written as zeros with pts_cnt = 0. */
+int pn2_query_ball_point(int b, int n, int m, float radius, int nsample, const float* xyz1,
+                         const float* xyz2, int* idx, int* pts_cnt, void* stream);
+
+/* groupPointLauncher(b,n,c,m,nsample,points,idx,out), tf_grouping_g.cu:133-136.
+ * points (b,n,c); idx (b,m,nsample); out (b,m,nsample,c). */
+int pn2_group_point(int b, int n, int c, int m, int nsample, const float* points, const int* idx,
+                    float* out, void* stream);
+
+/* groupPointGradLauncher(b,n,c,m,nsample,grad_out,idx,grad_points), tf_grouping_g.cu:137-141.
+ * grad_points (b,n,c) must be zero-filled by the caller. */
+int pn2_group_point_grad(int b, int n, int c, int m, int nsample, const float* grad_out,
+                         const int* idx, float* grad_points, void* stream);
+
+/* selectionSortLauncher(b,n,m,k,dist,outi,out), tf_grouping_g.cu:129-132 (select_top_k).
+ * dist (b,m,n); outi (b,m,n) i32, out (b,m,n) f32: the first k columns hold the k smallest values
+ * of each row, ascending, and their indices, as k rounds of selection sort with swaps produce;
+ * columns >= k hold the permuted remainder exactly as the reference leaves it. */
+int pn2_selection_sort(int b, int n, int m, int k, const float* dist, int* outi, float* out, void* stream);
+
+/* ---- 3d_interpolation (replaces the CPU functions of tf_interpolate.cpp; now on the GPU) -- */
+
+/* threenn_cpu(b,n,m,xyz1,xyz2,dist,idx), tf_interpolate.cpp:60-103.
+ * xyz1 (b,n,3) unknown, xyz2 (b,m,3) known; dist (b,n,3) f32 SQUARED distances ascending,
+ * idx (b,n,3) i32; ties -> lower index; m < 3 -> (+inf, 0) fill.  Bit-exact with the reference's
+ * x86 arithmetic (no contraction). */
+int pn2_three_nn(int b, int n, int m, const float* xyz1, const float* xyz2, float* dist, int* idx, void* stream);
+
+/* threeinterpolate_cpu(b,m,c,n,points,idx,weight,out), tf_interpolate.cpp:107-127.
+ * points (b,m,c); idx, weight (b,n,3); out (b,n,c). */
+int pn2_three_interpolate(int b, int m, int c, int n, const float* points, const int* idx,
+                          const float* weight, float* out, void* stream);
+
+/* threeinterpolate_grad_cpu(b,n,c,m,grad_out,idx,weight,grad_points), tf_interpolate.cpp:131-153.
+ * grad_points (b,m,c) must be zero-filled by the caller. */
+int pn2_three_interpolate_grad(int b, int n, int c, int m, const float* grad_out, const int* idx,
+                               const float* weight, float* grad_points, void* stream);
+
+/* ---- fused callers' glue (utils/pointnet_util.py) ------------------------------------------ */
+
+/* sample_and_group's grouping tail, utils/pointnet_util.py:45-54 (SSG) and :179-186 (MSG), in
+ * one pass: out[b,j,k,:] = concat of (xyz[idx]-new_xyz[j]) and points[idx] in the order chosen.
+ *   xyz (b,n,3), new_xyz (b,m,3), points (b,n,c) or NULL (c = 0), idx (b,m,nsample)
+ *   out (b,m,nsample,3+c);  grouped_xyz (b,m,nsample,3) or NULL (the 4th return of
+ *   sample_and_group);  xyz_first != 0: [xyz, feats] (SSG, :50), else [feats, xyz] (MSG, :184). */
+int pn2_group_concat(int b, int n, int c, int m, int nsample, const float* xyz, const float* new_xyz,
+                     const float* points, const int* idx, int xyz_first, float* out,
+                     float* grouped_xyz, void* stream);
+
+/* pointnet_fp_module's front end, utils/pointnet_util.py:211-216, in one pass over the unknown
+ * points: three_nn -> dist=max(dist,1e-10); w=(1/dist)/sum(1/dist) -> three_interpolate.
+ *   xyz1 (b,n,3), xyz2 (b,m,3), points2 (b,m,c) -> out (b,n,c).
+ *   dist/idx/weight (b,n,3) outputs are optional (NULL to skip). */
+int pn2_three_nn_interpolate(int b, int n, int m, int c, const float* xyz1, const float* xyz2,
+                             const float* points2, float* out, float* dist, int* idx, float* weight,
+                             void* stream);
+
+/* ---- host-buffer entry point (the reference feeds numpy through feed_dict) ----------------- */
+
+/* One SSG set-abstraction sampling+grouping layer (farthest_point_sample + gather_point +
+ * query_ball_point + group_point(xyz), utils/pointnet_util.py:40-45) on HOST buffers:
+ * copies h_xyz (b,n,3) to the device, runs the four ops, copies new_xyz (b,m,3), idx (b,m,nsample),
+ * pts_cnt (b,m) and grouped_xyz (b,m,nsample,3; NOT centred) back.  Host buffers should be
+ * pinned for the copies to be asynchronous.  `workspace` is a device buffer of at least
+ * pn2_sa_layer_workspace_bytes(b,n,m,nsample) bytes supplied by the caller.  Asynchronous on
+ * `stream`: synchronise the stream before reading the outputs. */
+size_t pn2_sa_layer_workspace_bytes(int b, int n, int m, int nsample);
+int pn2_sa_layer_host(int b, int n, int m, float radius, int nsample, const float* h_xyz,
+                      float* h_new_xyz, int* h_idx, int* h_pts_cnt, float* h_grouped_xyz,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- introspection ------------------------------------------------------------------------- */
+int pn2_api_version(void);
+const char* pn2_error_string(int code);
+/* number of kernel launches (not memcpys) this library has issued in this process */
+unsigned long long pn2_launch_count(void);
+/* the exact d2-domain threshold the ball query uses for `radius`
+ * (largest float t with max(sqrtf(t),1e-20f) < radius; negative if no t qualifies) */
+float pn2_ball_threshold(float radius);
+/* tuning override for experiments: "T,P,C" (threads, points/thread, cluster size); NULL resets */
+void pn2_set_fps_config(int threads, int points_per_thread, int cluster);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PN2_API_H_ */

@@ -1,0 +1,84 @@
+"""ctypes loader for libpn2_b200.so — the thin C-ABI layer between the Python ops and the CUDA
+kernels (the same mechanism the reference uses for its own native helper, utils/show3d_balls.py:23).
+
+There is NO CPU fallback: if the library cannot be loaded (and cannot be built), importing the
+ops raises; calling an op on a non-CUDA tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_float, c_int, c_size_t, c_ulonglong, c_void_p
+
+from . import _build
+
+_P = c_void_p
+_SIGNATURES = {
+    # name: (restype, argtypes)   — mirrors include/pn2_api.h
+    "pn2_fps": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P]),
+    "pn2_fps_gather": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P]),
+    "pn2_gather_point": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P]),
+    "pn2_gather_point_grad": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P]),
+    "pn2_query_ball_point": (c_int, [c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P]),
+    "pn2_group_point": (c_int, [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "pn2_group_point_grad": (c_int, [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "pn2_selection_sort": (c_int, [c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "pn2_three_nn": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P, _P]),
+    "pn2_three_interpolate": (c_int, [c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
+    "pn2_three_interpolate_grad": (c_int, [c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
+    "pn2_group_concat": (c_int, [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P, _P, _P]),
+    "pn2_three_nn_interpolate": (c_int, [c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pn2_sa_layer_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "pn2_sa_layer_host": (c_int, [c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "pn2_api_version": (c_int, []),
+    "pn2_error_string": (ctypes.c_char_p, [c_int]),
+    "pn2_launch_count": (c_ulonglong, []),
+    "pn2_ball_threshold": (c_float, [c_float]),
+    "pn2_set_fps_config": (None, [c_int, c_int, c_int]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load() -> ctypes.CDLL:
+    """Load (building first if missing/stale and nvcc is present) libpn2_b200.so. Raises on failure."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if _build.is_stale():
+        try:
+            _build.build()
+        except Exception as e:  # stale-but-present library on a box without nvcc is still usable
+            if not os.path.exists(path):
+                raise ImportError(f"libpn2_b200.so is missing and could not be built: {e}") from e
+    try:
+        lib = ctypes.CDLL(path)
+    except OSError as e:
+        raise ImportError(f"cannot load {path}: {e} — the CUDA extension is required, there is no fallback") from e
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class Pn2Error(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().pn2_error_string(rc)
+        raise Pn2Error(f"{what} failed: CUDA error {rc} ({msg.decode() if msg else '?'})")
+
+
+def launch_count() -> int:
+    return int(load().pn2_launch_count())

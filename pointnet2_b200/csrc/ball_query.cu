@@ -1,0 +1,193 @@
+// ball_query.cu — query_ball_point for sm_100a.
+//
+// Replaces query_ball_point_gpu / queryBallPointLauncher
+// (reference tf_ops/grouping/tf_grouping_g.cu:3-36, :125-128).
+//
+// Semantics (bit-exact): for each query j, the first `nsample` data indices k in ASCENDING order
+// with max(sqrtf(d2),1e-20f) < radius, d2 in the reference's contraction pattern
+// (pn2::d2_fma_pattern, operands query - point); the row is padded with the first hit; pts_cnt is
+// the number of real hits.  Rows with no hit are undefined in the reference; here they are zeros.
+//
+// The sqrtf is removed exactly: correctly-rounded sqrtf is monotone, so the hit test equals
+// !(d2 > thr) for the float threshold thr = max{t : sqrtf(t) < radius}, found once on the host by
+// bisection over float bit patterns (pn2_ball_threshold).  The negated form keeps the reference's
+// NaN behaviour (fmaxf(NaN,1e-20f) = 1e-20f < radius is a hit).
+//
+// Design: a group of G lanes (G = 1..32, chosen from the amount of parallelism B*M offers) owns one
+// query and tests G consecutive data points per step; data points are staged through shared memory
+// in float4-padded tiles (one LDS.128 per test, broadcast across the groups of a warp); hits are
+// rare, so the ordered compaction (ballot + popc prefix within the group) sits behind one
+// warp-uniform branch; a CTA stops scanning as soon as all of its queries are full.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "pn2_common.cuh"
+
+namespace pn2 {
+
+constexpr int kBqThreads = 256;
+constexpr int kBqTile = 2048;  // data points per shared-memory tile (32 KB as float4)
+constexpr int kBqUnroll = 4;
+
+template <int G>
+__global__ void __launch_bounds__(kBqThreads)
+ball_query_kernel(int n, int m, float thr, int nsample, const float* __restrict__ xyz1,
+                  const float* __restrict__ xyz2, int* __restrict__ idx, int* __restrict__ pts_cnt) {
+    constexpr int QPB = kBqThreads / G;  // queries per CTA
+    constexpr int STEP = G * kBqUnroll;  // data points consumed per unrolled step
+    __shared__ float4 s_pts[kBqTile + 32 * kBqUnroll];
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int g = tid % G;                     // lane within the group
+    const int gbase = lane - g;                // first lane of this group within the warp
+    const unsigned gmask_all = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
+    const int cloud = blockIdx.y;
+    const int q = blockIdx.x * QPB + tid / G;
+    const bool valid = q < m;
+
+    const float* __restrict__ data = xyz1 + (size_t)cloud * n * 3;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (valid) {
+        const float* qp = xyz2 + ((size_t)cloud * m + q) * 3;
+        qx = qp[0];
+        qy = qp[1];
+        qz = qp[2];
+    }
+    int* __restrict__ row = idx + ((size_t)cloud * m + (valid ? q : 0)) * nsample;
+
+    int cnt = valid ? 0 : nsample;  // out-of-range groups count as already full
+    int first = 0;
+
+    for (int base = 0; base < n; base += kBqTile) {
+        const int tn = min(kBqTile, n - base);
+        const int tn_pad = ((tn + STEP - 1) / STEP) * STEP;
+        // (the __syncthreads_and at the bottom of the previous iteration guarantees the previous
+        //  tile is fully consumed before it is overwritten)
+        for (int p = tid; p < tn_pad; p += kBqThreads) {
+            float4 v = make_float4(1e30f, 1e30f, 1e30f, 0.f);  // padding: far away, never a hit
+            if (p < tn) {
+                const float* s = data + (size_t)(base + p) * 3;
+                v.x = s[0];
+                v.y = s[1];
+                v.z = s[2];
+            }
+            s_pts[p] = v;
+        }
+        __syncthreads();
+
+        bool warp_done = __all_sync(kFullMask, cnt >= nsample);
+        for (int p = 0; p < tn_pad && !warp_done; p += STEP) {
+            bool hit[kBqUnroll];
+            bool any = false;
+#pragma unroll
+            for (int u = 0; u < kBqUnroll; ++u) {
+                const float4 v = s_pts[p + u * G + g];
+                const float d2 = d2_fma_pattern(qx, qy, qz, v.x, v.y, v.z);
+                hit[u] = !(d2 > thr);
+                any |= hit[u];
+            }
+            if (__any_sync(kFullMask, any && (cnt < nsample))) {
+#pragma unroll
+                for (int u = 0; u < kBqUnroll; ++u) {
+                    const int k = base + p + u * G + g;
+                    const bool h = hit[u] && (k < n) && (cnt < nsample);
+                    const unsigned bal = __ballot_sync(kFullMask, h);
+                    const unsigned gm = bal & gmask_all;
+                    if (bal != 0u) {
+                        // first hit of the row: every lane of the group learns its index
+                        const int src_lane = gm ? (__ffs(gm) - 1) : lane;
+                        const int k_first = __shfl_sync(kFullMask, k, src_lane);
+                        if (gm != 0u) {
+                            if (cnt == 0) first = k_first;
+                            const int rank = __popc(gm & ((1u << lane) - 1u));
+                            if (h && cnt + rank < nsample) row[cnt + rank] = k;
+                            cnt = min(cnt + __popc(gm), nsample);
+                        }
+                    }
+                }
+                warp_done = __all_sync(kFullMask, cnt >= nsample);
+            }
+        }
+        if (__syncthreads_and(cnt >= nsample)) break;
+    }
+
+    if (valid) {
+        // pad the tail of the row with the first hit (zeros if there was none)
+        for (int l = cnt + g; l < nsample; l += G) row[l] = first;
+        if (g == 0) pts_cnt[(size_t)cloud * m + q] = cnt;
+    }
+}
+
+template <int G>
+static int launch_bq(int b, int n, int m, float thr, int nsample, const float* xyz1, const float* xyz2, int* idx,
+                     int* pts_cnt, cudaStream_t st) {
+    constexpr int QPB = kBqThreads / G;
+    dim3 grid((m + QPB - 1) / QPB, b, 1);
+    ball_query_kernel<G><<<grid, kBqThreads, 0, st>>>(n, m, thr, nsample, xyz1, xyz2, idx, pts_cnt);
+    return finish_launch();
+}
+
+static int g_bq_group = 0;  // experiment override (PN2_BQ_GROUP env, read once)
+
+static int pick_group(int b, int m) {
+    static bool init = false;
+    if (!init) {
+        const char* e = getenv("PN2_BQ_GROUP");
+        if (e) g_bq_group = atoi(e);
+        init = true;
+    }
+    if (g_bq_group > 0) return g_bq_group;
+    // aim for >= ~2 CTAs' worth of lanes per SM: 148 SMs * 1024 lanes
+    const long long queries = (long long)b * m;
+    int G = 1;
+    while (G < 32 && queries * G < 148LL * 1024) G *= 2;
+    return G;
+}
+
+}  // namespace pn2
+
+extern "C" {
+
+float pn2_ball_threshold(float radius) {
+    // Largest float t >= 0 with max(sqrtf(t), 1e-20f) < radius; -1 if there is none.
+    if (!(radius > 1e-20f)) return -1.0f;
+    uint32_t lo = 0u, hi = 0x7f7fffffu;  // +0 .. FLT_MAX: the predicate is monotone in the bit pattern
+    float f;
+    memcpy(&f, &hi, 4);
+    if (sqrtf(f) < radius) return f;
+    while (hi - lo > 1u) {  // invariant: pred(lo) holds, pred(hi) does not
+        const uint32_t mid = lo + (hi - lo) / 2u;
+        memcpy(&f, &mid, 4);
+        if (sqrtf(f) < radius) lo = mid;
+        else hi = mid;
+    }
+    memcpy(&f, &lo, 4);
+    return f;
+}
+
+int pn2_query_ball_point(int b, int n, int m, float radius, int nsample, const float* xyz1, const float* xyz2,
+                         int* idx, int* pts_cnt, void* stream) {
+    using namespace pn2;
+    if (b < 0 || n <= 0 || m < 0 || nsample <= 0 || !(radius > 0.0f)) return (int)cudaErrorInvalidValue;
+    if (b == 0 || m == 0) return 0;
+    if (!xyz1 || !xyz2 || !idx || !pts_cnt) return (int)cudaErrorInvalidValue;
+    if (b > 65535) return (int)cudaErrorInvalidValue;
+    cudaStream_t st = as_stream(stream);
+    const float thr = pn2_ball_threshold(radius);
+    if (thr < 0.0f) {  // radius <= 1e-20f: the reference's test can never pass
+        cudaError_t e = cudaMemsetAsync(idx, 0, sizeof(int) * (size_t)b * m * nsample, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(pts_cnt, 0, sizeof(int) * (size_t)b * m, st);
+        return (int)e;
+    }
+    switch (pick_group(b, m)) {
+        case 1: return launch_bq<1>(b, n, m, thr, nsample, xyz1, xyz2, idx, pts_cnt, st);
+        case 2: return launch_bq<2>(b, n, m, thr, nsample, xyz1, xyz2, idx, pts_cnt, st);
+        case 4: return launch_bq<4>(b, n, m, thr, nsample, xyz1, xyz2, idx, pts_cnt, st);
+        case 8: return launch_bq<8>(b, n, m, thr, nsample, xyz1, xyz2, idx, pts_cnt, st);
+        case 16: return launch_bq<16>(b, n, m, thr, nsample, xyz1, xyz2, idx, pts_cnt, st);
+        default: return launch_bq<32>(b, n, m, thr, nsample, xyz1, xyz2, idx, pts_cnt, st);
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,553 @@
+// fps.cu — farthest point sampling for sm_100a.
+//
+// Replaces farthestpointsamplingKernel / farthestpointsamplingLauncher
+// (reference tf_ops/sampling/tf_sampling_g.cu:105-170, :203-205).
+//
+// Selection rule (bit-exact with the reference): start at index 0; every step the point whose
+// running minimum squared distance to the picked set is largest wins, ties resolved by
+// (k mod 512 ascending, then k ascending) — the order the reference's 512-thread strided scan
+// and lower-slot-wins tree produce.  Distances use the reference's contraction pattern
+// (pn2::d2_fma_pattern).
+//
+// Design (B200-first, not a translation):
+//   * the cloud's coordinates AND the running-minimum array live in REGISTERS (P points per
+//     thread); nothing is re-read from or written to global memory inside the M-step chain
+//     (the reference keeps the running minimum in global memory and re-reads points >= 3072
+//     from global every step, and burns 10 __syncthreads per step);
+//   * one step = P fused distance/min/compare updates per thread, two redux.sync warp
+//     reductions on a 64-bit (value, tie-break) key, one shared-memory hop and ONE barrier;
+//   * clouds too large for one CTA's register file are spread over a thread-block cluster
+//     (up to 16 CTAs); the per-step cross-CTA argmax is exchanged through distributed shared
+//     memory with st.async + mbarrier transaction counts (no cluster-wide barrier per step);
+//   * anything larger still falls back to a global-scratch kernel (the reference's layout).
+#include "pn2_common.cuh"
+
+namespace pn2 {
+
+// ---- 64-bit selection key --------------------------------------------------------------------
+// hi = float bits of the running minimum (non-negative, so unsigned order == float order)
+// lo = ~tb(k), tb(k) = (k mod 512) << 23 | (k / 512): larger lo == earlier in the tie-break order.
+__device__ __forceinline__ unsigned tb_encode(unsigned k) { return ((k & 511u) << 23) | (k >> 9); }
+__device__ __forceinline__ unsigned tb_decode(unsigned tb) { return ((tb & 0x7fffffu) << 9) | (tb >> 23); }
+
+// ---- PTX wrappers for the cluster exchange -----------------------------------------------------
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned cluster_nctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned mapa_shared(unsigned addr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_init(unsigned addr, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init_cluster() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned addr, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity_cluster(unsigned addr, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "PN2_WAIT:\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra PN2_DONE;\n\t"
+        "bra PN2_WAIT;\n\t"
+        "PN2_DONE:\n\t"
+        "}" ::"r"(addr),
+        "r"(parity)
+        : "memory");
+}
+// 8-byte store into a peer CTA's shared memory that also completes 8 tx-bytes on the peer's mbarrier.
+__device__ __forceinline__ void st_async_u64(unsigned remote_addr, unsigned long long v, unsigned remote_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr),
+                 "l"(v), "r"(remote_mbar)
+                 : "memory");
+}
+
+// ---- per-thread step: update P register-resident points against the last pick ------------------
+template <int P>
+__device__ __forceinline__ void fps_step(const float (&px)[P], const float (&py)[P], const float (&pz)[P],
+                                         float (&td)[P], float x1, float y1, float z1, float& best, int& bj) {
+    best = -1.0f;
+    bj = 0;
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const float d = d2_fma_pattern(px[j], py[j], pz[j], x1, y1, z1);
+        const float d2 = fminf(d, td[j]);  // padding slots carry td = -1 and can never win
+        td[j] = d2;
+        if (d2 > best) {
+            best = d2;
+            bj = j;
+        }
+    }
+}
+
+// =================================================================================================
+// One CTA per cloud.  Thread t owns points k = t + j*T (j < P): all of a thread's points share
+// the reference slot k mod 512 when T is a multiple of 512 (or P == 1), so the in-thread strict
+// '>' scan in ascending j reproduces the reference's in-slot order.
+// Dynamic shared memory: 3*n floats — a copy of the cloud, so the picked point's coordinates are a
+// 3-word broadcast LDS instead of a global/L2 round trip on the critical path.
+// =================================================================================================
+template <int P, int T>
+__global__ void __launch_bounds__(T, 1)
+fps_cta_kernel(int n, int m, const float* __restrict__ xyz, int* __restrict__ idx_out,
+               float* __restrict__ new_xyz) {
+    static_assert(P == 1 || T % 512 == 0, "slot order needs T % 512 == 0 when P > 1");
+    constexpr int NW = T / 32;
+    __shared__ uint2 s_keys[2][32];
+    extern __shared__ float s_xyz[];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cloud = blockIdx.x;
+    const float* __restrict__ pts = xyz + (size_t)cloud * n * 3;
+    int* __restrict__ out = idx_out + (size_t)cloud * m;
+    float* __restrict__ oxyz = new_xyz ? new_xyz + (size_t)cloud * m * 3 : nullptr;
+
+    for (int e = tid; e < 3 * n; e += T) s_xyz[e] = pts[e];
+    __syncthreads();
+    const float* __restrict__ src = s_xyz;
+
+    float px[P], py[P], pz[P], td[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const int k = tid + j * T;
+        if (k < n) {
+            px[j] = src[3 * k + 0];
+            py[j] = src[3 * k + 1];
+            pz[j] = src[3 * k + 2];
+            td[j] = 1e38f;
+        } else {
+            px[j] = py[j] = pz[j] = 0.0f;
+            td[j] = -1.0f;
+        }
+    }
+
+    float x1 = src[0], y1 = src[1], z1 = src[2];
+    if (tid == 0) {
+        out[0] = 0;
+        if (oxyz) {
+            oxyz[0] = x1;
+            oxyz[1] = y1;
+            oxyz[2] = z1;
+        }
+    }
+
+    for (int it = 1; it < m; ++it) {
+        float best;
+        int bj;
+        fps_step<P>(px, py, pz, td, x1, y1, z1, best, bj);
+        unsigned hi = 0u, lo = 0u;
+        if (best >= 0.0f) {
+            hi = __float_as_uint(best);
+            lo = ~tb_encode((unsigned)(tid + bj * T));
+        }
+        warp_max_pair(hi, lo);
+        const int buf = it & 1;
+        if (lane == 0) s_keys[buf][warp] = make_uint2(lo, hi);
+        __syncthreads();
+        uint2 e = (lane < NW) ? s_keys[buf][lane] : make_uint2(0u, 0u);
+        unsigned gh = e.y, gl = e.x;
+        warp_max_pair(gh, gl);
+        const int old = (int)tb_decode(~gl);
+        x1 = src[3 * old + 0];
+        y1 = src[3 * old + 1];
+        z1 = src[3 * old + 2];
+        if (tid == 0) {
+            out[it] = old;
+            if (oxyz) {
+                oxyz[3 * it + 0] = x1;
+                oxyz[3 * it + 1] = y1;
+                oxyz[3 * it + 2] = z1;
+            }
+        }
+    }
+}
+
+// =================================================================================================
+// One thread-block CLUSTER per cloud (C = 2..16 CTAs).  Thread t of CTA r owns points
+// k = t + T*(r + C*j): slot k mod 512 == t mod 512 again (T % 512 == 0).
+// Per step: CTA-local argmax as above, then warp 0 pushes the CTA's 8-byte key into slot r of
+// EVERY CTA's exchange buffer with st.async (which also completes 8 tx-bytes on that CTA's
+// mbarrier); all threads wait on their own CTA's mbarrier (expecting 8*C bytes), read the C keys
+// from local shared memory and reduce them.  Two buffers/mbarriers alternate by step parity.
+// XYZ_SMEM: coordinates are kept in shared memory instead of registers (only the running minimum
+// is register-resident) — for N/C too large for the register file.
+// =================================================================================================
+template <int P, int T, bool XYZ_SMEM>
+__global__ void __launch_bounds__(T, 1)
+fps_cluster_kernel(int n, int m, const float* __restrict__ xyz, int* __restrict__ idx_out,
+                   float* __restrict__ new_xyz) {
+    static_assert(T % 512 == 0, "slot order needs T % 512 == 0");
+    constexpr int NW = T / 32;
+    __shared__ uint2 s_keys[2][32];
+    __shared__ __align__(8) unsigned long long s_xkeys[2][16];
+    __shared__ __align__(8) unsigned long long s_mbar[2];
+    extern __shared__ float s_pts[];  // XYZ_SMEM: [3][P*T] SoA copy of this CTA's points
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned C = cluster_nctarank(), rank = cluster_ctarank();
+    const int cloud = blockIdx.x / C;
+    const float* __restrict__ pts = xyz + (size_t)cloud * n * 3;
+    int* __restrict__ out = idx_out + (size_t)cloud * m;
+    float* __restrict__ oxyz = new_xyz ? new_xyz + (size_t)cloud * m * 3 : nullptr;
+
+    if (tid == 0) {
+        mbar_init(smem_addr(&s_mbar[0]), 1);
+        mbar_init(smem_addr(&s_mbar[1]), 1);
+        fence_mbar_init_cluster();
+    }
+
+    float px[XYZ_SMEM ? 1 : P], py[XYZ_SMEM ? 1 : P], pz[XYZ_SMEM ? 1 : P], td[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const long long k = (long long)tid + (long long)T * (rank + (long long)C * j);
+        float x = 0.f, y = 0.f, z = 0.f, t = -1.0f;
+        if (k < n) {
+            x = pts[3 * k + 0];
+            y = pts[3 * k + 1];
+            z = pts[3 * k + 2];
+            t = 1e38f;
+        }
+        td[j] = t;
+        if constexpr (XYZ_SMEM) {
+            s_pts[0 * P * T + j * T + tid] = x;
+            s_pts[1 * P * T + j * T + tid] = y;
+            s_pts[2 * P * T + j * T + tid] = z;
+        } else {
+            px[j] = x;
+            py[j] = y;
+            pz[j] = z;
+        }
+    }
+
+    float x1 = pts[0], y1 = pts[1], z1 = pts[2];
+    if (rank == 0 && tid == 0) {
+        out[0] = 0;
+        if (oxyz) {
+            oxyz[0] = x1;
+            oxyz[1] = y1;
+            oxyz[2] = z1;
+        }
+    }
+    // every CTA's mbarriers must be initialised before any peer targets them
+    cluster_sync_all();
+
+    const unsigned mbar0 = smem_addr(&s_mbar[0]), mbar1 = smem_addr(&s_mbar[1]);
+
+    for (int it = 1; it < m; ++it) {
+        const int q = it - 1, buf = q & 1;
+        const unsigned parity = (unsigned)(q >> 1) & 1u;
+        const unsigned mbar = buf ? mbar1 : mbar0;
+        if (tid == 0) mbar_arrive_expect_tx(mbar, 8u * C);
+
+        float best = -1.0f;
+        int bj = 0;
+        if constexpr (XYZ_SMEM) {
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const float x = s_pts[0 * P * T + j * T + tid];
+                const float y = s_pts[1 * P * T + j * T + tid];
+                const float z = s_pts[2 * P * T + j * T + tid];
+                const float d = d2_fma_pattern(x, y, z, x1, y1, z1);
+                const float d2 = fminf(d, td[j]);
+                td[j] = d2;
+                if (d2 > best) {
+                    best = d2;
+                    bj = j;
+                }
+            }
+        } else {
+            fps_step<P>(px, py, pz, td, x1, y1, z1, best, bj);
+        }
+        unsigned hi = 0u, lo = 0u;
+        if (best >= 0.0f) {
+            hi = __float_as_uint(best);
+            lo = ~tb_encode((unsigned)(tid + T * (rank + C * bj)));
+        }
+        warp_max_pair(hi, lo);
+        if (lane == 0) s_keys[buf][warp] = make_uint2(lo, hi);
+        __syncthreads();
+        if (warp == 0) {
+            uint2 e = (lane < NW) ? s_keys[buf][lane] : make_uint2(0u, 0u);
+            unsigned ch = e.y, cl = e.x;
+            warp_max_pair(ch, cl);
+            if (lane < C) {
+                const unsigned long long key = ((unsigned long long)ch << 32) | cl;
+                st_async_u64(mapa_shared(smem_addr(&s_xkeys[buf][rank]), lane), key, mapa_shared(mbar, lane));
+            }
+        }
+        mbar_wait_parity_cluster(mbar, parity);
+        const unsigned long long xe = (lane < C) ? s_xkeys[buf][lane] : 0ull;
+        unsigned gh = (unsigned)(xe >> 32), gl = (unsigned)xe;
+        warp_max_pair(gh, gl);
+        const int old = (int)tb_decode(~gl);
+        x1 = __ldg(pts + 3 * (size_t)old + 0);
+        y1 = __ldg(pts + 3 * (size_t)old + 1);
+        z1 = __ldg(pts + 3 * (size_t)old + 2);
+        if (rank == 0 && tid == 0) {
+            out[it] = old;
+            if (oxyz) {
+                oxyz[3 * it + 0] = x1;
+                oxyz[3 * it + 1] = y1;
+                oxyz[3 * it + 2] = z1;
+            }
+        }
+    }
+    // no CTA may exit while a peer can still write into its shared memory
+    cluster_sync_all();
+}
+
+// =================================================================================================
+// Any-size fallback: running minimum in caller-provided global scratch (32*n floats, the
+// reference's own requirement, tf_sampling_g.cu:202), grid of <= 32 CTAs looping over clouds.
+// =================================================================================================
+template <int T>
+__global__ void __launch_bounds__(T, 1)
+fps_global_kernel(int b, int n, int m, const float* __restrict__ xyz, float* __restrict__ temp,
+                  int* __restrict__ idx_out, float* __restrict__ new_xyz) {
+    constexpr int NW = T / 32;
+    __shared__ uint2 s_keys[2][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* __restrict__ td = temp + (size_t)blockIdx.x * n;
+    for (int cloud = blockIdx.x; cloud < b; cloud += gridDim.x) {
+        const float* __restrict__ pts = xyz + (size_t)cloud * n * 3;
+        int* __restrict__ out = idx_out + (size_t)cloud * m;
+        float* __restrict__ oxyz = new_xyz ? new_xyz + (size_t)cloud * m * 3 : nullptr;
+        for (int k = tid; k < n; k += T) td[k] = 1e38f;
+        float x1 = pts[0], y1 = pts[1], z1 = pts[2];
+        if (tid == 0) {
+            out[0] = 0;
+            if (oxyz) {
+                oxyz[0] = x1;
+                oxyz[1] = y1;
+                oxyz[2] = z1;
+            }
+        }
+        __syncthreads();
+        for (int it = 1; it < m; ++it) {
+            float best = -1.0f;
+            int bk = 0;
+            for (int k = tid; k < n; k += T) {  // T % 512 == 0: one slot per thread, ascending k
+                const float d = d2_fma_pattern(pts[3 * (size_t)k], pts[3 * (size_t)k + 1], pts[3 * (size_t)k + 2], x1, y1, z1);
+                const float d2 = fminf(d, td[k]);
+                td[k] = d2;
+                if (d2 > best) {
+                    best = d2;
+                    bk = k;
+                }
+            }
+            unsigned hi = 0u, lo = 0u;
+            if (best >= 0.0f) {
+                hi = __float_as_uint(best);
+                lo = ~tb_encode((unsigned)bk);
+            }
+            warp_max_pair(hi, lo);
+            const int buf = it & 1;
+            if (lane == 0) s_keys[buf][warp] = make_uint2(lo, hi);
+            __syncthreads();
+            uint2 e = (lane < NW) ? s_keys[buf][lane] : make_uint2(0u, 0u);
+            unsigned gh = e.y, gl = e.x;
+            warp_max_pair(gh, gl);
+            const int old = (int)tb_decode(~gl);
+            x1 = pts[3 * (size_t)old + 0];
+            y1 = pts[3 * (size_t)old + 1];
+            z1 = pts[3 * (size_t)old + 2];
+            if (tid == 0) {
+                out[it] = old;
+                if (oxyz) {
+                    oxyz[3 * it + 0] = x1;
+                    oxyz[3 * it + 1] = y1;
+                    oxyz[3 * it + 2] = z1;
+                }
+            }
+        }
+        __syncthreads();  // td reused by the next cloud
+    }
+}
+
+// ---- host-side dispatch ------------------------------------------------------------------------
+static int g_cfg_threads = 0, g_cfg_ppt = 0, g_cfg_cluster = 0;  // pn2_set_fps_config override
+
+template <int P, int T>
+static int launch_cta(int b, int n, int m, const float* inp, int* out, float* new_xyz, cudaStream_t st) {
+    auto kern = fps_cta_kernel<P, T>;
+    size_t dyn = (size_t)n * 3 * sizeof(float);
+    if (dyn > 200 * 1024) return (int)cudaErrorInvalidValue;
+    if (dyn > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return (int)e;
+    }
+    kern<<<b, T, dyn, st>>>(n, m, inp, out, new_xyz);
+    return finish_launch();
+}
+
+template <int P, int T, bool XYZ_SMEM>
+static int launch_cluster(int C, int b, int n, int m, const float* inp, int* out, float* new_xyz, cudaStream_t st) {
+    auto kern = fps_cluster_kernel<P, T, XYZ_SMEM>;
+    size_t dyn = XYZ_SMEM ? (size_t)3 * P * T * sizeof(float) : 0;
+    cudaError_t e;
+    if (dyn > 48 * 1024) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (C > 8) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        if (e != cudaSuccess) return (int)e;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)b * C, 1, 1);
+    cfg.blockDim = dim3(T, 1, 1);
+    cfg.dynamicSmemBytes = dyn;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, n, m, inp, out, new_xyz);
+    count_launch();
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaGetLastError();
+}
+
+struct FpsPlan {
+    int threads, ppt, cluster;  // cluster == 0: global-scratch fallback; 1: single CTA
+    bool xyz_smem;
+};
+
+static int pow2_floor(int v) {
+    int p = 1;
+    while (p * 2 <= v) p *= 2;
+    return p;
+}
+
+static FpsPlan plan_fps(int b, int n) {
+    FpsPlan p{0, 0, 0, false};
+    if (g_cfg_threads > 0) {
+        p.threads = g_cfg_threads;
+        p.ppt = g_cfg_ppt;
+        p.cluster = g_cfg_cluster;
+        p.xyz_smem = (g_cfg_ppt >= 32);
+        return p;
+    }
+    // single CTA: everything register-resident in one SM
+    if (n <= 128) return {128, 1, 1, false};
+    if (n <= 256) return {256, 1, 1, false};
+    if (n <= 512) return {512, 1, 1, false};
+    if (n <= 1024) return {512, 2, 1, false};
+    if (n <= 2048) return {512, 4, 1, false};
+    if (n <= 4096) return {1024, 4, 1, false};
+    if (n <= 8192 && b >= 64) return {1024, 8, 1, false};
+    // cluster: as many CTAs per cloud as keeps all clouds co-resident on the 148 SMs
+    int cmax = pow2_floor(148 / (b > 148 ? 148 : b));
+    if (cmax > 16) cmax = 16;
+    if (cmax < 2) cmax = 2;
+    for (int C = cmax; C >= 2; C /= 2) {
+        long long per = ((long long)n + C - 1) / C;  // points per CTA
+        if (per < 512 && C > 2) continue;            // too thin: fewer CTAs
+        if (per <= 512 * 1) return {512, 1, C, false};
+        if (per <= 512 * 2) return {512, 2, C, false};
+        if (per <= 512 * 4) return {512, 4, C, false};
+        if (per <= 512 * 8) return {512, 8, C, false};
+        if (per <= 512 * 16) return {512, 16, C, false};
+        if (per <= 512 * 32 && C == cmax) return {512, 32, C, true};
+        break;
+    }
+    // widest cluster regardless of co-residency
+    {
+        long long per = ((long long)n + 15) / 16;
+        if (per <= 512 * 16) {
+            int ppt = per <= 512 ? 1 : per <= 1024 ? 2 : per <= 2048 ? 4 : per <= 4096 ? 8 : 16;
+            return {512, ppt, 16, false};
+        }
+        if (per <= 512 * 32) return {512, 32, 16, true};
+    }
+    return {1024, 0, 0, false};
+}
+
+#define PN2_TRY_CTA(PP, TT) \
+    if (plan.ppt == PP && plan.threads == TT) return launch_cta<PP, TT>(b, n, m, inp, out, new_xyz, st);
+#define PN2_TRY_CLU(PP, TT, XS) \
+    if (plan.ppt == PP && plan.threads == TT && plan.xyz_smem == XS) \
+        return launch_cluster<PP, TT, XS>(plan.cluster, b, n, m, inp, out, new_xyz, st);
+
+static int fps_dispatch(int b, int n, int m, const float* inp, float* temp, int* out, float* new_xyz, cudaStream_t st) {
+    if (b < 0 || n <= 0 || m < 0) return (int)cudaErrorInvalidValue;
+    if (b == 0 || m == 0) return 0;
+    if (!inp || !out) return (int)cudaErrorInvalidValue;
+    FpsPlan plan = plan_fps(b, n);
+    if (plan.cluster >= 1) {
+        long long cap = (long long)plan.threads * plan.ppt * plan.cluster;
+        if (cap < n) return (int)cudaErrorInvalidValue;
+    }
+    if (plan.cluster == 1) {
+        PN2_TRY_CTA(1, 128)
+        PN2_TRY_CTA(1, 256)
+        PN2_TRY_CTA(1, 512)
+        PN2_TRY_CTA(2, 512)
+        PN2_TRY_CTA(4, 512)
+        PN2_TRY_CTA(8, 512)
+        PN2_TRY_CTA(16, 512)
+        PN2_TRY_CTA(1, 1024)
+        PN2_TRY_CTA(2, 1024)
+        PN2_TRY_CTA(4, 1024)
+        PN2_TRY_CTA(8, 1024)
+        return (int)cudaErrorInvalidValue;
+    }
+    if (plan.cluster >= 2) {
+        if (plan.cluster > 16 || (plan.cluster & (plan.cluster - 1))) return (int)cudaErrorInvalidValue;
+        PN2_TRY_CLU(1, 512, false)
+        PN2_TRY_CLU(2, 512, false)
+        PN2_TRY_CLU(4, 512, false)
+        PN2_TRY_CLU(8, 512, false)
+        PN2_TRY_CLU(16, 512, false)
+        PN2_TRY_CLU(32, 512, true)
+        PN2_TRY_CLU(2, 1024, false)
+        PN2_TRY_CLU(4, 1024, false)
+        PN2_TRY_CLU(8, 1024, false)
+        return (int)cudaErrorInvalidValue;
+    }
+    // global-scratch fallback
+    if (!temp) return (int)cudaErrorInvalidValue;
+    int grid = b < 32 ? b : 32;
+    fps_global_kernel<1024><<<grid, 1024, 0, st>>>(b, n, m, inp, temp, out, new_xyz);
+    return finish_launch();
+}
+
+}  // namespace pn2
+
+extern "C" {
+
+int pn2_fps(int b, int n, int m, const float* inp, float* temp, int* out, void* stream) {
+    return pn2::fps_dispatch(b, n, m, inp, temp, out, nullptr, pn2::as_stream(stream));
+}
+
+int pn2_fps_gather(int b, int n, int m, const float* inp, int* out, float* new_xyz, void* stream) {
+    return pn2::fps_dispatch(b, n, m, inp, nullptr, out, new_xyz, pn2::as_stream(stream));
+}
+
+void pn2_set_fps_config(int threads, int points_per_thread, int cluster) {
+    pn2::g_cfg_threads = threads;
+    pn2::g_cfg_ppt = points_per_thread;
+    pn2::g_cfg_cluster = cluster;
+}
+
+}  // extern "C"

@@ -1,0 +1,56 @@
+// pn2_common.cuh — shared device/host helpers for libpn2_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pn2_api.h"
+
+namespace pn2 {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// ---- launch accounting (pn2_launch_count) --------------------------------------------------
+extern unsigned long long g_launch_count;
+inline void count_launch(int k = 1) { __atomic_fetch_add(&g_launch_count, (unsigned long long)k, __ATOMIC_RELAXED); }
+
+inline int finish_launch() {
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline unsigned ceil_div_u(unsigned long long a, unsigned long long b) { return (unsigned)((a + b - 1) / b); }
+
+// ---- arithmetic contracts --------------------------------------------------------------------
+// Squared distance exactly as nvcc contracts the reference's FPS and ball-query source
+// (tf_sampling_g.cu:142, tf_grouping_g.cu:24; SASS: FMUL dy*dy, FFMA dx, FFMA dz).  Written with
+// explicit round-to-nearest intrinsics so no compiler version or surrounding code can change it.
+__device__ __forceinline__ float d2_fma_pattern(float ax, float ay, float az, float bx, float by, float bz) {
+    const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+// Squared distance exactly as x86-64 g++ -O2 (no FMA) evaluates threenn_cpu's expression
+// (tf_interpolate.cpp:73): ((dx*dx + dy*dy) + dz*dz), each operation rounded on its own.
+__device__ __forceinline__ float d2_nofma(float ax, float ay, float az, float bx, float by, float bz) {
+    const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// ---- warp helpers ----------------------------------------------------------------------------
+__device__ __forceinline__ unsigned warp_max_u32(unsigned v) { return __reduce_max_sync(kFullMask, v); }
+
+// Lexicographic max of (hi, lo) pairs over the warp; every lane gets the result.
+__device__ __forceinline__ void warp_max_pair(unsigned& hi, unsigned& lo) {
+    const unsigned mh = warp_max_u32(hi);
+    const unsigned ml = warp_max_u32(hi == mh ? lo : 0u);
+    hi = mh;
+    lo = ml;
+}
+
+// ---- streaming memory ops ---------------------------------------------------------------------
+__device__ __forceinline__ void st_stream_f4(float4* p, float4 v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream_i4(int4* p, int4 v) { __stcs(p, v); }
+
+}  // namespace pn2

@@ -1,0 +1,249 @@
+"""PointNet++ layer glue — the torch twin of the reference's utils/pointnet_util.py for the
+set-abstraction / feature-propagation geometry path.
+
+``sample_and_group`` / ``sample_and_group_all`` keep the reference's signatures and return tuples
+(utils/pointnet_util.py:22-56, :59-84).  ``pointnet_sa_module``, ``pointnet_sa_module_msg`` and
+``pointnet_fp_module`` keep the reference's argument names for the sampling/grouping/interpolation
+half; the dense half (1x1 conv + BN + ReLU stacks, :115-153, :187-195, :218-228) is cuDNN/cuBLAS
+territory and outside this path: pass an ``mlp`` callable (e.g. a torch.nn.Sequential of
+Conv2d(1x1)+BatchNorm2d+ReLU on a channels-last view) or leave it None to get the grouped tensor
+pooled as-is.
+
+``fused=True`` (default) routes through the fused kernels (FPS+gather in one launch,
+group+centre+concat in one pass); ``fused=False`` issues the reference's exact op sequence.  Both
+produce identical values.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._tensor import on_device, ptr, require_cuda, same_device, stream_ptr
+from .tf_grouping import group_point, knn_point, query_ball_point
+from .tf_interpolate import three_interpolate, three_nn, three_nn_interpolate
+from .tf_sampling import farthest_point_sample, farthest_point_sample_and_gather, gather_point
+
+
+class _GroupConcat(torch.autograd.Function):
+    """out = concat(xyz[idx]-new_xyz, points[idx]) in either channel order, plus grouped_xyz."""
+
+    @staticmethod
+    def forward(ctx, xyz, new_xyz, points, idx, xyz_first):
+        b, n, _ = xyz.shape
+        _, m, s = idx.shape
+        c = 0 if points is None else points.shape[2]
+        out = torch.empty((b, m, s, 3 + c), dtype=torch.float32, device=xyz.device)
+        gxyz = torch.empty((b, m, s, 3), dtype=torch.float32, device=xyz.device)
+        if out.numel():
+            with on_device(xyz):
+                rc = _lib.load().pn2_group_concat(b, n, c, m, s, ptr(xyz), ptr(new_xyz), ptr(points), ptr(idx),
+                                                  1 if xyz_first else 0, ptr(out), ptr(gxyz), stream_ptr(xyz.device))
+            _lib.check(rc, "pn2_group_concat")
+        ctx.save_for_backward(idx)
+        ctx.meta = (b, n, c, m, s, bool(xyz_first), points is not None)
+        return out, gxyz
+
+    @staticmethod
+    def backward(ctx, g_out, g_gxyz):
+        (idx,) = ctx.saved_tensors
+        b, n, c, m, s, xyz_first, has_points = ctx.meta
+        lib = _lib.load()
+        dev = g_out.device
+        lo = 0 if xyz_first else c
+        g_xyz_part = g_out[..., lo:lo + 3]
+        if g_gxyz is not None:
+            g_xyz_part = g_xyz_part + g_gxyz
+        g_xyz_part = g_xyz_part.contiguous()
+        g_xyz = torch.zeros((b, n, 3), dtype=torch.float32, device=dev)
+        g_points = None
+        with on_device(g_out):
+            st = stream_ptr(dev)
+            _lib.check(lib.pn2_group_point_grad(b, n, 3, m, s, ptr(g_xyz_part), ptr(idx), ptr(g_xyz), st),
+                       "pn2_group_point_grad")
+            if has_points:
+                g_feat = (g_out[..., 3:] if xyz_first else g_out[..., :c]).contiguous()
+                g_points = torch.zeros((b, n, c), dtype=torch.float32, device=dev)
+                _lib.check(lib.pn2_group_point_grad(b, n, c, m, s, ptr(g_feat), ptr(idx), ptr(g_points), st),
+                           "pn2_group_point_grad")
+        g_new_xyz = -g_xyz_part.sum(dim=2)
+        return g_xyz, g_new_xyz, g_points, None, None
+
+
+def group_and_concat(xyz, new_xyz, points, idx, xyz_first: bool = True):
+    """Fused tail of sample_and_group: returns (new_points (b,m,s,3+c), grouped_xyz (b,m,s,3))."""
+    xyz = require_cuda(xyz, "xyz", torch.float32)
+    new_xyz = require_cuda(new_xyz, "new_xyz", torch.float32)
+    idx = require_cuda(idx, "idx", torch.int32)
+    if points is not None:
+        points = require_cuda(points, "points", torch.float32)
+        same_device(xyz, new_xyz, idx, points)
+        if points.dim() != 3 or points.shape[:2] != xyz.shape[:2]:
+            raise ValueError("points must be (batch_size, ndataset, channel) matching xyz")
+    else:
+        same_device(xyz, new_xyz, idx)
+    if idx.dim() != 3 or idx.shape[0] != xyz.shape[0] or new_xyz.shape[:2] != idx.shape[:2]:
+        raise ValueError("idx must be (batch_size, npoint, nsample) matching new_xyz")
+    return _GroupConcat.apply(xyz, new_xyz, points, idx, xyz_first)
+
+
+def sample_and_group(npoint, radius, nsample, xyz, points, knn=False, use_xyz=True, fused=True):
+    '''
+    Input:
+        npoint: int32
+        radius: float32
+        nsample: int32
+        xyz: (batch_size, ndataset, 3) tensor
+        points: (batch_size, ndataset, channel) tensor, if None will just use xyz as points
+        knn: bool, if True use kNN instead of radius search
+        use_xyz: bool, if True concat XYZ with local point features, otherwise just use point features
+    Output:
+        new_xyz: (batch_size, npoint, 3) tensor
+        new_points: (batch_size, npoint, nsample, 3+channel) tensor
+        idx: (batch_size, npoint, nsample) tensor, indices of local points as in ndataset points
+        grouped_xyz: (batch_size, npoint, nsample, 3) tensor, normalized point XYZs
+            (subtracted by seed point XYZ) in local regions
+    Reference: utils/pointnet_util.py:22-56.
+    '''
+    if fused and not xyz.requires_grad:
+        _, new_xyz = farthest_point_sample_and_gather(npoint, xyz)
+    else:
+        new_xyz = gather_point(xyz, farthest_point_sample(npoint, xyz))  # (batch_size, npoint, 3)
+    if knn:
+        _, idx = knn_point(nsample, xyz, new_xyz)
+    else:
+        idx, pts_cnt = query_ball_point(radius, nsample, xyz, new_xyz)
+    if fused:
+        feats = points if (points is not None and use_xyz) else None
+        if points is not None and not use_xyz:
+            grouped_xyz = group_point(xyz, idx) - new_xyz.unsqueeze(2)
+            return new_xyz, group_point(points, idx), idx, grouped_xyz
+        new_points, grouped_xyz = group_and_concat(xyz, new_xyz, feats, idx, xyz_first=True)
+        return new_xyz, new_points, idx, grouped_xyz
+    grouped_xyz = group_point(xyz, idx)  # (batch_size, npoint, nsample, 3)
+    grouped_xyz = grouped_xyz - new_xyz.unsqueeze(2)  # translation normalization (tile+sub, :46)
+    if points is not None:
+        grouped_points = group_point(points, idx)  # (batch_size, npoint, nsample, channel)
+        if use_xyz:
+            new_points = torch.cat([grouped_xyz, grouped_points], dim=-1)  # (:50) xyz first
+        else:
+            new_points = grouped_points
+    else:
+        new_points = grouped_xyz
+    return new_xyz, new_points, idx, grouped_xyz
+
+
+def sample_and_group_all(xyz, points, use_xyz=True):
+    '''
+    Inputs:
+        xyz: (batch_size, ndataset, 3) tensor
+        points: (batch_size, ndataset, channel) tensor, if None will just use xyz as points
+        use_xyz: bool, if True concat XYZ with local point features, otherwise just use point features
+    Outputs:
+        new_xyz: (batch_size, 1, 3) as (0,0,0)
+        new_points: (batch_size, 1, ndataset, 3+channel) tensor
+    Note:
+        Equivalent to sample_and_group with npoint=1, radius=inf, use (0,0,0) as the centroid
+    Reference: utils/pointnet_util.py:59-84 (no kernels: zeros, arange, reshape, concat).
+    '''
+    batch_size, nsample = xyz.shape[0], xyz.shape[1]
+    new_xyz = torch.zeros((batch_size, 1, 3), dtype=torch.float32, device=xyz.device)
+    idx = torch.arange(nsample, dtype=torch.int32, device=xyz.device).reshape(1, 1, nsample).repeat(batch_size, 1, 1)
+    grouped_xyz = xyz.reshape(batch_size, 1, nsample, 3)
+    if points is not None:
+        if use_xyz:
+            new_points = torch.cat([xyz, points], dim=2)
+        else:
+            new_points = points
+        new_points = new_points.unsqueeze(1)
+    else:
+        new_points = grouped_xyz
+    return new_xyz, new_points, idx, grouped_xyz
+
+
+def _apply_mlp(mlp: Optional[Callable], t: torch.Tensor) -> torch.Tensor:
+    return t if mlp is None else mlp(t)
+
+
+def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp: Optional[Callable] = None,
+                       mlp2: Optional[Callable] = None, group_all=False, pooling='max', knn=False, use_xyz=True,
+                       fused=True):
+    ''' PointNet Set Abstraction (SA) Module — reference utils/pointnet_util.py:87-154.
+        mlp / mlp2 are callables on a (batch, npoint, nsample, channel) tensor (the reference's
+        1x1-conv stacks); None leaves the features untouched.
+        Return: new_xyz (b,npoint,3), new_points (b,npoint,channels), idx (b,npoint,nsample)
+    '''
+    if group_all:
+        new_xyz, new_points, idx, grouped_xyz = sample_and_group_all(xyz, points, use_xyz)
+    else:
+        new_xyz, new_points, idx, grouped_xyz = sample_and_group(npoint, radius, nsample, xyz, points, knn, use_xyz,
+                                                                 fused=fused)
+    new_points = _apply_mlp(mlp, new_points)
+    if pooling == 'max':
+        new_points = new_points.max(dim=2, keepdim=True).values
+    elif pooling == 'avg':
+        new_points = new_points.mean(dim=2, keepdim=True)
+    elif pooling == 'weighted_avg':
+        dists = torch.linalg.vector_norm(grouped_xyz, ord=2, dim=-1, keepdim=True)
+        exp_dists = torch.exp(-dists * 5)
+        weights = exp_dists / exp_dists.sum(dim=2, keepdim=True)
+        new_points = (new_points * weights).sum(dim=2, keepdim=True)
+    elif pooling == 'max_and_avg':
+        new_points = torch.cat([new_points.mean(dim=2, keepdim=True), new_points.max(dim=2, keepdim=True).values], dim=-1)
+    else:
+        raise ValueError(f"unknown pooling {pooling!r}")
+    new_points = _apply_mlp(mlp2, new_points)
+    return new_xyz, new_points.squeeze(2), idx
+
+
+def pointnet_sa_module_msg(xyz, points, npoint, radius_list: Sequence[float], nsample_list: Sequence[int],
+                           mlp_list: Optional[Sequence[Optional[Callable]]] = None, use_xyz=True, fused=True):
+    ''' PointNet Set Abstraction (SA) module with Multi-Scale Grouping — reference
+        utils/pointnet_util.py:156-196.  One FPS+gather, then per scale: ball query, group,
+        centre, concat in the MSG order [features, xyz] (:184), MLP, max-pool; scales concatenated.
+        Return: new_xyz (b,npoint,3), new_points (b,npoint,sum of channels)
+    '''
+    if fused and not xyz.requires_grad:
+        _, new_xyz = farthest_point_sample_and_gather(npoint, xyz)
+    else:
+        new_xyz = gather_point(xyz, farthest_point_sample(npoint, xyz))
+    new_points_list = []
+    for i in range(len(radius_list)):
+        radius, nsample = radius_list[i], nsample_list[i]
+        idx, pts_cnt = query_ball_point(radius, nsample, xyz, new_xyz)
+        if fused and (points is None or use_xyz):
+            grouped_points, _ = group_and_concat(xyz, new_xyz, points, idx, xyz_first=False)
+        else:
+            grouped_xyz = group_point(xyz, idx) - new_xyz.unsqueeze(2)
+            if points is not None:
+                grouped_points = group_point(points, idx)
+                if use_xyz:
+                    grouped_points = torch.cat([grouped_points, grouped_xyz], dim=-1)
+            else:
+                grouped_points = grouped_xyz
+        grouped_points = _apply_mlp(None if mlp_list is None else mlp_list[i], grouped_points)
+        new_points_list.append(grouped_points.max(dim=2).values)
+    return new_xyz, torch.cat(new_points_list, dim=-1)
+
+
+def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp: Optional[Callable] = None, fused=True):
+    ''' PointNet Feature Propogation (FP) Module — reference utils/pointnet_util.py:199-229.
+        xyz1 (b,n1,3) dense, xyz2 (b,n2,3) sparser, points1 (b,n1,c1) or None, points2 (b,n2,c2).
+        Return: new_points (b,n1,mlp[-1]) (or (b,n1,c2+c1) when mlp is None)
+    '''
+    if fused and not points2.requires_grad:
+        interpolated_points = three_nn_interpolate(xyz1, xyz2, points2)
+    else:
+        dist, idx = three_nn(xyz1, xyz2)
+        dist = torch.clamp(dist, min=1e-10)
+        norm = (1.0 / dist).sum(dim=2, keepdim=True)
+        weight = (1.0 / dist) / norm
+        interpolated_points = three_interpolate(points2, idx, weight)
+    if points1 is not None:
+        new_points1 = torch.cat([interpolated_points, points1], dim=2)  # B,ndataset1,nchannel1+nchannel2
+    else:
+        new_points1 = interpolated_points
+    if mlp is not None:
+        new_points1 = mlp(new_points1.unsqueeze(2)).squeeze(2)
+    return new_points1

@@ -1,0 +1,156 @@
+"""Grouping ops — drop-in for the reference's tf_ops/grouping/tf_grouping.py.
+
+Same function names, positional order and return tuples as tf_grouping.py:8-73 on contiguous CUDA
+torch tensors.  group_point is differentiable w.r.t. ``points`` (tf_grouping.py:42-46);
+query_ball_point / select_top_k have no gradient (ops.NoGradient, :21,:32).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._tensor import on_device, ptr, require_cuda, same_device, stream_ptr
+
+
+def query_ball_point(radius: float, nsample: int, xyz1: torch.Tensor, xyz2: torch.Tensor):
+    """
+    Input:
+        radius: float32, ball search radius
+        nsample: int32, number of points selected in each ball region
+        xyz1: (batch_size, ndataset, 3) float32 array, input points
+        xyz2: (batch_size, npoint, 3) float32 array, query points
+    Output:
+        idx: (batch_size, npoint, nsample) int32 array, indices to input points
+        pts_cnt: (batch_size, npoint) int32 array, number of unique points in each local region
+    Reference: tf_grouping.py:8-20 -> QueryBallPointGpuOp (tf_grouping.cpp:67-106) ->
+    query_ball_point_gpu (tf_grouping_g.cu:3-36).  Rows with no point in the ball (undefined in the
+    reference) come back as zeros with pts_cnt 0.
+    """
+    radius = float(radius)
+    nsample = int(nsample)
+    if not radius > 0:
+        raise ValueError("QueryBallPoint expects positive radius")
+    if nsample <= 0:
+        raise ValueError("QueryBallPoint expects positive nsample")
+    xyz1 = require_cuda(xyz1, "xyz1", torch.float32)
+    xyz2 = require_cuda(xyz2, "xyz2", torch.float32)
+    same_device(xyz1, xyz2)
+    if xyz1.dim() != 3 or xyz1.shape[2] != 3:
+        raise ValueError(f"QueryBallPoint expects (batch_size, ndataset, 3) xyz1 shape, got {tuple(xyz1.shape)}")
+    if xyz2.dim() != 3 or xyz2.shape[2] != 3 or xyz2.shape[0] != xyz1.shape[0]:
+        raise ValueError(f"QueryBallPoint expects (batch_size, npoint, 3) xyz2 shape, got {tuple(xyz2.shape)}")
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    if n <= 0 and b * m:
+        raise ValueError("QueryBallPoint expects a non-empty xyz1")
+    idx = torch.empty((b, m, nsample), dtype=torch.int32, device=xyz1.device)
+    pts_cnt = torch.empty((b, m), dtype=torch.int32, device=xyz1.device)
+    if b * m:
+        with on_device(xyz1):
+            rc = _lib.load().pn2_query_ball_point(b, n, m, radius, nsample, ptr(xyz1), ptr(xyz2), ptr(idx),
+                                                  ptr(pts_cnt), stream_ptr(xyz1.device))
+        _lib.check(rc, "pn2_query_ball_point")
+    return idx, pts_cnt
+
+
+def select_top_k(k: int, dist: torch.Tensor):
+    """
+    Input:
+        k: int32, number of k SMALLEST elements selected
+        dist: (b,m,n) float32 array, distance matrix, m query points, n dataset points
+    Output:
+        idx: (b,m,n) int32 array, first k in n are indices to the top k
+        dist_out: (b,m,n) float32 array, first k in n are the top k
+    Reference: tf_grouping.py:22-31 -> SelectionSortGpuOp (tf_grouping.cpp:110-139) ->
+    selection_sort_gpu (tf_grouping_g.cu:83-123).
+    """
+    k = int(k)
+    if k <= 0:
+        raise ValueError("SelectionSort expects positive k")
+    dist = require_cuda(dist, "dist", torch.float32)
+    if dist.dim() != 3:
+        raise ValueError(f"SelectionSort expects (b,m,n) dist shape, got {tuple(dist.shape)}")
+    b, m, n = dist.shape
+    outi = torch.empty((b, m, n), dtype=torch.int32, device=dist.device)
+    out = torch.empty((b, m, n), dtype=torch.float32, device=dist.device)
+    if b * m * n:
+        with on_device(dist):
+            rc = _lib.load().pn2_selection_sort(b, n, m, k, ptr(dist), ptr(outi), ptr(out), stream_ptr(dist.device))
+        _lib.check(rc, "pn2_selection_sort")
+    return outi, out
+
+
+class _GroupPoint(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, idx):
+        b, n, c = points.shape
+        _, m, s = idx.shape
+        out = torch.empty((b, m, s, c), dtype=torch.float32, device=points.device)
+        if out.numel():
+            with on_device(points):
+                rc = _lib.load().pn2_group_point(b, n, c, m, s, ptr(points), ptr(idx), ptr(out),
+                                                 stream_ptr(points.device))
+            _lib.check(rc, "pn2_group_point")
+        ctx.save_for_backward(idx)
+        ctx.shape = (b, n, c)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (idx,) = ctx.saved_tensors
+        b, n, c = ctx.shape
+        _, m, s = idx.shape
+        grad_out = grad_out.contiguous()
+        # zero-filled by the caller, as GroupPointGradGpuOp does (tf_grouping.cpp:204)
+        grad_points = torch.zeros((b, n, c), dtype=torch.float32, device=grad_out.device)
+        if grad_out.numel():
+            with on_device(grad_out):
+                rc = _lib.load().pn2_group_point_grad(b, n, c, m, s, ptr(grad_out), ptr(idx), ptr(grad_points),
+                                                      stream_ptr(grad_out.device))
+            _lib.check(rc, "pn2_group_point_grad")
+        return grad_points, None
+
+
+def group_point(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """
+    Input:
+        points: (batch_size, ndataset, channel) float32 array, points to sample from
+        idx: (batch_size, npoint, nsample) int32 array, indices to points
+    Output:
+        out: (batch_size, npoint, nsample, channel) float32 array, values sampled from points
+    Reference: tf_grouping.py:33-41 -> group_point_gpu (tf_grouping_g.cu:40-57); gradient
+    tf_grouping.py:42-46 -> group_point_grad_gpu (:61-78).
+    """
+    points = require_cuda(points, "points", torch.float32)
+    idx = require_cuda(idx, "idx", torch.int32)
+    same_device(points, idx)
+    if points.dim() != 3:
+        raise ValueError(f"GroupPoint expects (batch_size, num_points, channel) points shape, got {tuple(points.shape)}")
+    if idx.dim() != 3 or idx.shape[0] != points.shape[0]:
+        raise ValueError(f"GroupPoint expects (batch_size, npoints, nsample) idx shape, got {tuple(idx.shape)}")
+    if points.shape[1] <= 0 and idx.numel():
+        raise ValueError("GroupPoint expects a non-empty points tensor")
+    return _GroupPoint.apply(points, idx)
+
+
+def knn_point(k: int, xyz1: torch.Tensor, xyz2: torch.Tensor):
+    """
+    Input:
+        k: int32, number of k in k-nn search
+        xyz1: (batch_size, ndataset, c) float32 array, input points
+        xyz2: (batch_size, npoint, c) float32 array, query points
+    Output:
+        val: (batch_size, npoint, k) float32 array, L2 distances
+        idx: (batch_size, npoint, k) int32 array, indices to input points
+    Reference: tf_grouping.py:48-73 — the same composite: pairwise squared distances
+    sum((xyz1 - xyz2)**2, -1) as an (b,m,n) matrix, select_top_k, slice the first k columns.
+    """
+    xyz1 = require_cuda(xyz1, "xyz1", torch.float32)
+    xyz2 = require_cuda(xyz2, "xyz2", torch.float32)
+    same_device(xyz1, xyz2)
+    if xyz1.dim() != 3 or xyz2.dim() != 3 or xyz1.shape[0] != xyz2.shape[0] or xyz1.shape[2] != xyz2.shape[2]:
+        raise ValueError("knn_point expects (b,n,c) xyz1 and (b,m,c) xyz2")
+    diff = xyz1.unsqueeze(1) - xyz2.unsqueeze(2)  # (b,m,n,c): tile(xyz1) - tile(xyz2), tf_grouping.py:64-66
+    dist = (diff * diff).sum(-1)
+    outi, out = select_top_k(k, dist)
+    return out[:, :, :k].contiguous(), outi[:, :, :k].contiguous()

@@ -1,0 +1,134 @@
+"""Interpolation ops — drop-in for the reference's tf_ops/3d_interpolation/tf_interpolate.py.
+
+Same names, argument order and returns as tf_interpolate.py:8-34, on contiguous CUDA torch
+tensors.  The reference only has CPU kernels for these (tf_interpolate.cpp:187,222,262), so
+TensorFlow bounces the tensors through host memory; here they run on the device.
+three_interpolate is differentiable w.r.t. ``points`` only (tf_interpolate.py:29-34); three_nn has
+no gradient (:18).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._tensor import on_device, ptr, require_cuda, same_device, stream_ptr
+
+
+def three_nn(xyz1: torch.Tensor, xyz2: torch.Tensor):
+    """
+    Input:
+        xyz1: (b,n,3) float32 array, unknown points
+        xyz2: (b,m,3) float32 array, known points
+    Output:
+        dist: (b,n,3) float32 array, distances to known points   [SQUARED, ascending]
+        idx: (b,n,3) int32 array, indices to known points
+    Reference: tf_interpolate.py:8-17 -> ThreeNNOp (tf_interpolate.cpp:157-187) -> threenn_cpu (:60-103).
+    """
+    xyz1 = require_cuda(xyz1, "xyz1", torch.float32)
+    xyz2 = require_cuda(xyz2, "xyz2", torch.float32)
+    same_device(xyz1, xyz2)
+    if xyz1.dim() != 3 or xyz1.shape[2] != 3:
+        raise ValueError(f"ThreeNN expects (b,n,3) xyz1 shape, got {tuple(xyz1.shape)}")
+    if xyz2.dim() != 3 or xyz2.shape[2] != 3 or xyz2.shape[0] != xyz1.shape[0]:
+        raise ValueError(f"ThreeNN expects (b,m,3) xyz2 shape, got {tuple(xyz2.shape)}")
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    dist = torch.empty((b, n, 3), dtype=torch.float32, device=xyz1.device)
+    idx = torch.empty((b, n, 3), dtype=torch.int32, device=xyz1.device)
+    if b * n:
+        with on_device(xyz1):
+            rc = _lib.load().pn2_three_nn(b, n, m, ptr(xyz1), ptr(xyz2), ptr(dist), ptr(idx), stream_ptr(xyz1.device))
+        _lib.check(rc, "pn2_three_nn")
+    return dist, idx
+
+
+class _ThreeInterpolate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, points, idx, weight):
+        b, m, c = points.shape
+        n = idx.shape[1]
+        out = torch.empty((b, n, c), dtype=torch.float32, device=points.device)
+        if out.numel():
+            with on_device(points):
+                rc = _lib.load().pn2_three_interpolate(b, m, c, n, ptr(points), ptr(idx), ptr(weight), ptr(out),
+                                                       stream_ptr(points.device))
+            _lib.check(rc, "pn2_three_interpolate")
+        ctx.save_for_backward(idx, weight)
+        ctx.shape = (b, m, c)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        idx, weight = ctx.saved_tensors
+        b, m, c = ctx.shape
+        n = idx.shape[1]
+        grad_out = grad_out.contiguous()
+        # zero-filled by the caller, as ThreeInterpolateGradOp does (tf_interpolate.cpp:258)
+        grad_points = torch.zeros((b, m, c), dtype=torch.float32, device=grad_out.device)
+        if grad_out.numel():
+            with on_device(grad_out):
+                rc = _lib.load().pn2_three_interpolate_grad(b, n, c, m, ptr(grad_out), ptr(idx), ptr(weight),
+                                                            ptr(grad_points), stream_ptr(grad_out.device))
+            _lib.check(rc, "pn2_three_interpolate_grad")
+        return grad_points, None, None
+
+
+def three_interpolate(points: torch.Tensor, idx: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """
+    Input:
+        points: (b,m,c) float32 array, known points
+        idx: (b,n,3) int32 array, indices to known points
+        weight: (b,n,3) float32 array, weights on known points
+    Output:
+        out: (b,n,c) float32 array, interpolated point values
+    Reference: tf_interpolate.py:19-28 -> threeinterpolate_cpu (tf_interpolate.cpp:107-127);
+    gradient :29-34 -> threeinterpolate_grad_cpu (:131-153).
+    """
+    points = require_cuda(points, "points", torch.float32)
+    idx = require_cuda(idx, "idx", torch.int32)
+    weight = require_cuda(weight, "weight", torch.float32)
+    same_device(points, idx, weight)
+    if points.dim() != 3:
+        raise ValueError(f"ThreeInterpolate expects (b,m,c) points shape, got {tuple(points.shape)}")
+    b = points.shape[0]
+    if idx.dim() != 3 or idx.shape[0] != b or idx.shape[2] != 3:
+        raise ValueError(f"ThreeInterpolate expects (b,n,3) idx shape, got {tuple(idx.shape)}")
+    if weight.dim() != 3 or tuple(weight.shape) != tuple(idx.shape):
+        raise ValueError(f"ThreeInterpolate expects (b,n,3) weight shape, got {tuple(weight.shape)}")
+    if points.shape[1] <= 0 and idx.numel():
+        raise ValueError("ThreeInterpolate expects a non-empty points tensor")
+    return _ThreeInterpolate.apply(points, idx, weight.detach())
+
+
+def three_nn_interpolate(xyz1: torch.Tensor, xyz2: torch.Tensor, points2: torch.Tensor, return_aux: bool = False):
+    """Fused feature-propagation front end (utils/pointnet_util.py:211-216): three_nn, the
+    inverse-distance weights (dist=max(dist,1e-10); w=(1/dist)/sum(1/dist)) and three_interpolate
+    in one kernel; dist/idx/weight stay on chip unless ``return_aux``.  Forward only (use the
+    unfused ops when ``points2`` needs a gradient).
+    Returns out (b,n,c) [, dist (b,n,3), idx (b,n,3), weight (b,n,3)]."""
+    xyz1 = require_cuda(xyz1, "xyz1", torch.float32)
+    xyz2 = require_cuda(xyz2, "xyz2", torch.float32)
+    points2 = require_cuda(points2, "points2", torch.float32)
+    same_device(xyz1, xyz2, points2)
+    if xyz1.dim() != 3 or xyz1.shape[2] != 3 or xyz2.dim() != 3 or xyz2.shape[2] != 3 or xyz1.shape[0] != xyz2.shape[0]:
+        raise ValueError("three_nn_interpolate expects (b,n,3) xyz1 and (b,m,3) xyz2")
+    if points2.dim() != 3 or points2.shape[:2] != xyz2.shape[:2]:
+        raise ValueError("three_nn_interpolate expects (b,m,c) points2 matching xyz2")
+    b, n, _ = xyz1.shape
+    m = xyz2.shape[1]
+    c = points2.shape[2]
+    if m <= 0:
+        raise ValueError("three_nn_interpolate expects at least one known point")
+    dev = xyz1.device
+    out = torch.empty((b, n, c), dtype=torch.float32, device=dev)
+    dist = torch.empty((b, n, 3), dtype=torch.float32, device=dev) if return_aux else None
+    idx = torch.empty((b, n, 3), dtype=torch.int32, device=dev) if return_aux else None
+    weight = torch.empty((b, n, 3), dtype=torch.float32, device=dev) if return_aux else None
+    if b * n:
+        with on_device(xyz1):
+            rc = _lib.load().pn2_three_nn_interpolate(b, n, m, c, ptr(xyz1), ptr(xyz2), ptr(points2.detach()), ptr(out),
+                                                      ptr(dist), ptr(idx), ptr(weight), stream_ptr(dev))
+        _lib.check(rc, "pn2_three_nn_interpolate")
+    if return_aux:
+        return out, dist, idx, weight
+    return out
