@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py — set-abstraction throughput on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this implementation
+    python bench.py --impl reference [...]                         # the reference's CPU path
+    torchrun --nproc-per-node N bench.py --gpus N ...              # one rank per GPU (weak scaling)
+
+A "step" is one pass of the hot path — farthest_point_sample + gather_point + query_ball_point +
+group_point(xyz) — over one batch of the SSG set-abstraction configuration
+(BASELINE.json configs[1]: B=32 N=4096 npoint=1024 nsample=32 radius=0.1, uniform synthetic
+clouds).  Prints ONE JSON line (rank 0).
+
+  value      whole-job points/s (B*N per rank per step, summed over ranks / max-over-ranks time),
+             inputs resident in HBM, CUDA-event timed per step, L2 flushed between steps.
+  e2e        the same metric through the host-buffer C-ABI call (pn2_sa_layer_host): pinned host
+             xyz -> H2D -> 3 kernels -> D2H of new_xyz/idx/pts_cnt/grouped_xyz, all inside the
+             timed region.
+  roofline   dominant kernel (FPS): algorithmic bytes / its CUDA-event time vs the measured HBM peak.
+  cpu_baseline  the same workload on the host cores (FPS: oracle port — the reference has no CPU
+             FPS; ball query + group: the reference's own CPU functions when oracle/_ref travelled).
+
+Extra (not part of the driver contract): --report FILE writes per-kernel tables for all
+BASELINE.json configs; --fps-sweep / --bq-sweep time kernel variants.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "set-abstraction points/sec"
+UNIT = "points/s"
+L2_FLUSH_BYTES = 256 << 20  # > 126 MB L2
+
+
+# ------------------------------------------------------------------------------------------------
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()  # the exact process we started
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_pass(xyz: np.ndarray, npoint: int, radius: float, nsample: int, threads: int, use_ref: bool):
+    """One pass of the hot path on the host: per cloud FPS (oracle port) + gather + ball query +
+    group (reference CPU functions if available), clouds spread over `threads` host threads
+    (ctypes releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import oracle as O
+
+    def one(i):
+        c = xyz[i:i + 1]
+        idx = O.oracle_fps(npoint, c)
+        new_xyz = O.oracle_gather_point(c, idx)
+        if use_ref:
+            bi = O.refcpu_query_ball_point(radius, nsample, c, new_xyz)
+            g = O.refcpu_group_point(c, bi)
+        else:
+            bi, _ = O.oracle_query_ball_point(radius, nsample, c, new_xyz, use_fma=False)
+            g = O.oracle_group_point(c, bi)
+        return g.shape
+
+    if threads <= 1:
+        for i in range(xyz.shape[0]):
+            one(i)
+    else:
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            list(ex.map(one, range(xyz.shape[0])))
+
+
+def cpu_baseline(cfg, budget_s: float = 12.0):
+    from oracle import oracle as O
+    from pointnet2_b200 import workloads as W
+    xyz = W.DISTRIBUTIONS[cfg["dist"]](cfg["b"], cfg["n"], cfg["seed"])
+    cores = cpu_cores()
+    use_ref = O.have_refcpu()
+    O.lib()
+    if use_ref:
+        O.refcpu()
+    cpu_pass(xyz[:min(cores, cfg["b"])], cfg["npoint"], cfg["radius"], cfg["nsample"], cores, use_ref)  # warm-up
+    t0 = time.perf_counter()
+    passes = 0
+    while True:
+        cpu_pass(xyz, cfg["npoint"], cfg["radius"], cfg["nsample"], cores, use_ref)
+        passes += 1
+        el = time.perf_counter() - t0
+        if el >= budget_s or passes >= 200:
+            break
+    value = passes * cfg["b"] * cfg["n"] / el
+    return {"value": value, "unit": UNIT, "cores": cores,
+            "kind": "port",  # FPS dominates the CPU time and the reference has no CPU FPS (GPU-only op)
+            "sample": (f"{passes} pass(es) of the full {cfg['name']} batch ({cfg['b']}x{cfg['n']} pts) in {el:.2f}s on {cores} "
+                       f"host threads (one cloud per task); FPS = oracle C restatement of tf_sampling_g.cu:105-170; "
+                       f"ball query+group = " + ("reference CPU functions test/query_ball_point.cpp:19-66 (oracle/_ref)" if use_ref
+                                                  else "oracle C restatement")),
+            "ms_per_pass": 1e3 * el / passes}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference_arm(args, cfg):
+    """--impl reference: the reference's CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # other ranks exit 0 without work
+    from oracle import oracle as O
+    from pointnet2_b200 import workloads as W
+    xyz = W.DISTRIBUTIONS[cfg["dist"]](cfg["b"], cfg["n"], cfg["seed"])
+    cores = cpu_cores()
+    use_ref = O.have_refcpu()
+    for _ in range(max(args.warmup, 1)):
+        cpu_pass(xyz, cfg["npoint"], cfg["radius"], cfg["nsample"], cores, use_ref)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_pass(xyz, cfg["npoint"], cfg["radius"], cfg["nsample"], cores, use_ref)
+    el = time.perf_counter() - t0
+    value = args.steps * cfg["b"] * cfg["n"] / el
+    sample = (f"each step = the full {cfg['name']} batch ({cfg['b']}x{cfg['n']} pts) on {cores} host threads; FPS = C restatement "
+              f"(the reference has no CPU FPS), ball query+group = " + ("reference CPU code (oracle/_ref)" if use_ref else "oracle port"))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(cfg, 1),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(cfg, world):
+    return {"workload": f"{cfg['name']}: SSG SA layer FPS+gather_point+query_ball_point+group_point(xyz), "
+                        f"B={cfg['b']}/GPU N={cfg['n']} npoint={cfg['npoint']} nsample={cfg['nsample']} radius={cfg['radius']}",
+            "global_batch": cfg["b"] * world, "points_per_cloud": cfg["n"], "parallelism": f"dp{world} (clouds sharded, no collective)",
+            "distribution": "uniform [0,1)^3, seed 100+rank", "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB memset, untimed)"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200_arm(args, cfg):
+    import torch
+    import torch.distributed as dist
+
+    from pointnet2_b200 import _lib, workloads as W
+    from pointnet2_b200.host import SetAbstractionHost
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    lib = _lib.load()
+    b, n, m, s, r = cfg["b"], cfg["n"], cfg["npoint"], cfg["nsample"], cfg["radius"]
+    xyz_np = W.DISTRIBUTIONS[cfg["dist"]](b, n, cfg["seed"] + rank)
+    xyz = torch.from_numpy(xyz_np).to(dev)
+    fps_idx = torch.empty((b, m), dtype=torch.int32, device=dev)
+    new_xyz = torch.empty((b, m, 3), dtype=torch.float32, device=dev)
+    idx = torch.empty((b, m, s), dtype=torch.int32, device=dev)
+    cnt = torch.empty((b, m), dtype=torch.int32, device=dev)
+    grouped = torch.empty((b, m, s, 3), dtype=torch.float32, device=dev)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream(dev)
+    sp = st.cuda_stream
+
+    def step_device(ev=None):
+        if ev:
+            ev[0].record(st)
+        rc = lib.pn2_fps_gather(b, n, m, xyz.data_ptr(), fps_idx.data_ptr(), new_xyz.data_ptr(), sp)
+        if ev:
+            ev[1].record(st)
+        rc |= lib.pn2_query_ball_point(b, n, m, r, s, xyz.data_ptr(), new_xyz.data_ptr(), idx.data_ptr(), cnt.data_ptr(), sp)
+        if ev:
+            ev[2].record(st)
+        rc |= lib.pn2_group_point(b, n, 3, m, s, xyz.data_ptr(), idx.data_ptr(), grouped.data_ptr(), sp)
+        if ev:
+            ev[3].record(st)
+        if rc:
+            raise RuntimeError(f"kernel launch failed rc={rc}")
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident leg ---------------------------------------------------------------
+    for _ in range(args.warmup):
+        flush.zero_()
+        step_device()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    barrier()
+    for k in range(args.steps):
+        flush.zero_()
+        step_device(evs[k])
+    barrier()
+    launches = _lib.launch_count() - launches0
+    t_fps = [e[0].elapsed_time(e[1]) for e in evs]
+    t_bq = [e[1].elapsed_time(e[2]) for e in evs]
+    t_grp = [e[2].elapsed_time(e[3]) for e in evs]
+    t_step = [e[0].elapsed_time(e[3]) for e in evs]
+    total_ms = max_over_ranks(sum(t_step))
+    value = world * b * n * args.steps / (total_ms * 1e-3)
+
+    # ---- end-to-end leg: host buffers through the C-ABI host call --------------------------
+    sess = SetAbstractionHost(b, n, m, r, s, device=dev)
+    sess.h_xyz.numpy()[...] = xyz_np
+    for _ in range(args.warmup):
+        flush.zero_()
+        sess.launch(st)
+    e2e_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches1 = _lib.launch_count()
+    barrier()
+    for k in range(args.steps):
+        flush.zero_()
+        e2e_ev[k][0].record(st)
+        sess.launch(st)
+        e2e_ev[k][1].record(st)
+    barrier()
+    launches += _lib.launch_count() - launches1
+    e2e_ms = max_over_ranks(sum(a.elapsed_time(bb) for a, bb in e2e_ev))
+    e2e_value = world * b * n * args.steps / (e2e_ms * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+    # sanity: the e2e outputs must equal the device-resident outputs
+    same = bool((sess.h_idx.to(dev) == idx).all()) and bool((sess.h_new_xyz.to(dev) == new_xyz).all())
+
+    if rank == 0:
+        peak, peak_kind = measured_peaks()
+        fps_ms = statistics.mean(t_fps)
+        fps_bytes = W.bytes_fps(b, n, m, with_new_xyz=True)
+        achieved = fps_bytes / (fps_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("fps_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        layer_bytes = W.bytes_sa_layer(b, n, m, s)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(cfg, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": sess.h2d_bytes, "d2h_bytes_per_step": sess.d2h_bytes,
+                    "ms_per_step": e2e_ms / args.steps, "outputs_match_device_leg": same},
+            "gpu_launches": int(launches),  # this library's kernels inside the two timed regions (3 per step each)
+            "roofline": {"bound": "hbm", "kernel": "fps_cta_kernel<4,1024> (FPS + fused gather_point)", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_kind": f"of {peak_kind}",
+                         "algorithmic_bytes_per_launch": fps_bytes, "ms_per_launch": fps_ms,
+                         "note": "FPS is a serial chain of npoint argmax steps: latency/FP32-issue bound, not HBM bound",
+                         "secondary": {"point_pairs_per_s": b * (m - 1) * n / (fps_ms * 1e-3),
+                                       "whole_layer_GBps": layer_bytes / (statistics.mean(t_step) * 1e-3) / 1e9,
+                                       "whole_layer_frac": layer_bytes / (statistics.mean(t_step) * 1e-3) / 1e9 / peak}},
+            "kernels_ms": {"fps_gather": fps_ms, "query_ball_point": statistics.mean(t_bq), "group_point": statistics.mean(t_grp),
+                           "step": statistics.mean(t_step),
+                           "GBps": {"query_ball_point": W.bytes_ball_query(b, n, m, s) / (statistics.mean(t_bq) * 1e-3) / 1e9,
+                                    "group_point": W.bytes_group(b, n, m, s, 3) / (statistics.mean(t_grp) * 1e-3) / 1e9}},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(cfg, budget_s=args.cpu_budget)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--report", type=str, default=None, help="write per-kernel tables for all BASELINE configs to this file")
+    ap.add_argument("--fps-sweep", action="store_true")
+    ap.add_argument("--bq-sweep", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    from pointnet2_b200 import workloads as W
+    cfg = dict(W.CFG2_SSG_SA)
+    if args.report or args.fps_sweep or args.bq_sweep:
+        import bench_report
+        bench_report.main(args)
+        return
+    if args.impl == "reference":
+        run_reference_arm(args, cfg)
+    else:
+        run_b200_arm(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

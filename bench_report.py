@@ -1,0 +1,234 @@
+"""Per-kernel tables and tuning sweeps (NOT the driver contract — that is bench.py's default mode).
+
+    python bench.py --report gpurun_out/report.json     # every BASELINE.json config, per kernel
+    python bench.py --fps-sweep                          # FPS kernel variants (threads, pts/thread, cluster)
+    python bench.py --bq-sweep                           # ball query lanes-per-query
+
+All timings: CUDA events on the launching stream, >= 3 warm-ups, L2 flushed (256 MiB memset)
+before every timed launch, median of the repeats.
+"""
+from __future__ import annotations
+
+import json
+import os
+import statistics
+import sys
+
+import numpy as np
+
+
+def _setup():
+    import torch
+    from pointnet2_b200 import _lib
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    return torch, lib, dev, flush
+
+
+def timeit(torch, flush, fn, reps=10, warm=3):
+    st = torch.cuda.current_stream()
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        fn()
+        b.record(st)
+        b.synchronize()
+        ts.append(a.elapsed_time(b))
+    return statistics.median(ts)
+
+
+def fps_sweep(out_path=None):
+    torch, lib, dev, flush = _setup()
+    from pointnet2_b200 import workloads as W
+    rows = []
+    cases = [(32, 1024, 512), (32, 4096, 1024), (16, 8192, 1024), (2, 8192, 1024), (8, 4096, 1024), (8, 16384, 4096),
+             (8, 65536, 2048), (1, 65536, 2048), (8, 262144, 512), (1, 262144, 512)]
+    variants = [(128, 1, 1), (256, 1, 1), (512, 1, 1), (512, 2, 1), (512, 4, 1), (512, 8, 1), (512, 16, 1), (1024, 1, 1),
+                (1024, 2, 1), (1024, 4, 1), (1024, 8, 1)]
+    for C in (2, 4, 8, 16):
+        for (t, p) in [(512, 1), (512, 2), (512, 4), (512, 8), (512, 16), (512, 32), (1024, 2), (1024, 4), (1024, 8)]:
+            variants.append((t, p, C))
+    for (b, n, m) in cases:
+        xyz = torch.from_numpy(W.cloud_uniform(b, n, 100)).to(dev)
+        idx = torch.empty((b, m), dtype=torch.int32, device=dev)
+        nx = torch.empty((b, m, 3), dtype=torch.float32, device=dev)
+        ref = None
+        for (t, p, c) in [(0, 0, 0)] + variants:
+            if t and (t * p * c < n or t * p * c > 16 * n or b * c > 8 * 148):
+                continue
+            lib.pn2_set_fps_config(t, p, c)
+            rc = [0]
+
+            def fn():
+                rc[0] |= lib.pn2_fps_gather(b, n, m, xyz.data_ptr(), idx.data_ptr(), nx.data_ptr(), None)
+            try:
+                ms = timeit(torch, flush, fn, reps=5, warm=2)
+            except Exception as e:  # noqa: BLE001
+                rows.append(dict(b=b, n=n, m=m, cfg=[t, p, c], error=str(e)))
+                continue
+            finally:
+                lib.pn2_set_fps_config(0, 0, 0)
+            if rc[0]:
+                rows.append(dict(b=b, n=n, m=m, cfg=[t, p, c], error=f"rc={rc[0]}"))
+                continue
+            if ref is None:
+                ref = idx.clone()
+            ok = bool(torch.equal(ref, idx))
+            row = dict(b=b, n=n, m=m, cfg=[t, p, c], ms=ms, us_per_iter=1e3 * ms / (m - 1), same_as_default=ok,
+                       pairs_per_s=b * (m - 1) * n / (ms * 1e-3))
+            rows.append(row)
+            print(json.dumps(row), flush=True)
+    if out_path:
+        json.dump(rows, open(out_path, "w"), indent=1)
+    return rows
+
+
+def bq_sweep(out_path=None):
+    torch, lib, dev, flush = _setup()
+    from pointnet2_b200 import workloads as W
+    rows = []
+    cases = [("U", 32, 4096, 1024, 0.1, 32), ("S", 32, 1024, 512, 0.1, 16), ("S", 32, 1024, 512, 0.4, 128),
+             ("S", 32, 512, 128, 0.8, 128), ("D", 2, 8192, 1024, 0.1, 32), ("D", 16, 8192, 1024, 0.1, 32),
+             ("U", 8, 16384, 4096, 0.1, 32), ("U", 1, 65536, 16384, 0.1, 32)]
+    for (gen, b, n, m, r, s) in cases:
+        xyz = torch.from_numpy(W.DISTRIBUTIONS[gen](b, n, 100)).to(dev)
+        fi = torch.empty((b, m), dtype=torch.int32, device=dev)
+        nx = torch.empty((b, m, 3), dtype=torch.float32, device=dev)
+        lib.pn2_fps_gather(b, n, m, xyz.data_ptr(), fi.data_ptr(), nx.data_ptr(), None)
+        idx = torch.empty((b, m, s), dtype=torch.int32, device=dev)
+        cnt = torch.empty((b, m), dtype=torch.int32, device=dev)
+        for g in (0, 1, 2, 4, 8, 16, 32):
+            lib.pn2_set_bq_group(g)
+            ms = timeit(torch, flush, lambda: lib.pn2_query_ball_point(b, n, m, r, s, xyz.data_ptr(), nx.data_ptr(),
+                                                                       idx.data_ptr(), cnt.data_ptr(), None), reps=7)
+            lib.pn2_set_bq_group(0)
+            row = dict(gen=gen, b=b, n=n, m=m, r=r, s=s, group=g, ms=ms, mean_cnt=float(cnt.float().mean()),
+                       GBps=W.bytes_ball_query(b, n, m, s) / (ms * 1e-3) / 1e9)
+            rows.append(row)
+            print(json.dumps(row), flush=True)
+    if out_path:
+        json.dump(rows, open(out_path, "w"), indent=1)
+    return rows
+
+
+def report(out_path):
+    """Per-kernel time, algorithmic GB/s and fraction of the measured HBM peak for every BASELINE config."""
+    torch, lib, dev, flush = _setup()
+    from bench import measured_peaks
+    from pointnet2_b200 import workloads as W
+    peak, kind = measured_peaks()
+    rows = []
+
+    def add(cfg, kernel, ms, nbytes, extra=None):
+        gbps = nbytes / (ms * 1e-3) / 1e9
+        row = dict(config=cfg, kernel=kernel, ms=ms, algorithmic_MB=nbytes / 1e6, GBps=gbps, frac_of_peak=gbps / peak,
+                   peak=f"{peak} GB/s of {kind}")
+        if extra:
+            row.update(extra)
+        rows.append(row)
+        print(json.dumps(row), flush=True)
+
+    def T(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    def sa_layer(tag, xyz, feats, m, r, s, xyz_first=True):
+        b, n, _ = xyz.shape
+        fi = torch.empty((b, m), dtype=torch.int32, device=dev)
+        nx = torch.empty((b, m, 3), dtype=torch.float32, device=dev)
+        ms = timeit(torch, flush, lambda: lib.pn2_fps_gather(b, n, m, xyz.data_ptr(), fi.data_ptr(), nx.data_ptr(), None))
+        add(tag, "fps+gather", ms, W.bytes_fps(b, n, m, True), dict(pairs_per_s=b * (m - 1) * n / (ms * 1e-3), us_per_iter=1e3 * ms / max(m - 1, 1)))
+        idx = torch.empty((b, m, s), dtype=torch.int32, device=dev)
+        cnt = torch.empty((b, m), dtype=torch.int32, device=dev)
+        ms = timeit(torch, flush, lambda: lib.pn2_query_ball_point(b, n, m, r, s, xyz.data_ptr(), nx.data_ptr(), idx.data_ptr(), cnt.data_ptr(), None))
+        add(tag, f"query_ball_point r={r} S={s}", ms, W.bytes_ball_query(b, n, m, s), dict(mean_cnt=float(cnt.float().mean())))
+        g = torch.empty((b, m, s, 3), dtype=torch.float32, device=dev)
+        ms = timeit(torch, flush, lambda: lib.pn2_group_point(b, n, 3, m, s, xyz.data_ptr(), idx.data_ptr(), g.data_ptr(), None))
+        add(tag, f"group_point C=3 S={s}", ms, W.bytes_group(b, n, m, s, 3))
+        c = 0 if feats is None else feats.shape[2]
+        if c:
+            gf = torch.empty((b, m, s, c), dtype=torch.float32, device=dev)
+            ms = timeit(torch, flush, lambda: lib.pn2_group_point(b, n, c, m, s, feats.data_ptr(), idx.data_ptr(), gf.data_ptr(), None))
+            add(tag, f"group_point C={c} S={s}", ms, W.bytes_group(b, n, m, s, c))
+            del gf
+        out = torch.empty((b, m, s, 3 + c), dtype=torch.float32, device=dev)
+        ms = timeit(torch, flush, lambda: lib.pn2_group_concat(b, n, c, m, s, xyz.data_ptr(), nx.data_ptr(), feats.data_ptr() if c else None,
+                                                               idx.data_ptr(), 1 if xyz_first else 0, out.data_ptr(), None, None))
+        add(tag, f"group_concat (fused tail) C={c}+3 S={s}", ms, 4 * b * m * s + 4 * b * min(n, m * s) * (c + 3) + 4 * b * m * s * (c + 3))
+        return nx
+
+    # cfg2 in the three input distributions
+    c2 = W.CFG2_SSG_SA
+    for gen in ("U", "S", "D"):
+        sa_layer(f"cfg2[{gen}]", T(W.DISTRIBUTIONS[gen](c2["b"], c2["n"], 100)), None, c2["npoint"], c2["radius"], c2["nsample"])
+    # cfg3 MSG stack
+    c3 = W.CFG3_MSG
+    xyz = T(W.cloud_surface(c3["b"], c3["n"], 100))
+    L1, L2 = c3["layers"]
+    nx1 = None
+    for r, s in zip(L1["radii"], L1["nsamples"]):
+        nx1 = sa_layer("cfg3.L1", xyz, None, L1["npoint"], r, s, xyz_first=False)
+    feats = T(W.features(c3["b"], L1["npoint"], L2["c"], 103))
+    for r, s in zip(L2["radii"], L2["nsamples"]):
+        sa_layer("cfg3.L2", nx1, feats, L2["npoint"], r, s, xyz_first=False)
+    # cfg4 sem-seg: SA chain + FP chain, B=16 on one GPU and the 2-clouds-per-GPU shard
+    c4 = W.CFG4_SEMSEG
+    for b in (16, 2):
+        cur = T(W.cloud_duplicates(b, c4["n"], 100))
+        levels = [cur]
+        for L in c4["sa"]:
+            f = T(W.features(b, cur.shape[1], L["c"], 104)) if L["c"] else None
+            cur = sa_layer(f"cfg4[B={b}].SA{L['npoint']}", cur, f, L["npoint"], L["radius"], L["nsample"])
+            levels.append(cur)
+        for F in c4["fp"]:
+            x1 = [l for l in levels if l.shape[1] == F["n"]][0]
+            x2 = [l for l in levels if l.shape[1] == F["m"]][0]
+            p2 = T(W.features(b, F["m"], F["c"], 105))
+            n_, m_, c_ = F["n"], F["m"], F["c"]
+            d = torch.empty((b, n_, 3), dtype=torch.float32, device=dev)
+            i = torch.empty((b, n_, 3), dtype=torch.int32, device=dev)
+            ms = timeit(torch, flush, lambda: lib.pn2_three_nn(b, n_, m_, x1.data_ptr(), x2.data_ptr(), d.data_ptr(), i.data_ptr(), None))
+            add(f"cfg4[B={b}].FP{n_}<-{m_}", "three_nn", ms, W.bytes_three_nn(b, n_, m_), dict(pairs_per_s=b * n_ * m_ / (ms * 1e-3)))
+            w = torch.full((b, n_, 3), 1 / 3, dtype=torch.float32, device=dev)
+            o = torch.empty((b, n_, c_), dtype=torch.float32, device=dev)
+            ms = timeit(torch, flush, lambda: lib.pn2_three_interpolate(b, m_, c_, n_, p2.data_ptr(), i.data_ptr(), w.data_ptr(), o.data_ptr(), None))
+            add(f"cfg4[B={b}].FP{n_}<-{m_}", f"three_interpolate C={c_}", ms, W.bytes_three_interpolate(b, n_, m_, c_))
+            ms = timeit(torch, flush, lambda: lib.pn2_three_nn_interpolate(b, n_, m_, c_, x1.data_ptr(), x2.data_ptr(), p2.data_ptr(), o.data_ptr(), None, None, None, None))
+            add(f"cfg4[B={b}].FP{n_}<-{m_}", f"three_nn_interpolate (fused) C={c_}", ms, 12 * b * n_ + 12 * b * m_ + 4 * b * m_ * c_ + 4 * b * n_ * c_)
+    # cfg5 sweep: FPS + gather + ball query, B=8 and the per-GPU shards
+    c5 = W.CFG5_SWEEP
+    for n in c5["ns"]:
+        for b in (8, 1):
+            if n >= 262144 and b == 8 and os.environ.get("PN2_REPORT_BIG", "1") != "1":
+                continue
+            xyz = T(W.cloud_uniform(b, n, 100 + int(np.log2(n))))
+            m = n // 4
+            fi = torch.empty((b, m), dtype=torch.int32, device=dev)
+            nx = torch.empty((b, m, 3), dtype=torch.float32, device=dev)
+            ms = timeit(torch, flush, lambda: lib.pn2_fps_gather(b, n, m, xyz.data_ptr(), fi.data_ptr(), nx.data_ptr(), None), reps=3, warm=1)
+            add(f"cfg5[B={b},N={n}]", "fps+gather", ms, W.bytes_fps(b, n, m, True), dict(pairs_per_s=b * (m - 1) * n / (ms * 1e-3), us_per_iter=1e3 * ms / (m - 1),
+                                                                                         points_per_s=b * n / (ms * 1e-3)))
+            idx = torch.empty((b, m, 32), dtype=torch.int32, device=dev)
+            cnt = torch.empty((b, m), dtype=torch.int32, device=dev)
+            ms = timeit(torch, flush, lambda: lib.pn2_query_ball_point(b, n, m, 0.1, 32, xyz.data_ptr(), nx.data_ptr(), idx.data_ptr(), cnt.data_ptr(), None), reps=3, warm=1)
+            add(f"cfg5[B={b},N={n}]", "query_ball_point", ms, W.bytes_ball_query(b, n, m, 32), dict(mean_cnt=float(cnt.float().mean())))
+    json.dump(rows, open(out_path, "w"), indent=1)
+
+
+def main(args):
+    os.makedirs("gpurun_out", exist_ok=True)
+    if args.fps_sweep:
+        fps_sweep("gpurun_out/fps_sweep.json")
+    if args.bq_sweep:
+        bq_sweep("gpurun_out/bq_sweep.json")
+    if args.report:
+        report(args.report)
+
+
+if __name__ == "__main__":
+    print("use: python bench.py --report FILE | --fps-sweep | --bq-sweep", file=sys.stderr)

@@ -134,8 +134,11 @@ unsigned long long pn2_launch_count(void);
 /* the exact d2-domain threshold the ball query uses for `radius`
  * (largest float t with max(sqrtf(t),1e-20f) < radius; negative if no t qualifies) */
 float pn2_ball_threshold(float radius);
-/* tuning override for experiments: "T,P,C" (threads, points/thread, cluster size); NULL resets */
+/* tuning override for experiments: threads, points/thread, cluster size of the FPS kernel
+ * (cluster 0 = global-scratch fallback); threads = 0 restores the built-in plan */
 void pn2_set_fps_config(int threads, int points_per_thread, int cluster);
+/* tuning override: lanes cooperating on one ball query (1,2,4,..,32); 0 restores the heuristic */
+void pn2_set_bq_group(int lanes_per_query);
 
 #ifdef __cplusplus
 }

@@ -35,6 +35,7 @@ _SIGNATURES = {
     "pn2_launch_count": (c_ulonglong, []),
     "pn2_ball_threshold": (c_float, [c_float]),
     "pn2_set_fps_config": (None, [c_int, c_int, c_int]),
+    "pn2_set_bq_group": (None, [c_int]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

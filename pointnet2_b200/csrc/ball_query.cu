@@ -128,7 +128,7 @@ static int launch_bq(int b, int n, int m, float thr, int nsample, const float* x
     return finish_launch();
 }
 
-static int g_bq_group = 0;  // experiment override (PN2_BQ_GROUP env, read once)
+static int g_bq_group = 0;  // experiment override (pn2_set_bq_group, or PN2_BQ_GROUP env read once)
 
 static int pick_group(int b, int m) {
     static bool init = false;
@@ -165,6 +165,8 @@ float pn2_ball_threshold(float radius) {
     memcpy(&f, &lo, 4);
     return f;
 }
+
+void pn2_set_bq_group(int lanes_per_query) { pn2::g_bq_group = lanes_per_query; }
 
 int pn2_query_ball_point(int b, int n, int m, float radius, int nsample, const float* xyz1, const float* xyz2,
                          int* idx, int* pts_cnt, void* stream) {
