@@ -138,10 +138,11 @@ static int pick_group(int b, int m) {
         init = true;
     }
     if (g_bq_group > 0) return g_bq_group;
-    // aim for >= ~2 CTAs' worth of lanes per SM: 148 SMs * 1024 lanes
+    // enough lanes to fill every SM's 2048 thread slots (measured: more, smaller groups win until
+    // the machine is full; see profiles/)
     const long long queries = (long long)b * m;
     int G = 1;
-    while (G < 32 && queries * G < 148LL * 1024) G *= 2;
+    while (G < 32 && queries * G < 148LL * 2048) G *= 2;
     return G;
 }
 
