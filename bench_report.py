@@ -51,6 +51,8 @@ def fps_sweep(out_path=None):
              (8, 65536, 2048), (1, 65536, 2048), (8, 262144, 512), (1, 262144, 512)]
     variants = [(128, 1, 1), (256, 1, 1), (512, 1, 1), (512, 2, 1), (512, 4, 1), (512, 8, 1), (512, 16, 1), (1024, 1, 1),
                 (1024, 2, 1), (1024, 4, 1), (1024, 8, 1)]
+    variants += [(128, 1, -1), (256, 1, -1), (512, 1, -1), (1024, 1, -1), (512, 2, -1), (1024, 2, -1), (512, 4, -1),
+                 (1024, 4, -1), (512, 8, -1)]
     for C in (2, 4, 8, 16):
         for (t, p) in [(512, 1), (512, 2), (512, 4), (512, 8), (512, 16), (512, 32), (1024, 2), (1024, 4), (1024, 8)]:
             variants.append((t, p, C))
@@ -60,7 +62,7 @@ def fps_sweep(out_path=None):
         nx = torch.empty((b, m, 3), dtype=torch.float32, device=dev)
         ref = None
         for (t, p, c) in [(0, 0, 0)] + variants:
-            if t and (t * p * c < n or t * p * c > 16 * n or b * c > 8 * 148):
+            if t and (t * p * abs(c) < n or t * p * abs(c) > 16 * n or b * abs(c) > 8 * 148):
                 continue
             lib.pn2_set_fps_config(t, p, c)
             rc = [0]

@@ -180,6 +180,283 @@ fps_cta_kernel(int n, int m, const float* __restrict__ xyz, int* __restrict__ id
 }
 
 // =================================================================================================
+// Bucketed FPS, one CTA per cloud (the default for n <= 4096): EXACT, but most of the work of a
+// step is pruned.
+//
+// At start the CTA sorts its cloud along a Morton curve in shared memory; warp w then owns the
+// w-th run of 32*P consecutive sorted points (P per lane, in registers) — a spatially compact
+// BUCKET with a bounding box.  For a new pick s, every computed distance d(k,s) of a point in the
+// bucket is >= LB(s) = the reference's distance formula applied to the per-axis gaps between s
+// and the box: rounding is monotone, so fl(x_k - s_x) is at least the rounded gap in magnitude,
+// and the FMUL/FFMA/FFMA chain is monotone in |dx|,|dy|,|dz|.  Hence if LB(s) >= max_k td[k]
+// the step changes nothing in this bucket (min(d,td)=td for every k) and the warp skips it,
+// re-publishing its cached best.  Late in the sampling nearly every bucket is skipped, so a step
+// costs one box test + the shared argmax instead of n distance updates.
+//
+// The winner's coordinates travel with its key (so no index->coordinate lookup sits on the
+// critical path), the in-warp and cross-warp argmax use ONE redux + a ballot (the second redux on
+// the tie-break half of the key runs only when the maximum is not unique), and the per-warp table
+// is double-buffered so a step needs a single barrier.
+// =================================================================================================
+__device__ __forceinline__ unsigned morton_part(unsigned v) {  // spread the low 10 bits to every 3rd bit
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+__device__ __forceinline__ float warp_min_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(kFullMask, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFullMask, v, o));
+    return v;
+}
+
+// Pick the lane holding the warp's maximal (hi, lo) key; returns the lane (uniform) and the
+// maximal hi.  One redux + ballot when the maximum is unique, one more redux otherwise.
+__device__ __forceinline__ int warp_argmax_key(unsigned hi, unsigned lo, unsigned& max_hi) {
+    max_hi = warp_max_u32(hi);
+    unsigned bal = __ballot_sync(kFullMask, hi == max_hi);
+    if (__popc(bal) > 1) {
+        const unsigned ml = warp_max_u32(hi == max_hi ? lo : 0u);
+        bal = __ballot_sync(kFullMask, hi == max_hi && lo == ml);
+    }
+    return __ffs(bal) - 1;
+}
+
+template <int P, int T>
+__global__ void __launch_bounds__(T, 1)
+fps_bucket_kernel(int n, int m, int npad, const float* __restrict__ xyz, int* __restrict__ idx_out,
+                  float* __restrict__ new_xyz) {
+    constexpr int NW = T / 32;
+    __shared__ unsigned s_hi[2][32];
+    __shared__ float4 s_cand[2][32];  // (lo as float bits, x, y, z) of each warp's best point
+    __shared__ float s_red[6][32];
+    extern __shared__ float s_dyn[];  // [3*n] cloud copy, then [npad] sort keys
+    float* s_xyz = s_dyn;
+    unsigned* s_key = reinterpret_cast<unsigned*>(s_dyn + 3 * (size_t)n);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cloud = blockIdx.x;
+    const float* __restrict__ pts = xyz + (size_t)cloud * n * 3;
+    int* __restrict__ out = idx_out + (size_t)cloud * m;
+    float* __restrict__ oxyz = new_xyz ? new_xyz + (size_t)cloud * m * 3 : nullptr;
+
+    // ---- stage the cloud, find its bounding box ----------------------------------------------
+    for (int e = tid; e < 3 * n; e += T) s_xyz[e] = pts[e];
+    __syncthreads();
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int k = tid; k < n; k += T) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = s_xyz[3 * k + c];
+            mn[c] = fminf(mn[c], v);
+            mx[c] = fmaxf(mx[c], v);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float a = warp_min_f(mn[c]), b = warp_max_f(mx[c]);
+        if (lane == 0) {
+            s_red[c][warp] = a;
+            s_red[3 + c][warp] = b;
+        }
+    }
+    __syncthreads();
+    float scale[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        mn[c] = warp_min_f(lane < NW ? s_red[c][lane] : INFINITY);
+        mx[c] = warp_max_f(lane < NW ? s_red[3 + c][lane] : -INFINITY);
+        const float ext = mx[c] - mn[c];
+        scale[c] = (ext > 0.f && ext < 3.0e38f) ? 64.0f / ext : 0.0f;
+    }
+    // ---- Morton keys (6 bits per axis) | position, bitonic sort in shared memory --------------
+    for (int p = tid; p < npad; p += T) {
+        unsigned key = 0xffffffffu;
+        if (p < n) {
+            unsigned q[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float f = (s_xyz[3 * p + c] - mn[c]) * scale[c];
+                f = fminf(fmaxf(f, 0.f), 63.f);  // also maps NaN to 0
+                q[c] = (unsigned)f;
+            }
+            const unsigned mort = morton_part(q[0]) | (morton_part(q[1]) << 1) | (morton_part(q[2]) << 2);
+            key = (mort << 14) | (unsigned)p;  // p < 16384
+        }
+        s_key[p] = key;
+    }
+    __syncthreads();
+    for (int kk = 2; kk <= npad; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < npad; i += T) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned a = s_key[i], b = s_key[ixj];
+                    const bool up = (i & kk) == 0;
+                    if ((a > b) == up) {
+                        s_key[i] = b;
+                        s_key[ixj] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // ---- this thread's P points of its warp's bucket, ordered by the tie-break key -----------
+    float px[P], py[P], pz[P], td[P];
+    unsigned tb[P];
+    bool any_valid = false;
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const int pos = warp * (32 * P) + j * 32 + lane;
+        px[j] = py[j] = pz[j] = 0.f;
+        td[j] = -1.0f;
+        tb[j] = 0xffffffffu;
+        if (pos < n) {
+            const unsigned k = s_key[pos] & 0x3fffu;
+            px[j] = s_xyz[3 * k + 0];
+            py[j] = s_xyz[3 * k + 1];
+            pz[j] = s_xyz[3 * k + 2];
+            td[j] = 1e38f;
+            tb[j] = tb_encode(k);
+            any_valid = true;
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < P - 1; ++a) {
+#pragma unroll
+        for (int b = 0; b < P - 1 - a; ++b) {
+            if (tb[b] > tb[b + 1]) {
+                float t;
+                unsigned u;
+                t = px[b]; px[b] = px[b + 1]; px[b + 1] = t;
+                t = py[b]; py[b] = py[b + 1]; py[b + 1] = t;
+                t = pz[b]; pz[b] = pz[b + 1]; pz[b + 1] = t;
+                t = td[b]; td[b] = td[b + 1]; td[b + 1] = t;
+                u = tb[b]; tb[b] = tb[b + 1]; tb[b + 1] = u;
+            }
+        }
+    }
+    // bucket bounding box (empty buckets: +inf/-inf, their gap is +inf and they are always skipped)
+    float blo[3] = {INFINITY, INFINITY, INFINITY}, bhi[3] = {-INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        if (td[j] >= 0.f) {
+            blo[0] = fminf(blo[0], px[j]); bhi[0] = fmaxf(bhi[0], px[j]);
+            blo[1] = fminf(blo[1], py[j]); bhi[1] = fmaxf(bhi[1], py[j]);
+            blo[2] = fminf(blo[2], pz[j]); bhi[2] = fmaxf(bhi[2], pz[j]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        blo[c] = warp_min_f(blo[c]);
+        bhi[c] = warp_max_f(bhi[c]);
+    }
+    // initial candidate of the bucket: running minimum 1e38 everywhere -> earliest tie-break key
+    float wmax = -1.0f;
+    {
+        unsigned hi = 0u, lo = 0u;
+        if (any_valid) {  // tb[0] is this thread's smallest key among its valid points (padding sorts last)
+            hi = __float_as_uint(1e38f);
+            lo = ~tb[0];
+        }
+        unsigned mh;
+        const int L = warp_argmax_key(hi, lo, mh);
+        if (lane == L) {
+            s_hi[0][warp] = mh;
+            s_cand[0][warp] = make_float4(__uint_as_float(lo), px[0], py[0], pz[0]);
+        }
+        if (mh != 0u) wmax = __uint_as_float(mh);
+    }
+    float x1 = s_xyz[0], y1 = s_xyz[1], z1 = s_xyz[2];
+    if (tid == 0) {
+        out[0] = 0;
+        if (oxyz) {
+            oxyz[0] = x1;
+            oxyz[1] = y1;
+            oxyz[2] = z1;
+        }
+    }
+    __syncthreads();
+
+    for (int it = 1; it < m; ++it) {
+        const int buf = it & 1;
+        // lower bound of every computed distance from the pick to this bucket
+        const float gx = fmaxf(fmaxf(__fsub_rn(blo[0], x1), __fsub_rn(x1, bhi[0])), 0.f);
+        const float gy = fmaxf(fmaxf(__fsub_rn(blo[1], y1), __fsub_rn(y1, bhi[1])), 0.f);
+        const float gz = fmaxf(fmaxf(__fsub_rn(blo[2], z1), __fsub_rn(z1, bhi[2])), 0.f);
+        const float lb = __fmaf_rn(gz, gz, __fmaf_rn(gx, gx, __fmul_rn(gy, gy)));
+        if (lb < wmax) {  // warp-uniform: the pick can lower some running minimum in this bucket
+            float best = -1.0f;
+            int bj = 0;
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const float d = d2_fma_pattern(px[j], py[j], pz[j], x1, y1, z1);
+                const float d2 = fminf(d, td[j]);
+                td[j] = d2;
+                if (d2 > best) {  // ascending tie-break order within the thread: first maximum wins
+                    best = d2;
+                    bj = j;
+                }
+            }
+            float cx = px[0], cy = py[0], cz = pz[0];
+            unsigned ctb = tb[0];
+#pragma unroll
+            for (int j = 1; j < P; ++j) {
+                if (bj == j) {
+                    cx = px[j]; cy = py[j]; cz = pz[j];
+                    ctb = tb[j];
+                }
+            }
+            unsigned hi = 0u, lo = 0u;
+            if (best >= 0.0f) {
+                hi = __float_as_uint(best);
+                lo = ~ctb;
+            }
+            unsigned mh;
+            const int L = warp_argmax_key(hi, lo, mh);
+            if (lane == L) {
+                s_hi[buf][warp] = mh;
+                s_cand[buf][warp] = make_float4(__uint_as_float(lo), cx, cy, cz);
+            }
+            wmax = __uint_as_float(mh);  // an active bucket has valid points: mh is a real distance
+        } else if (lane == 0) {
+            s_hi[buf][warp] = s_hi[buf ^ 1][warp];
+            s_cand[buf][warp] = s_cand[buf ^ 1][warp];
+        }
+        __syncthreads();
+        const bool in = lane < NW;
+        const unsigned h = in ? s_hi[buf][lane] : 0u;
+        const unsigned gh = warp_max_u32(h);
+        unsigned bal = __ballot_sync(kFullMask, in && h == gh);
+        if (__popc(bal) > 1) {
+            const unsigned l = (in && h == gh) ? __float_as_uint(s_cand[buf][lane].x) : 0u;
+            const unsigned gl = warp_max_u32(l);
+            bal = __ballot_sync(kFullMask, in && h == gh && l == gl);
+        }
+        const float4 c = s_cand[buf][__ffs(bal) - 1];
+        x1 = c.y;
+        y1 = c.z;
+        z1 = c.w;
+        if (tid == 0) {
+            out[it] = (int)tb_decode(~__float_as_uint(c.x));
+            if (oxyz) {
+                oxyz[3 * it + 0] = x1;
+                oxyz[3 * it + 1] = y1;
+                oxyz[3 * it + 2] = z1;
+            }
+        }
+    }
+}
+
+// =================================================================================================
 // One thread-block CLUSTER per cloud (C = 2..16 CTAs).  Thread t of CTA r owns points
 // k = t + T*(r + C*j): slot k mod 512 == t mod 512 again (T % 512 == 0).
 // Per step: CTA-local argmax as above, then warp 0 pushes the CTA's 8-byte key into slot r of
@@ -397,6 +674,21 @@ static int launch_cta(int b, int n, int m, const float* inp, int* out, float* ne
     return finish_launch();
 }
 
+template <int P, int T>
+static int launch_bucket(int b, int n, int m, const float* inp, int* out, float* new_xyz, cudaStream_t st) {
+    auto kern = fps_bucket_kernel<P, T>;
+    int npad = 1;
+    while (npad < n) npad <<= 1;
+    size_t dyn = (size_t)n * 3 * sizeof(float) + (size_t)npad * sizeof(unsigned);
+    if (dyn > 200 * 1024 || n > 16384) return (int)cudaErrorInvalidValue;
+    if (dyn > 40 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return (int)e;
+    }
+    kern<<<b, T, dyn, st>>>(n, m, npad, inp, out, new_xyz);
+    return finish_launch();
+}
+
 template <int P, int T, bool XYZ_SMEM>
 static int launch_cluster(int C, int b, int n, int m, const float* inp, int* out, float* new_xyz, cudaStream_t st) {
     auto kern = fps_cluster_kernel<P, T, XYZ_SMEM>;
@@ -429,7 +721,7 @@ static int launch_cluster(int C, int b, int n, int m, const float* inp, int* out
 }
 
 struct FpsPlan {
-    int threads, ppt, cluster;  // cluster == 0: global-scratch fallback; 1: single CTA
+    int threads, ppt, cluster;  // cluster == 0: global-scratch fallback; 1: single CTA; -1: bucketed single CTA
     bool xyz_smem;
 };
 
@@ -448,13 +740,13 @@ static FpsPlan plan_fps(int b, int n) {
         p.xyz_smem = (g_cfg_ppt >= 32);
         return p;
     }
-    // single CTA: everything register-resident in one SM
-    if (n <= 128) return {128, 1, 1, false};
-    if (n <= 256) return {256, 1, 1, false};
-    if (n <= 512) return {512, 1, 1, false};
-    if (n <= 1024) return {512, 2, 1, false};
-    if (n <= 2048) return {512, 4, 1, false};
-    if (n <= 4096) return {1024, 4, 1, false};
+    // single CTA, bucketed (cluster = -1): exact bounding-box pruning, everything in one SM
+    if (n <= 128) return {128, 1, -1, false};
+    if (n <= 256) return {256, 1, -1, false};
+    if (n <= 512) return {512, 1, -1, false};
+    if (n <= 1024) return {1024, 1, -1, false};
+    if (n <= 2048) return {1024, 2, -1, false};
+    if (n <= 4096) return {1024, 4, -1, false};
     if (n <= 8192 && b >= 64) return {1024, 8, 1, false};
     // cluster: as many CTAs per cloud as keeps all clouds co-resident on the 148 SMs
     int cmax = pow2_floor(148 / (b > 148 ? 148 : b));
@@ -494,9 +786,23 @@ static int fps_dispatch(int b, int n, int m, const float* inp, float* temp, int*
     if (b == 0 || m == 0) return 0;
     if (!inp || !out) return (int)cudaErrorInvalidValue;
     FpsPlan plan = plan_fps(b, n);
-    if (plan.cluster >= 1) {
-        long long cap = (long long)plan.threads * plan.ppt * plan.cluster;
+    if (plan.cluster >= 1 || plan.cluster == -1) {
+        long long cap = (long long)plan.threads * plan.ppt * (plan.cluster < 0 ? 1 : plan.cluster);
         if (cap < n) return (int)cudaErrorInvalidValue;
+    }
+    if (plan.cluster == -1) {
+#define PN2_TRY_BKT(PP, TT) \
+    if (plan.ppt == PP && plan.threads == TT) return launch_bucket<PP, TT>(b, n, m, inp, out, new_xyz, st);
+        PN2_TRY_BKT(1, 128)
+        PN2_TRY_BKT(1, 256)
+        PN2_TRY_BKT(1, 512)
+        PN2_TRY_BKT(1, 1024)
+        PN2_TRY_BKT(2, 512)
+        PN2_TRY_BKT(2, 1024)
+        PN2_TRY_BKT(4, 512)
+        PN2_TRY_BKT(4, 1024)
+        PN2_TRY_BKT(8, 512)
+        return (int)cudaErrorInvalidValue;
     }
     if (plan.cluster == 1) {
         PN2_TRY_CTA(1, 128)

@@ -44,13 +44,16 @@ def test_fps_matches_oracle(dev, gen, b, n, m):
 
 
 @pytest.mark.parametrize("cfg", [(512, 2, 2), (512, 1, 4), (512, 4, 2), (512, 8, 4), (1024, 2, 2), (512, 2, 8),
-                                 (512, 1, 16), (512, 16, 2), (512, 32, 2), (1024, 4, 1), (512, 8, 1), (512, 16, 1)])
-@pytest.mark.parametrize("gen", ["U", "D"])
+                                 (512, 1, 16), (512, 16, 2), (512, 32, 2), (1024, 4, 1), (512, 8, 1), (512, 16, 1),
+                                 (128, 1, -1), (256, 1, -1), (512, 1, -1), (1024, 1, -1), (512, 2, -1), (1024, 2, -1),
+                                 (512, 4, -1), (1024, 4, -1), (512, 8, -1)])
+@pytest.mark.parametrize("gen", ["U", "D", "S"])
 def test_fps_every_kernel_variant_matches_oracle(dev, cfg, gen):
-    """Force each (threads, points/thread, cluster) kernel variant, including the DSMEM cluster
-    exchange and the shared-memory-coordinate variant, on a cloud that fits it."""
+    """Force each (threads, points/thread, cluster) kernel variant — register-resident single CTA
+    (cluster 1), bucketed single CTA (cluster -1), the DSMEM cluster exchange (cluster >= 2) and
+    the shared-memory-coordinate variant — on a cloud that fits it."""
     threads, ppt, cluster = cfg
-    cap = threads * ppt * cluster
+    cap = threads * ppt * abs(cluster)
     n = min(cap, 6000) - 3
     xyz = W.DISTRIBUTIONS[gen](2, n, 32)
     lib = _lib.load()
