@@ -180,23 +180,29 @@ fps_cta_kernel(int n, int m, const float* __restrict__ xyz, int* __restrict__ id
 }
 
 // =================================================================================================
-// Bucketed FPS, one CTA per cloud (the default for n <= 4096): EXACT, but most of the work of a
+// Bucketed FPS, one CTA per cloud (the default for n <= 8192): EXACT, but most of the work of a
 // step is pruned.
 //
 // At start the CTA sorts its cloud along a Morton curve in shared memory; warp w then owns the
-// w-th run of 32*P consecutive sorted points (P per lane, in registers) — a spatially compact
-// BUCKET with a bounding box.  For a new pick s, every computed distance d(k,s) of a point in the
-// bucket is >= LB(s) = the reference's distance formula applied to the per-axis gaps between s
-// and the box: rounding is monotone, so fl(x_k - s_x) is at least the rounded gap in magnitude,
-// and the FMUL/FFMA/FFMA chain is monotone in |dx|,|dy|,|dz|.  Hence if LB(s) >= max_k td[k]
-// the step changes nothing in this bucket (min(d,td)=td for every k) and the warp skips it,
-// re-publishing its cached best.  Late in the sampling nearly every bucket is skipped, so a step
-// costs one box test + the shared argmax instead of n distance updates.
+// w-th run of 32*P consecutive sorted points (P per lane, coordinates and running minimum in
+// registers) — a spatially compact BUCKET with a bounding box.  For a new pick s, every computed
+// distance d(k,s) of a point in the bucket is >= LB(s) = the reference's distance formula applied
+// to the per-axis gaps between s and the box: rounding is monotone, so |fl(x_k - s_x)| is at
+// least the rounded gap, and the FMUL/FFMA/FFMA chain is monotone in |dx|,|dy|,|dz|.  Hence if
+// LB(s) >= max_k td[k] the step changes nothing in this bucket (min(d,td)=td for every k) and the
+// warp skips it, re-publishing its cached best.  Late in the sampling most buckets are skipped.
 //
-// The winner's coordinates travel with its key (so no index->coordinate lookup sits on the
-// critical path), the in-warp and cross-warp argmax use ONE redux + a ballot (the second redux on
-// the tie-break half of the key runs only when the maximum is not unique), and the per-warp table
-// is double-buffered so a step needs a single barrier.
+// Measured on B200 (profiles/r1_microbench_latency.txt) the step is bound by the ALU pipe (2
+// cycles per warp instruction), the XU pipe (ffs/popc) and barrier latency (78 cycles at 32
+// warps, 29 at 8), so the kernel uses FEW warps with many points each, keeps ffs/popc off the
+// common path (predicated publishing instead of leader election; redux instead of ballot+ffs),
+// publishes only (value, sorted position) per warp and looks the winner's coordinates up once
+// from a float4 table in shared memory.
+//
+// Tie-break exactness: within a bucket the points are re-sorted by the reference tie-break key
+// tb(k) and dealt to lanes in runs of P, so the in-thread strict '>' scan in register order picks
+// the smallest tb among equal values; across lanes / warps equal values are rare and take a slow
+// path that compares tb explicitly.
 // =================================================================================================
 __device__ __forceinline__ unsigned morton_part(unsigned v) {  // spread the low 10 bits to every 3rd bit
     v = (v | (v << 16)) & 0x030000FFu;
@@ -217,16 +223,26 @@ __device__ __forceinline__ float warp_max_f(float v) {
     return v;
 }
 
-// Pick the lane holding the warp's maximal (hi, lo) key; returns the lane (uniform) and the
-// maximal hi.  One redux + ballot when the maximum is unique, one more redux otherwise.
-__device__ __forceinline__ int warp_argmax_key(unsigned hi, unsigned lo, unsigned& max_hi) {
-    max_hi = warp_max_u32(hi);
-    unsigned bal = __ballot_sync(kFullMask, hi == max_hi);
-    if (__popc(bal) > 1) {
-        const unsigned ml = warp_max_u32(hi == max_hi ? lo : 0u);
-        bal = __ballot_sync(kFullMask, hi == max_hi && lo == ml);
+// ascending bitonic sort of s_key[0..len) in segments of `seg` (seg a power of two dividing len)
+template <int T>
+__device__ __forceinline__ void bitonic_sort_smem(unsigned* s_key, int len, int seg, int tid) {
+    for (int kk = 2; kk <= seg; kk <<= 1) {
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < len; i += T) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned a = s_key[i], b = s_key[ixj];
+                    // the last level of a segmented sort must be ascending in EVERY segment
+                    const bool up = ((i & kk) == 0) || (kk == seg);
+                    if ((a > b) == up) {
+                        s_key[i] = b;
+                        s_key[ixj] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
     }
-    return __ffs(bal) - 1;
 }
 
 template <int P, int T>
@@ -234,12 +250,13 @@ __global__ void __launch_bounds__(T, 1)
 fps_bucket_kernel(int n, int m, int npad, const float* __restrict__ xyz, int* __restrict__ idx_out,
                   float* __restrict__ new_xyz) {
     constexpr int NW = T / 32;
-    __shared__ unsigned s_hi[2][32];
-    __shared__ float4 s_cand[2][32];  // (lo as float bits, x, y, z) of each warp's best point
+    constexpr int BUCKET = 32 * P;
+    static_assert(NW <= 32, "one table entry per lane");
+    __shared__ uint2 s_tab[2][32];  // per warp: (max running minimum as float bits, sorted position of its argmax)
     __shared__ float s_red[6][32];
-    extern __shared__ float s_dyn[];  // [3*n] cloud copy, then [npad] sort keys
-    float* s_xyz = s_dyn;
-    unsigned* s_key = reinterpret_cast<unsigned*>(s_dyn + 3 * (size_t)n);
+    extern __shared__ float4 s_dyn4[];  // [n] sorted points (x, y, z, tb bits), then [npad] u32 sort keys
+    float4* s_sorted = s_dyn4;
+    unsigned* s_key = reinterpret_cast<unsigned*>(s_dyn4 + n);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cloud = blockIdx.x;
@@ -247,14 +264,12 @@ fps_bucket_kernel(int n, int m, int npad, const float* __restrict__ xyz, int* __
     int* __restrict__ out = idx_out + (size_t)cloud * m;
     float* __restrict__ oxyz = new_xyz ? new_xyz + (size_t)cloud * m * 3 : nullptr;
 
-    // ---- stage the cloud, find its bounding box ----------------------------------------------
-    for (int e = tid; e < 3 * n; e += T) s_xyz[e] = pts[e];
-    __syncthreads();
+    // ---- bounding box of the cloud --------------------------------------------------------------
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
     for (int k = tid; k < n; k += T) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const float v = s_xyz[3 * k + c];
+            const float v = __ldg(pts + 3 * (size_t)k + c);
             mn[c] = fminf(mn[c], v);
             mx[c] = fmaxf(mx[c], v);
         }
@@ -276,106 +291,71 @@ fps_bucket_kernel(int n, int m, int npad, const float* __restrict__ xyz, int* __
         const float ext = mx[c] - mn[c];
         scale[c] = (ext > 0.f && ext < 3.0e38f) ? 64.0f / ext : 0.0f;
     }
-    // ---- Morton keys (6 bits per axis) | position, bitonic sort in shared memory --------------
-    for (int p = tid; p < npad; p += T) {
+    // ---- Morton keys (6 bits per axis) | original index; bitonic sort; then, inside every
+    //      bucket, re-sort by the tie-break key so lanes hold their points in tie-break order ----
+    for (int k = tid; k < npad; k += T) {
         unsigned key = 0xffffffffu;
-        if (p < n) {
+        if (k < n) {
             unsigned q[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                float f = (s_xyz[3 * p + c] - mn[c]) * scale[c];
+                float f = (__ldg(pts + 3 * (size_t)k + c) - mn[c]) * scale[c];
                 f = fminf(fmaxf(f, 0.f), 63.f);  // also maps NaN to 0
                 q[c] = (unsigned)f;
             }
             const unsigned mort = morton_part(q[0]) | (morton_part(q[1]) << 1) | (morton_part(q[2]) << 2);
-            key = (mort << 14) | (unsigned)p;  // p < 16384
+            key = (mort << 14) | (unsigned)k;  // k < 16384
         }
-        s_key[p] = key;
+        s_key[k] = key;
     }
     __syncthreads();
-    for (int kk = 2; kk <= npad; kk <<= 1) {
-        for (int j = kk >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < npad; i += T) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const unsigned a = s_key[i], b = s_key[ixj];
-                    const bool up = (i & kk) == 0;
-                    if ((a > b) == up) {
-                        s_key[i] = b;
-                        s_key[ixj] = a;
-                    }
-                }
-            }
-            __syncthreads();
-        }
+    bitonic_sort_smem<T>(s_key, npad, npad, tid);
+    for (int p = tid; p < npad; p += T) {
+        const unsigned key = s_key[p];
+        s_key[p] = (key == 0xffffffffu) ? 0xffffffffu : tb_encode(key & 0x3fffu);
     }
-    // ---- this thread's P points of its warp's bucket, ordered by the tie-break key -----------
+    __syncthreads();
+    if (npad >= BUCKET) bitonic_sort_smem<T>(s_key, npad, BUCKET, tid);
+    else bitonic_sort_smem<T>(s_key, npad, npad, tid);
+    for (int p = tid; p < n; p += T) {  // valid entries occupy [0, n): padding sorted to the global end in pass 1
+        const unsigned tbk = s_key[p];
+        const unsigned k = tb_decode(tbk);
+        s_sorted[p] = make_float4(__ldg(pts + 3 * (size_t)k), __ldg(pts + 3 * (size_t)k + 1), __ldg(pts + 3 * (size_t)k + 2),
+                                  __uint_as_float(tbk));
+    }
+    __syncthreads();
+
+    // ---- this thread's P points: sorted positions warp*BUCKET + lane*P + j ----------------------
+    const int pos0 = warp * BUCKET + lane * P;
     float px[P], py[P], pz[P], td[P];
-    unsigned tb[P];
-    bool any_valid = false;
-#pragma unroll
-    for (int j = 0; j < P; ++j) {
-        const int pos = warp * (32 * P) + j * 32 + lane;
-        px[j] = py[j] = pz[j] = 0.f;
-        td[j] = -1.0f;
-        tb[j] = 0xffffffffu;
-        if (pos < n) {
-            const unsigned k = s_key[pos] & 0x3fffu;
-            px[j] = s_xyz[3 * k + 0];
-            py[j] = s_xyz[3 * k + 1];
-            pz[j] = s_xyz[3 * k + 2];
-            td[j] = 1e38f;
-            tb[j] = tb_encode(k);
-            any_valid = true;
-        }
-    }
-#pragma unroll
-    for (int a = 0; a < P - 1; ++a) {
-#pragma unroll
-        for (int b = 0; b < P - 1 - a; ++b) {
-            if (tb[b] > tb[b + 1]) {
-                float t;
-                unsigned u;
-                t = px[b]; px[b] = px[b + 1]; px[b + 1] = t;
-                t = py[b]; py[b] = py[b + 1]; py[b + 1] = t;
-                t = pz[b]; pz[b] = pz[b + 1]; pz[b + 1] = t;
-                t = td[b]; td[b] = td[b + 1]; td[b + 1] = t;
-                u = tb[b]; tb[b] = tb[b + 1]; tb[b + 1] = u;
-            }
-        }
-    }
-    // bucket bounding box (empty buckets: +inf/-inf, their gap is +inf and they are always skipped)
     float blo[3] = {INFINITY, INFINITY, INFINITY}, bhi[3] = {-INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
     for (int j = 0; j < P; ++j) {
-        if (td[j] >= 0.f) {
-            blo[0] = fminf(blo[0], px[j]); bhi[0] = fmaxf(bhi[0], px[j]);
-            blo[1] = fminf(blo[1], py[j]); bhi[1] = fmaxf(bhi[1], py[j]);
-            blo[2] = fminf(blo[2], pz[j]); bhi[2] = fmaxf(bhi[2], pz[j]);
+        px[j] = py[j] = pz[j] = 0.f;
+        td[j] = -1.0f;  // padding: can never win, never lowers
+        if (pos0 + j < n) {
+            const float4 v = s_sorted[pos0 + j];
+            px[j] = v.x; py[j] = v.y; pz[j] = v.z;
+            td[j] = 1e38f;
+            blo[0] = fminf(blo[0], v.x); bhi[0] = fmaxf(bhi[0], v.x);
+            blo[1] = fminf(blo[1], v.y); bhi[1] = fmaxf(bhi[1], v.y);
+            blo[2] = fminf(blo[2], v.z); bhi[2] = fmaxf(bhi[2], v.z);
         }
     }
+    // bucket bounding box (empty buckets: +inf/-inf, their gap is +inf and they are always skipped)
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         blo[c] = warp_min_f(blo[c]);
         bhi[c] = warp_max_f(bhi[c]);
     }
-    // initial candidate of the bucket: running minimum 1e38 everywhere -> earliest tie-break key
+    // initial table entry: running minimum 1e38 everywhere -> the bucket's first point in
+    // tie-break order, which is sorted position warp*BUCKET (lane 0, j 0) if the bucket is non-empty
     float wmax = -1.0f;
-    {
-        unsigned hi = 0u, lo = 0u;
-        if (any_valid) {  // tb[0] is this thread's smallest key among its valid points (padding sorts last)
-            hi = __float_as_uint(1e38f);
-            lo = ~tb[0];
-        }
-        unsigned mh;
-        const int L = warp_argmax_key(hi, lo, mh);
-        if (lane == L) {
-            s_hi[0][warp] = mh;
-            s_cand[0][warp] = make_float4(__uint_as_float(lo), px[0], py[0], pz[0]);
-        }
-        if (mh != 0u) wmax = __uint_as_float(mh);
-    }
-    float x1 = s_xyz[0], y1 = s_xyz[1], z1 = s_xyz[2];
+    if (warp * BUCKET < n) wmax = 1e38f;
+    if (lane == 0) s_tab[0][warp] = make_uint2(wmax > 0.f ? __float_as_uint(1e38f) : 0u, (unsigned)min(warp * BUCKET, n - 1));
+
+    // the first pick is original index 0
+    float x1 = __ldg(pts + 0), y1 = __ldg(pts + 1), z1 = __ldg(pts + 2);
     if (tid == 0) {
         out[0] = 0;
         if (oxyz) {
@@ -388,7 +368,7 @@ fps_bucket_kernel(int n, int m, int npad, const float* __restrict__ xyz, int* __
 
     for (int it = 1; it < m; ++it) {
         const int buf = it & 1;
-        // lower bound of every computed distance from the pick to this bucket
+        // lower bound of every computed distance from the pick to a point of this bucket
         const float gx = fmaxf(fmaxf(__fsub_rn(blo[0], x1), __fsub_rn(x1, bhi[0])), 0.f);
         const float gy = fmaxf(fmaxf(__fsub_rn(blo[1], y1), __fsub_rn(y1, bhi[1])), 0.f);
         const float gz = fmaxf(fmaxf(__fsub_rn(blo[2], z1), __fsub_rn(z1, bhi[2])), 0.f);
@@ -401,52 +381,47 @@ fps_bucket_kernel(int n, int m, int npad, const float* __restrict__ xyz, int* __
                 const float d = d2_fma_pattern(px[j], py[j], pz[j], x1, y1, z1);
                 const float d2 = fminf(d, td[j]);
                 td[j] = d2;
-                if (d2 > best) {  // ascending tie-break order within the thread: first maximum wins
+                if (d2 > best) {  // register order == tie-break order: the first maximum wins
                     best = d2;
                     bj = j;
                 }
             }
-            float cx = px[0], cy = py[0], cz = pz[0];
-            unsigned ctb = tb[0];
-#pragma unroll
-            for (int j = 1; j < P; ++j) {
-                if (bj == j) {
-                    cx = px[j]; cy = py[j]; cz = pz[j];
-                    ctb = tb[j];
-                }
+            const bool has = best >= 0.0f;  // false only for lanes holding nothing but padding
+            const unsigned hi = has ? __float_as_uint(best) : 0u;
+            const unsigned mh = warp_max_u32(hi);
+            bool mine = (hi == mh);
+            const unsigned bal = __ballot_sync(kFullMask, mine);
+            if (bal & (bal - 1u)) {  // several lanes share the maximum: explicit tie-break (rare)
+                const unsigned lo = (mine && has) ? ~__float_as_uint(s_sorted[min(pos0 + bj, n - 1)].w) : 0u;
+                const unsigned ml = warp_max_u32(lo);
+                mine = mine && (lo == ml);
+                const unsigned bal2 = __ballot_sync(kFullMask, mine);
+                mine = mine && (lane == __ffs(bal2) - 1);  // all-padding buckets: any single lane
             }
-            unsigned hi = 0u, lo = 0u;
-            if (best >= 0.0f) {
-                hi = __float_as_uint(best);
-                lo = ~ctb;
-            }
-            unsigned mh;
-            const int L = warp_argmax_key(hi, lo, mh);
-            if (lane == L) {
-                s_hi[buf][warp] = mh;
-                s_cand[buf][warp] = make_float4(__uint_as_float(lo), cx, cy, cz);
-            }
+            if (mine) s_tab[buf][warp] = make_uint2(mh, (unsigned)min(pos0 + bj, n - 1));
             wmax = __uint_as_float(mh);  // an active bucket has valid points: mh is a real distance
-        } else if (lane == 0) {
-            s_hi[buf][warp] = s_hi[buf ^ 1][warp];
-            s_cand[buf][warp] = s_cand[buf ^ 1][warp];
+        } else {
+            // carry the cached entry forward; every lane stores the same value (no divergent branch)
+            s_tab[buf][warp] = s_tab[buf ^ 1][warp];
         }
         __syncthreads();
         const bool in = lane < NW;
-        const unsigned h = in ? s_hi[buf][lane] : 0u;
-        const unsigned gh = warp_max_u32(h);
-        unsigned bal = __ballot_sync(kFullMask, in && h == gh);
-        if (__popc(bal) > 1) {
-            const unsigned l = (in && h == gh) ? __float_as_uint(s_cand[buf][lane].x) : 0u;
-            const unsigned gl = warp_max_u32(l);
-            bal = __ballot_sync(kFullMask, in && h == gh && l == gl);
+        const uint2 e = in ? s_tab[buf][lane] : make_uint2(0u, 0u);
+        const unsigned gh = warp_max_u32(e.x);
+        bool top = in && (e.x == gh);
+        const unsigned gbal = __ballot_sync(kFullMask, top);
+        if (gbal & (gbal - 1u)) {  // several buckets share the maximum: explicit tie-break (rare)
+            const unsigned lo = top ? ~__float_as_uint(s_sorted[e.y].w) : 0u;
+            const unsigned gl = warp_max_u32(lo);
+            top = top && (lo == gl);
         }
-        const float4 c = s_cand[buf][__ffs(bal) - 1];
-        x1 = c.y;
-        y1 = c.z;
-        z1 = c.w;
+        const unsigned wpos = warp_max_u32(top ? e.y : 0u);
+        const float4 c = s_sorted[wpos];
+        x1 = c.x;
+        y1 = c.y;
+        z1 = c.z;
         if (tid == 0) {
-            out[it] = (int)tb_decode(~__float_as_uint(c.x));
+            out[it] = (int)tb_decode(__float_as_uint(c.w));
             if (oxyz) {
                 oxyz[3 * it + 0] = x1;
                 oxyz[3 * it + 1] = y1;
@@ -679,8 +654,8 @@ static int launch_bucket(int b, int n, int m, const float* inp, int* out, float*
     auto kern = fps_bucket_kernel<P, T>;
     int npad = 1;
     while (npad < n) npad <<= 1;
-    size_t dyn = (size_t)n * 3 * sizeof(float) + (size_t)npad * sizeof(unsigned);
-    if (dyn > 200 * 1024 || n > 16384) return (int)cudaErrorInvalidValue;
+    size_t dyn = (size_t)n * sizeof(float4) + (size_t)npad * sizeof(unsigned);
+    if (dyn > 220 * 1024 || n > 16384) return (int)cudaErrorInvalidValue;
     if (dyn > 40 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
         if (e != cudaSuccess) return (int)e;
@@ -740,14 +715,18 @@ static FpsPlan plan_fps(int b, int n) {
         p.xyz_smem = (g_cfg_ppt >= 32);
         return p;
     }
-    // single CTA, bucketed (cluster = -1): exact bounding-box pruning, everything in one SM
-    if (n <= 128) return {128, 1, -1, false};
-    if (n <= 256) return {256, 1, -1, false};
-    if (n <= 512) return {512, 1, -1, false};
-    if (n <= 1024) return {1024, 1, -1, false};
-    if (n <= 2048) return {1024, 2, -1, false};
-    if (n <= 4096) return {1024, 4, -1, false};
-    if (n <= 8192 && b >= 64) return {1024, 8, 1, false};
+    // single CTA, register-resident (cluster = 1).  Measured on B200 (profiles/r1_fps_sweep*.json):
+    // 16 warps x P points beat 32 warps x P/2 at every size — the step is bound by the ALU pipe,
+    // the per-warp replicated reduction code and barrier latency, all of which shrink with fewer warps.
+    // The bucketed kernel (cluster = -1) prunes ~75 % of the distance updates but its longer
+    // dependent chain cancels the gain at these sizes; it stays selectable via pn2_set_fps_config.
+    if (n <= 128) return {128, 1, 1, false};
+    if (n <= 256) return {256, 1, 1, false};
+    if (n <= 512) return {512, 1, 1, false};
+    if (n <= 1024) return {512, 2, 1, false};
+    if (n <= 2048) return {512, 4, 1, false};
+    if (n <= 4096) return {512, 8, 1, false};
+    if (n <= 8192 && b > 37) return {512, 16, 1, false};  // too many clouds for 4-CTA clusters to be co-resident
     // cluster: as many CTAs per cloud as keeps all clouds co-resident on the 148 SMs
     int cmax = pow2_floor(148 / (b > 148 ? 148 : b));
     if (cmax > 16) cmax = 16;
@@ -794,14 +773,26 @@ static int fps_dispatch(int b, int n, int m, const float* inp, float* temp, int*
 #define PN2_TRY_BKT(PP, TT) \
     if (plan.ppt == PP && plan.threads == TT) return launch_bucket<PP, TT>(b, n, m, inp, out, new_xyz, st);
         PN2_TRY_BKT(1, 128)
+        PN2_TRY_BKT(2, 128)
+        PN2_TRY_BKT(4, 128)
+        PN2_TRY_BKT(8, 128)
+        PN2_TRY_BKT(16, 128)
+        PN2_TRY_BKT(32, 128)
         PN2_TRY_BKT(1, 256)
+        PN2_TRY_BKT(2, 256)
+        PN2_TRY_BKT(4, 256)
+        PN2_TRY_BKT(8, 256)
+        PN2_TRY_BKT(16, 256)
+        PN2_TRY_BKT(32, 256)
         PN2_TRY_BKT(1, 512)
-        PN2_TRY_BKT(1, 1024)
         PN2_TRY_BKT(2, 512)
-        PN2_TRY_BKT(2, 1024)
         PN2_TRY_BKT(4, 512)
-        PN2_TRY_BKT(4, 1024)
         PN2_TRY_BKT(8, 512)
+        PN2_TRY_BKT(16, 512)
+        PN2_TRY_BKT(1, 1024)
+        PN2_TRY_BKT(2, 1024)
+        PN2_TRY_BKT(4, 1024)
+        PN2_TRY_BKT(8, 1024)
         return (int)cudaErrorInvalidValue;
     }
     if (plan.cluster == 1) {

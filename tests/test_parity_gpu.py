@@ -32,7 +32,8 @@ def N(t):
 FPS_CASES = [
     ("U", 4, 1024, 256), ("U", 2, 100, 50), ("U", 2, 40, 64), ("U", 3, 513, 100), ("D", 2, 1500, 700),
     ("S", 2, 2048, 300), ("S", 2, 3000, 128), ("U", 2, 4096, 512), ("D", 2, 5000, 200), ("U", 1, 8192, 256),
-    ("U", 1, 1, 4), ("U", 2, 127, 127), ("U", 2, 129, 40), ("S", 1, 1025, 64),
+    ("U", 1, 1, 4), ("U", 2, 127, 127), ("U", 2, 129, 40), ("S", 1, 1025, 64), ("D", 2, 8192, 300), ("S", 2, 6000, 200),
+    ("U", 2, 2, 5), ("U", 2, 33, 33), ("D", 3, 64, 64),
 ]
 
 
@@ -45,8 +46,10 @@ def test_fps_matches_oracle(dev, gen, b, n, m):
 
 @pytest.mark.parametrize("cfg", [(512, 2, 2), (512, 1, 4), (512, 4, 2), (512, 8, 4), (1024, 2, 2), (512, 2, 8),
                                  (512, 1, 16), (512, 16, 2), (512, 32, 2), (1024, 4, 1), (512, 8, 1), (512, 16, 1),
-                                 (128, 1, -1), (256, 1, -1), (512, 1, -1), (1024, 1, -1), (512, 2, -1), (1024, 2, -1),
-                                 (512, 4, -1), (1024, 4, -1), (512, 8, -1)])
+                                 (128, 1, -1), (128, 2, -1), (128, 4, -1), (128, 8, -1), (128, 16, -1), (128, 32, -1),
+                                 (256, 1, -1), (256, 2, -1), (256, 4, -1), (256, 8, -1), (256, 16, -1), (256, 32, -1),
+                                 (512, 1, -1), (512, 2, -1), (512, 4, -1), (512, 8, -1), (512, 16, -1),
+                                 (1024, 1, -1), (1024, 2, -1), (1024, 4, -1), (1024, 8, -1)])
 @pytest.mark.parametrize("gen", ["U", "D", "S"])
 def test_fps_every_kernel_variant_matches_oracle(dev, cfg, gen):
     """Force each (threads, points/thread, cluster) kernel variant — register-resident single CTA
