@@ -308,6 +308,11 @@ def run_b200_arm(args, cfg):
     same = bool((sess.h_idx.to(dev) == idx).all()) and bool((sess.h_new_xyz.to(dev) == new_xyz).all())
 
     if rank == 0:
+        import ctypes
+        pt, pp, pc = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        lib.pn2_fps_plan(b, n, ctypes.byref(pt), ctypes.byref(pp), ctypes.byref(pc))
+        kinds = {1: "fps_cta_kernel", -1: "fps_bucket_kernel", 0: "fps_global_kernel"}
+        fps_kernel = f"{kinds.get(pc.value, 'fps_cluster_kernel')}<{pp.value},{pt.value}>" + (f" cluster={pc.value}" if pc.value > 1 else "")
         peak, peak_kind = measured_peaks()
         fps_ms = statistics.mean(t_fps)
         fps_bytes = W.bytes_fps(b, n, m, with_new_xyz=True)
@@ -327,7 +332,7 @@ def run_b200_arm(args, cfg):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": sess.h2d_bytes, "d2h_bytes_per_step": sess.d2h_bytes,
                     "ms_per_step": e2e_ms / args.steps, "outputs_match_device_leg": same},
             "gpu_launches": int(launches),  # this library's kernels inside the two timed regions (3 per step each)
-            "roofline": {"bound": "hbm", "kernel": "fps_cta_kernel<4,1024> (FPS + fused gather_point)", "achieved": achieved,
+            "roofline": {"bound": "hbm", "kernel": fps_kernel + " (FPS + fused gather_point)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_kind": f"of {peak_kind}",
                          "algorithmic_bytes_per_launch": fps_bytes, "ms_per_launch": fps_ms,
                          "note": "FPS is a serial chain of npoint argmax steps: latency/FP32-issue bound, not HBM bound",

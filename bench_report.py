@@ -90,6 +90,7 @@ def fps_sweep(out_path=None):
         cases = [c for c in cases if c[1] <= 8192]
     variants = [(128, 1, 1), (256, 1, 1), (512, 1, 1), (512, 2, 1), (512, 4, 1), (512, 8, 1), (512, 16, 1), (1024, 1, 1),
                 (1024, 2, 1), (1024, 4, 1), (1024, 8, 1)]
+    variants += [(128, p, 1) for p in (2, 4, 8, 16, 32)] + [(256, p, 1) for p in (2, 4, 8, 16, 32)]
     for t, ps in ((128, (1, 2, 4, 8, 16, 32)), (256, (1, 2, 4, 8, 16, 32)), (512, (1, 2, 4, 8, 16)), (1024, (1, 2, 4, 8))):
         variants += [(t, p, -1) for p in ps]
     for C in (2, 4, 8, 16):

@@ -137,6 +137,10 @@ float pn2_ball_threshold(float radius);
 /* tuning override for experiments: threads, points/thread, cluster size of the FPS kernel
  * (cluster 0 = global-scratch fallback); threads = 0 restores the built-in plan */
 void pn2_set_fps_config(int threads, int points_per_thread, int cluster);
+/* the kernel variant pn2_fps would launch for (b, n): threads per CTA, points per thread and
+ * cluster size (1 = one CTA per cloud, >= 2 = thread-block cluster per cloud, -1 = bucketed single
+ * CTA, 0 = global-scratch fallback) */
+int pn2_fps_plan(int b, int n, int* threads, int* points_per_thread, int* cluster);
 /* tuning override: lanes cooperating on one ball query (1,2,4,..,32); 0 restores the heuristic */
 void pn2_set_bq_group(int lanes_per_query);
 

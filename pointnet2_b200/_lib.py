@@ -34,6 +34,7 @@ _SIGNATURES = {
     "pn2_error_string": (ctypes.c_char_p, [c_int]),
     "pn2_launch_count": (c_ulonglong, []),
     "pn2_ball_threshold": (c_float, [c_float]),
+    "pn2_fps_plan": (c_int, [c_int, c_int, _P, _P, _P]),
     "pn2_set_fps_config": (None, [c_int, c_int, c_int]),
     "pn2_set_bq_group": (None, [c_int]),
 }

@@ -80,27 +80,36 @@ __device__ __forceinline__ void st_async_u64(unsigned remote_addr, unsigned long
 }
 
 // ---- per-thread step: update P register-resident points against the last pick ------------------
-template <int P>
+// D = number of distinct reference slots (k mod 512) one thread's points fall into: thread t of a
+// T-thread CTA owns k = t + j*T, so for T < 512 its slots cycle with period D = 512/T.  The scan
+// visits the points in tie-break order (slot ascending, then k ascending): for each slot residue
+// r = j mod D in turn, j ascending — so the strict '>' keeps the reference's winner.
+template <int P, int D = 1>
 __device__ __forceinline__ void fps_step(const float (&px)[P], const float (&py)[P], const float (&pz)[P],
                                          float (&td)[P], float x1, float y1, float z1, float& best, int& bj) {
     best = -1.0f;
     bj = 0;
+    constexpr int DD = (D < P) ? D : P;
 #pragma unroll
-    for (int j = 0; j < P; ++j) {
-        const float d = d2_fma_pattern(px[j], py[j], pz[j], x1, y1, z1);
-        const float d2 = fminf(d, td[j]);  // padding slots carry td = -1 and can never win
-        td[j] = d2;
-        if (d2 > best) {
-            best = d2;
-            bj = j;
+    for (int r = 0; r < DD; ++r) {
+#pragma unroll
+        for (int j = r; j < P; j += DD) {
+            const float d = d2_fma_pattern(px[j], py[j], pz[j], x1, y1, z1);
+            const float d2 = fminf(d, td[j]);  // padding slots carry td = -1 and can never win
+            td[j] = d2;
+            if (d2 > best) {
+                best = d2;
+                bj = j;
+            }
         }
     }
 }
 
 // =================================================================================================
-// One CTA per cloud.  Thread t owns points k = t + j*T (j < P): all of a thread's points share
-// the reference slot k mod 512 when T is a multiple of 512 (or P == 1), so the in-thread strict
-// '>' scan in ascending j reproduces the reference's in-slot order.
+// One CTA per cloud.  Thread t owns points k = t + j*T (j < P).  When T is a multiple of 512 all of
+// a thread's points share the reference slot k mod 512 and the in-thread strict '>' scan in
+// ascending j reproduces the reference's in-slot order; for T < 512 the scan order is permuted
+// (fps_step) so it is still the reference's (slot, k) order.
 // Dynamic shared memory: 3*n floats — a copy of the cloud, so the picked point's coordinates are a
 // 3-word broadcast LDS instead of a global/L2 round trip on the critical path.
 // =================================================================================================
@@ -108,8 +117,9 @@ template <int P, int T>
 __global__ void __launch_bounds__(T, 1)
 fps_cta_kernel(int n, int m, const float* __restrict__ xyz, int* __restrict__ idx_out,
                float* __restrict__ new_xyz) {
-    static_assert(P == 1 || T % 512 == 0, "slot order needs T % 512 == 0 when P > 1");
+    static_assert(T % 512 == 0 || 512 % T == 0, "T must divide or be a multiple of the reference's 512 slots");
     constexpr int NW = T / 32;
+    constexpr int D = (T >= 512) ? 1 : 512 / T;
     __shared__ uint2 s_keys[2][32];
     extern __shared__ float s_xyz[];
 
@@ -151,7 +161,7 @@ fps_cta_kernel(int n, int m, const float* __restrict__ xyz, int* __restrict__ id
     for (int it = 1; it < m; ++it) {
         float best;
         int bj;
-        fps_step<P>(px, py, pz, td, x1, y1, z1, best, bj);
+        fps_step<P, D>(px, py, pz, td, x1, y1, z1, best, bj);
         unsigned hi = 0u, lo = 0u;
         if (best >= 0.0f) {
             hi = __float_as_uint(best);
@@ -716,17 +726,18 @@ static FpsPlan plan_fps(int b, int n) {
         return p;
     }
     // single CTA, register-resident (cluster = 1).  Measured on B200 (profiles/r1_fps_sweep*.json):
-    // 16 warps x P points beat 32 warps x P/2 at every size — the step is bound by the ALU pipe,
-    // the per-warp replicated reduction code and barrier latency, all of which shrink with fewer warps.
+    // few warps with many points each win at every size (4-8 warps; e.g. N=4096: 8 warps x 16 points
+    // 0.313 us/step, 16 x 8: 0.410, 32 x 4: 0.501) — the step is bound by the ALU pipe, the per-warp
+    // replicated reduction code and barrier latency, all of which shrink with fewer warps.
     // The bucketed kernel (cluster = -1) prunes ~75 % of the distance updates but its longer
     // dependent chain cancels the gain at these sizes; it stays selectable via pn2_set_fps_config.
     if (n <= 128) return {128, 1, 1, false};
-    if (n <= 256) return {256, 1, 1, false};
-    if (n <= 512) return {512, 1, 1, false};
-    if (n <= 1024) return {512, 2, 1, false};
-    if (n <= 2048) return {512, 4, 1, false};
-    if (n <= 4096) return {512, 8, 1, false};
-    if (n <= 8192 && b > 37) return {512, 16, 1, false};  // too many clouds for 4-CTA clusters to be co-resident
+    if (n <= 256) return {128, 2, 1, false};
+    if (n <= 512) return {256, 2, 1, false};
+    if (n <= 1024) return {128, 8, 1, false};
+    if (n <= 2048) return {128, 16, 1, false};
+    if (n <= 4096) return {256, 16, 1, false};
+    if (n <= 8192) return {256, 32, 1, false};
     // cluster: as many CTAs per cloud as keeps all clouds co-resident on the 148 SMs
     int cmax = pow2_floor(148 / (b > 148 ? 148 : b));
     if (cmax > 16) cmax = 16;
@@ -797,6 +808,16 @@ static int fps_dispatch(int b, int n, int m, const float* inp, float* temp, int*
     }
     if (plan.cluster == 1) {
         PN2_TRY_CTA(1, 128)
+        PN2_TRY_CTA(2, 128)
+        PN2_TRY_CTA(4, 128)
+        PN2_TRY_CTA(8, 128)
+        PN2_TRY_CTA(16, 128)
+        PN2_TRY_CTA(32, 128)
+        PN2_TRY_CTA(2, 256)
+        PN2_TRY_CTA(4, 256)
+        PN2_TRY_CTA(8, 256)
+        PN2_TRY_CTA(16, 256)
+        PN2_TRY_CTA(32, 256)
         PN2_TRY_CTA(1, 256)
         PN2_TRY_CTA(1, 512)
         PN2_TRY_CTA(2, 512)
@@ -839,6 +860,15 @@ int pn2_fps(int b, int n, int m, const float* inp, float* temp, int* out, void* 
 
 int pn2_fps_gather(int b, int n, int m, const float* inp, int* out, float* new_xyz, void* stream) {
     return pn2::fps_dispatch(b, n, m, inp, nullptr, out, new_xyz, pn2::as_stream(stream));
+}
+
+int pn2_fps_plan(int b, int n, int* threads, int* points_per_thread, int* cluster) {
+    if (b <= 0 || n <= 0) return (int)cudaErrorInvalidValue;
+    const pn2::FpsPlan p = pn2::plan_fps(b, n);
+    if (threads) *threads = p.threads;
+    if (points_per_thread) *points_per_thread = p.ppt;
+    if (cluster) *cluster = p.cluster;
+    return 0;
 }
 
 void pn2_set_fps_config(int threads, int points_per_thread, int cluster) {

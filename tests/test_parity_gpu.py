@@ -46,6 +46,7 @@ def test_fps_matches_oracle(dev, gen, b, n, m):
 
 @pytest.mark.parametrize("cfg", [(512, 2, 2), (512, 1, 4), (512, 4, 2), (512, 8, 4), (1024, 2, 2), (512, 2, 8),
                                  (512, 1, 16), (512, 16, 2), (512, 32, 2), (1024, 4, 1), (512, 8, 1), (512, 16, 1),
+                                 (128, 2, 1), (128, 8, 1), (128, 32, 1), (256, 2, 1), (256, 4, 1), (256, 16, 1), (256, 32, 1),
                                  (128, 1, -1), (128, 2, -1), (128, 4, -1), (128, 8, -1), (128, 16, -1), (128, 32, -1),
                                  (256, 1, -1), (256, 2, -1), (256, 4, -1), (256, 8, -1), (256, 16, -1), (256, 32, -1),
                                  (512, 1, -1), (512, 2, -1), (512, 4, -1), (512, 8, -1), (512, 16, -1),
