@@ -93,6 +93,8 @@ def fps_sweep(out_path=None):
     variants += [(128, p, 1) for p in (2, 4, 8, 16, 32)] + [(256, p, 1) for p in (2, 4, 8, 16, 32)]
     for t, ps in ((128, (1, 2, 4, 8, 16, 32)), (256, (1, 2, 4, 8, 16, 32)), (512, (1, 2, 4, 8, 16)), (1024, (1, 2, 4, 8))):
         variants += [(t, p, -1) for p in ps]
+    for t, ps in ((128, (2, 4, 8, 16, 32)), (256, (2, 4, 8, 16, 32)), (512, (2, 4, 8, 16))):
+        variants += [(t, p, -2) for p in ps]
     for C in (2, 4, 8, 16):
         for (t, p) in [(512, 1), (512, 2), (512, 4), (512, 8), (512, 16), (512, 32), (1024, 2), (1024, 4), (1024, 8)]:
             variants.append((t, p, C))
@@ -102,7 +104,8 @@ def fps_sweep(out_path=None):
         nx = torch.empty((b, m, 3), dtype=torch.float32, device=dev)
         ref = None
         for (t, p, c) in [(0, 0, 0)] + variants:
-            if t and (t * p * abs(c) < n or t * p * abs(c) > (4 if c < 0 else 16) * n or b * abs(c) > 8 * 148):
+            cc = c if c > 0 else 1
+            if t and (t * p * cc < n or t * p * cc > (4 if c < 0 else 16) * n or b * cc > 8 * 148):
                 continue
             lib.pn2_set_fps_config(t, p, c)
             rc = [0]

@@ -190,6 +190,167 @@ fps_cta_kernel(int n, int m, const float* __restrict__ xyz, int* __restrict__ id
 }
 
 // =================================================================================================
+// fps_cta2_kernel — the same one-CTA-per-cloud scheme as fps_cta_kernel with the per-step update
+// restructured around what the profile showed binds it (profiles/r1_microbench_latency.txt):
+//   * packed FP32x2 arithmetic (PTX sub/mul/fma .f32x2 -> SASS FADD2/FMUL2/FFMA2): two points per
+//     instruction for the 6 distance ops, IEEE round-to-nearest per lane, so bit-identical to the
+//     scalar pattern while halving the issue slots the FMA side takes;
+//   * registers hold the points in SCAN order (the reference's tie-break order for this thread), in
+//     NACC contiguous blocks with one running (best, index) accumulator each — the serial
+//     FSETP->FSEL dependency chain of a fat thread becomes NACC independent chains; blocks are merged
+//     in order with a strict '>', which keeps the first maximum in scan order.
+// =================================================================================================
+__device__ __forceinline__ unsigned long long f2_pack(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+template <int P, int T>
+__global__ void __launch_bounds__(T, 1)
+fps_cta2_kernel(int n, int m, const float* __restrict__ xyz, int* __restrict__ idx_out,
+                float* __restrict__ new_xyz) {
+    static_assert(P % 2 == 0, "packed pairs");
+    static_assert(T % 512 == 0 || 512 % T == 0, "T must divide or be a multiple of the reference's 512 slots");
+    constexpr int NW = T / 32;
+    constexpr int D = (T >= 512) ? 1 : 512 / T;  // slot residues per thread
+    constexpr int DD = (D < P) ? D : P;
+    constexpr int Q = P / DD;                    // points per slot residue
+    constexpr int H = P / 2;                     // packed pairs
+    constexpr int NACC = (P >= 16) ? 4 : (P >= 8 ? 2 : 1);
+    constexpr int HB = H / NACC;                 // pairs per accumulator block
+    __shared__ uint2 s_keys[2][32];
+    extern __shared__ float s_xyz[];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cloud = blockIdx.x;
+    const float* __restrict__ pts = xyz + (size_t)cloud * n * 3;
+    int* __restrict__ out = idx_out + (size_t)cloud * m;
+    float* __restrict__ oxyz = new_xyz ? new_xyz + (size_t)cloud * m * 3 : nullptr;
+
+    for (int e = tid; e < 3 * n; e += T) s_xyz[e] = pts[e];
+    __syncthreads();
+    const float* __restrict__ src = s_xyz;
+
+    // scan-order element e <-> strided point j = (e % Q) * DD + e / Q, k = tid + j*T
+    unsigned long long X[H], Y[H], Z[H];
+    float td[P];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        float c[2][3];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int e = 2 * h + u;
+            const int j = (e % Q) * DD + e / Q;
+            const int k = tid + j * T;
+            c[u][0] = c[u][1] = c[u][2] = 0.0f;
+            td[e] = -1.0f;  // padding: can never win
+            if (k < n) {
+                c[u][0] = src[3 * k + 0];
+                c[u][1] = src[3 * k + 1];
+                c[u][2] = src[3 * k + 2];
+                td[e] = 1e38f;
+            }
+        }
+        X[h] = f2_pack(c[0][0], c[1][0]);
+        Y[h] = f2_pack(c[0][1], c[1][1]);
+        Z[h] = f2_pack(c[0][2], c[1][2]);
+    }
+
+    float x1 = src[0], y1 = src[1], z1 = src[2];
+    if (tid == 0) {
+        out[0] = 0;
+        if (oxyz) {
+            oxyz[0] = x1;
+            oxyz[1] = y1;
+            oxyz[2] = z1;
+        }
+    }
+
+    for (int it = 1; it < m; ++it) {
+        const unsigned long long X1 = f2_pack(x1, x1), Y1 = f2_pack(y1, y1), Z1 = f2_pack(z1, z1);
+        float best[NACC];
+        int be[NACC];
+#pragma unroll
+        for (int a = 0; a < NACC; ++a) {
+            best[a] = -1.0f;
+            be[a] = 0;
+#pragma unroll
+            for (int hh = 0; hh < HB; ++hh) {
+                const int h = a * HB + hh;
+                const unsigned long long dx = f2_sub(X[h], X1), dy = f2_sub(Y[h], Y1), dz = f2_sub(Z[h], Z1);
+                const unsigned long long d = f2_fma(dz, dz, f2_fma(dx, dx, f2_mul(dy, dy)));
+                float d0, d1;
+                f2_unpack(d, d0, d1);
+                const float a0 = fminf(d0, td[2 * h]);
+                td[2 * h] = a0;
+                if (a0 > best[a]) {
+                    best[a] = a0;
+                    be[a] = 2 * h;
+                }
+                const float a1 = fminf(d1, td[2 * h + 1]);
+                td[2 * h + 1] = a1;
+                if (a1 > best[a]) {
+                    best[a] = a1;
+                    be[a] = 2 * h + 1;
+                }
+            }
+        }
+#pragma unroll
+        for (int a = 1; a < NACC; ++a) {  // in block order, strict '>': the first maximum in scan order survives
+            if (best[a] > best[0]) {
+                best[0] = best[a];
+                be[0] = be[a];
+            }
+        }
+        unsigned hi = 0u, lo = 0u;
+        if (best[0] >= 0.0f) {
+            const int e = be[0];
+            const int j = (e % Q) * DD + e / Q;  // Q, DD are powers of two
+            hi = __float_as_uint(best[0]);
+            lo = ~tb_encode((unsigned)(tid + j * T));
+        }
+        warp_max_pair(hi, lo);
+        const int buf = it & 1;
+        if (lane == 0) s_keys[buf][warp] = make_uint2(lo, hi);
+        __syncthreads();
+        uint2 ent = (lane < NW) ? s_keys[buf][lane] : make_uint2(0u, 0u);
+        unsigned gh = ent.y, gl = ent.x;
+        warp_max_pair(gh, gl);
+        const int old = (int)tb_decode(~gl);
+        x1 = src[3 * old + 0];
+        y1 = src[3 * old + 1];
+        z1 = src[3 * old + 2];
+        if (tid == 0) {
+            out[it] = old;
+            if (oxyz) {
+                oxyz[3 * it + 0] = x1;
+                oxyz[3 * it + 1] = y1;
+                oxyz[3 * it + 2] = z1;
+            }
+        }
+    }
+}
+
+// =================================================================================================
 // Bucketed FPS, one CTA per cloud (the default for n <= 8192): EXACT, but most of the work of a
 // step is pruned.
 //
@@ -660,6 +821,19 @@ static int launch_cta(int b, int n, int m, const float* inp, int* out, float* ne
 }
 
 template <int P, int T>
+static int launch_cta2(int b, int n, int m, const float* inp, int* out, float* new_xyz, cudaStream_t st) {
+    auto kern = fps_cta2_kernel<P, T>;
+    size_t dyn = (size_t)n * 3 * sizeof(float);
+    if (dyn > 200 * 1024) return (int)cudaErrorInvalidValue;
+    if (dyn > 40 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return (int)e;
+    }
+    kern<<<b, T, dyn, st>>>(n, m, inp, out, new_xyz);
+    return finish_launch();
+}
+
+template <int P, int T>
 static int launch_bucket(int b, int n, int m, const float* inp, int* out, float* new_xyz, cudaStream_t st) {
     auto kern = fps_bucket_kernel<P, T>;
     int npad = 1;
@@ -706,7 +880,7 @@ static int launch_cluster(int C, int b, int n, int m, const float* inp, int* out
 }
 
 struct FpsPlan {
-    int threads, ppt, cluster;  // cluster == 0: global-scratch fallback; 1: single CTA; -1: bucketed single CTA
+    int threads, ppt, cluster;  // cluster == 0: global-scratch fallback; 1: single CTA; -1: bucketed single CTA; -2: single CTA, packed-math variant
     bool xyz_smem;
 };
 
@@ -776,9 +950,28 @@ static int fps_dispatch(int b, int n, int m, const float* inp, float* temp, int*
     if (b == 0 || m == 0) return 0;
     if (!inp || !out) return (int)cudaErrorInvalidValue;
     FpsPlan plan = plan_fps(b, n);
-    if (plan.cluster >= 1 || plan.cluster == -1) {
+    if (plan.cluster >= 1 || plan.cluster == -1 || plan.cluster == -2) {
         long long cap = (long long)plan.threads * plan.ppt * (plan.cluster < 0 ? 1 : plan.cluster);
         if (cap < n) return (int)cudaErrorInvalidValue;
+    }
+    if (plan.cluster == -2) {
+#define PN2_TRY_CTA2(PP, TT) \
+    if (plan.ppt == PP && plan.threads == TT) return launch_cta2<PP, TT>(b, n, m, inp, out, new_xyz, st);
+        PN2_TRY_CTA2(2, 128)
+        PN2_TRY_CTA2(4, 128)
+        PN2_TRY_CTA2(8, 128)
+        PN2_TRY_CTA2(16, 128)
+        PN2_TRY_CTA2(32, 128)
+        PN2_TRY_CTA2(2, 256)
+        PN2_TRY_CTA2(4, 256)
+        PN2_TRY_CTA2(8, 256)
+        PN2_TRY_CTA2(16, 256)
+        PN2_TRY_CTA2(32, 256)
+        PN2_TRY_CTA2(2, 512)
+        PN2_TRY_CTA2(4, 512)
+        PN2_TRY_CTA2(8, 512)
+        PN2_TRY_CTA2(16, 512)
+        return (int)cudaErrorInvalidValue;
     }
     if (plan.cluster == -1) {
 #define PN2_TRY_BKT(PP, TT) \

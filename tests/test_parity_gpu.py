@@ -47,6 +47,8 @@ def test_fps_matches_oracle(dev, gen, b, n, m):
 @pytest.mark.parametrize("cfg", [(512, 2, 2), (512, 1, 4), (512, 4, 2), (512, 8, 4), (1024, 2, 2), (512, 2, 8),
                                  (512, 1, 16), (512, 16, 2), (512, 32, 2), (1024, 4, 1), (512, 8, 1), (512, 16, 1),
                                  (128, 2, 1), (128, 8, 1), (128, 32, 1), (256, 2, 1), (256, 4, 1), (256, 16, 1), (256, 32, 1),
+                                 (128, 2, -2), (128, 4, -2), (128, 8, -2), (128, 16, -2), (128, 32, -2), (256, 2, -2), (256, 4, -2),
+                                 (256, 8, -2), (256, 16, -2), (256, 32, -2), (512, 2, -2), (512, 4, -2), (512, 8, -2), (512, 16, -2),
                                  (128, 1, -1), (128, 2, -1), (128, 4, -1), (128, 8, -1), (128, 16, -1), (128, 32, -1),
                                  (256, 1, -1), (256, 2, -1), (256, 4, -1), (256, 8, -1), (256, 16, -1), (256, 32, -1),
                                  (512, 1, -1), (512, 2, -1), (512, 4, -1), (512, 8, -1), (512, 16, -1),
@@ -57,7 +59,7 @@ def test_fps_every_kernel_variant_matches_oracle(dev, cfg, gen):
     (cluster 1), bucketed single CTA (cluster -1), the DSMEM cluster exchange (cluster >= 2) and
     the shared-memory-coordinate variant — on a cloud that fits it."""
     threads, ppt, cluster = cfg
-    cap = threads * ppt * abs(cluster)
+    cap = threads * ppt * (cluster if cluster > 0 else 1)
     n = min(cap, 6000) - 3
     xyz = W.DISTRIBUTIONS[gen](2, n, 32)
     lib = _lib.load()
