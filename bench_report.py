@@ -138,7 +138,7 @@ def bq_sweep(out_path=None):
     torch, lib, dev, flush = _setup()
     from pointnet2_b200 import workloads as W
     rows = []
-    cases = [("U", 32, 4096, 1024, 0.1, 32), ("S", 32, 1024, 512, 0.1, 16), ("S", 32, 1024, 512, 0.4, 128),
+    cases = [("U", 32, 4096, 1024, 0.001, 32), ("U", 32, 4096, 1024, 0.1, 32), ("S", 32, 1024, 512, 0.1, 16), ("S", 32, 1024, 512, 0.4, 128),
              ("S", 32, 512, 128, 0.8, 128), ("D", 2, 8192, 1024, 0.1, 32), ("D", 16, 8192, 1024, 0.1, 32),
              ("U", 8, 16384, 4096, 0.1, 32), ("U", 1, 65536, 16384, 0.1, 32)]
     for (gen, b, n, m, r, s) in cases:

@@ -27,21 +27,51 @@
 namespace pn2 {
 
 constexpr int kBqThreads = 256;
-constexpr int kBqTile = 2048;  // data points per shared-memory tile (32 KB as float4)
-constexpr int kBqUnroll = 4;
+constexpr int kBqTile = 2048;             // data points per shared-memory tile
+constexpr int kBqPairs = kBqTile / 2;     // stored as pairs: (x0,x1,y0,y1) + (z0,z1)
+constexpr int kBqUnroll = 2;              // pairs per lane per step (4 points)
+
+// packed FP32x2 arithmetic (SASS FADD2 / FMUL2 / FFMA2): two points per instruction, IEEE
+// round-to-nearest per half, i.e. bit-identical to the scalar contraction pattern
+__device__ __forceinline__ unsigned long long bq_pack(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void bq_unpack(unsigned long long v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long bq_sub2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long bq_mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long bq_fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
 
 template <int G>
 __global__ void __launch_bounds__(kBqThreads)
 ball_query_kernel(int n, int m, float thr, int nsample, const float* __restrict__ xyz1,
                   const float* __restrict__ xyz2, int* __restrict__ idx, int* __restrict__ pts_cnt) {
-    constexpr int QPB = kBqThreads / G;  // queries per CTA
-    constexpr int STEP = G * kBqUnroll;  // data points consumed per unrolled step
-    __shared__ float4 s_pts[kBqTile + 32 * kBqUnroll];
+    constexpr int QPB = kBqThreads / G;      // queries per CTA
+    constexpr int STEP = G * kBqUnroll;      // pairs consumed per unrolled step by one group
+    // pair layout: s_xy[i] = (x0, x1, y0, y1) of points 2i, 2i+1; s_z[i] = (z0, z1)
+    __shared__ ulonglong2 s_xy[kBqPairs + 32 * kBqUnroll];
+    __shared__ unsigned long long s_z[kBqPairs + 32 * kBqUnroll];
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int g = tid % G;                     // lane within the group
     const int gbase = lane - g;                // first lane of this group within the warp
     const unsigned gmask_all = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << gbase);
+    const unsigned lt_mask = (1u << lane) - 1u;
     const int cloud = blockIdx.y;
     const int q = blockIdx.x * QPB + tid / G;
     const bool valid = q < m;
@@ -54,56 +84,64 @@ ball_query_kernel(int n, int m, float thr, int nsample, const float* __restrict_
         qy = qp[1];
         qz = qp[2];
     }
+    const unsigned long long QX = bq_pack(qx, qx), QY = bq_pack(qy, qy), QZ = bq_pack(qz, qz);
     int* __restrict__ row = idx + ((size_t)cloud * m + (valid ? q : 0)) * nsample;
 
     int cnt = valid ? 0 : nsample;  // out-of-range groups count as already full
-    int first = 0;
 
     for (int base = 0; base < n; base += kBqTile) {
         const int tn = min(kBqTile, n - base);
-        const int tn_pad = ((tn + STEP - 1) / STEP) * STEP;
+        const int tp = (tn + 1) >> 1;                              // pairs holding real points
+        const int tp_pad = ((tp + STEP - 1) / STEP) * STEP;
         // (the __syncthreads_and at the bottom of the previous iteration guarantees the previous
         //  tile is fully consumed before it is overwritten)
-        for (int p = tid; p < tn_pad; p += kBqThreads) {
-            float4 v = make_float4(1e30f, 1e30f, 1e30f, 0.f);  // padding: far away, never a hit
+        float* sxy = reinterpret_cast<float*>(s_xy);
+        float* sz = reinterpret_cast<float*>(s_z);
+        for (int p = tid; p < 2 * tp_pad; p += kBqThreads) {
+            float x = 1e30f, y = 1e30f, z = 1e30f;  // padding: far away, never a hit
             if (p < tn) {
-                const float* s = data + (size_t)(base + p) * 3;
-                v.x = s[0];
-                v.y = s[1];
-                v.z = s[2];
+                const float* src = data + (size_t)(base + p) * 3;
+                x = src[0];
+                y = src[1];
+                z = src[2];
             }
-            s_pts[p] = v;
+            const int pi = p >> 1, par = p & 1;
+            sxy[4 * pi + par] = x;
+            sxy[4 * pi + 2 + par] = y;
+            sz[2 * pi + par] = z;
         }
         __syncthreads();
 
         bool warp_done = __all_sync(kFullMask, cnt >= nsample);
-        for (int p = 0; p < tn_pad && !warp_done; p += STEP) {
-            bool hit[kBqUnroll];
+        for (int p = 0; p < tp_pad && !warp_done; p += STEP) {
+            bool h[kBqUnroll][2];
             bool any = false;
 #pragma unroll
             for (int u = 0; u < kBqUnroll; ++u) {
-                const float4 v = s_pts[p + u * G + g];
-                const float d2 = d2_fma_pattern(qx, qy, qz, v.x, v.y, v.z);
-                hit[u] = !(d2 > thr);
-                any |= hit[u];
+                const ulonglong2 xy = s_xy[p + u * G + g];
+                const unsigned long long zz = s_z[p + u * G + g];
+                const unsigned long long dx = bq_sub2(QX, xy.x), dy = bq_sub2(QY, xy.y), dz = bq_sub2(QZ, zz);
+                const unsigned long long d = bq_fma2(dz, dz, bq_fma2(dx, dx, bq_mul2(dy, dy)));
+                float d0, d1;
+                bq_unpack(d, d0, d1);
+                h[u][0] = !(d0 > thr);
+                h[u][1] = !(d1 > thr);
+                any |= h[u][0] | h[u][1];
             }
             if (__any_sync(kFullMask, any && (cnt < nsample))) {
 #pragma unroll
                 for (int u = 0; u < kBqUnroll; ++u) {
-                    const int k = base + p + u * G + g;
-                    const bool h = hit[u] && (k < n) && (cnt < nsample);
-                    const unsigned bal = __ballot_sync(kFullMask, h);
-                    const unsigned gm = bal & gmask_all;
-                    if (bal != 0u) {
-                        // first hit of the row: every lane of the group learns its index
-                        const int src_lane = gm ? (__ffs(gm) - 1) : lane;
-                        const int k_first = __shfl_sync(kFullMask, k, src_lane);
-                        if (gm != 0u) {
-                            if (cnt == 0) first = k_first;
-                            const int rank = __popc(gm & ((1u << lane) - 1u));
-                            if (h && cnt + rank < nsample) row[cnt + rank] = k;
-                            cnt = min(cnt + __popc(gm), nsample);
-                        }
+                    const int k0 = base + 2 * (p + u * G + g);
+                    const bool a0 = h[u][0] && (k0 < n) && (cnt < nsample);
+                    const bool a1 = h[u][1] && (k0 + 1 < n) && (cnt < nsample);
+                    const unsigned b0 = __ballot_sync(kFullMask, a0), b1 = __ballot_sync(kFullMask, a1);
+                    const unsigned g0 = b0 & gmask_all, g1 = b1 & gmask_all;
+                    if (g0 | g1) {  // hits in this group: emit them in index order (lane, then parity)
+                        const int r0 = cnt + __popc(g0 & lt_mask) + __popc(g1 & lt_mask);
+                        if (a0 && r0 < nsample) row[r0] = k0;
+                        const int r1 = r0 + (a0 ? 1 : 0);
+                        if (a1 && r1 < nsample) row[r1] = k0 + 1;
+                        cnt = min(cnt + __popc(g0) + __popc(g1), nsample);
                     }
                 }
                 warp_done = __all_sync(kFullMask, cnt >= nsample);
@@ -113,7 +151,10 @@ ball_query_kernel(int n, int m, float thr, int nsample, const float* __restrict_
     }
 
     if (valid) {
-        // pad the tail of the row with the first hit (zeros if there was none)
+        // pad the tail of the row with the first hit (zeros if there was none); the first hit was
+        // written by a lane of this warp: make it visible, then read it back through L2
+        __syncwarp(gmask_all);
+        const int first = (cnt > 0) ? __ldcg(row) : 0;
         for (int l = cnt + g; l < nsample; l += G) row[l] = first;
         if (g == 0) pts_cnt[(size_t)cloud * m + q] = cnt;
     }

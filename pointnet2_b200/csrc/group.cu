@@ -64,35 +64,111 @@ group_point_vec4_kernel(int n, int c4, IndexT rows_per_cloud, IndexT total_vec, 
     }
 }
 
-// ---- group_point, general path: any c (e.g. 3).  One thread per 4 consecutive output floats ----
-template <typename IndexT>
+// ---- group_point general path and the fused sample_and_group tail: LPR lanes per output row ----
+// Row r of cloud `blockIdx.y` is the (3+c)- or c-wide output row of one (centroid, sample) pair:
+//   HAS_XYZ: out[r, xyz_lo..xyz_lo+3) = xyz[a] - new_xyz[r / nsample]   (also to grouped_xyz if given)
+//            out[r, feat_lo..feat_lo+c) = points[a]                      a = idx[r]
+//   else   : out[r, 0..c) = points[a]
+// LPR consecutive lanes own one row and walk its channels with stride LPR, so a warp's loads and
+// stores are runs of consecutive 4-byte words (full sectors) whatever the row width; the per-row
+// index/centroid loads are broadcasts.  No per-element division or branching.
+template <int LPR, bool HAS_XYZ>
 __global__ void __launch_bounds__(kCopyThreads)
-group_point_scalar_kernel(int n, int c, IndexT rows_per_cloud, IndexT total, const float* __restrict__ points,
-                          const int* __restrict__ idx, float* __restrict__ out) {
-    const IndexT stride = (IndexT)gridDim.x * kCopyThreads * 4;
-    for (IndexT e0 = ((IndexT)blockIdx.x * kCopyThreads + threadIdx.x) * 4; e0 < total; e0 += stride) {
-        IndexT row = e0 / (IndexT)c;
-        int l = (int)(e0 - row * (IndexT)c);
-        float v[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            v[t] = 0.f;
-            if (e0 + t < total) {
-                const IndexT cloud = row / rows_per_cloud;
-                const int a = __ldg(idx + row);
-                v[t] = __ldg(points + ((size_t)cloud * n + a) * c + l);
-            }
-            if (++l == c) {
-                l = 0;
-                ++row;
+group_rows_kernel(int n, int c, int nsample, unsigned rows_per_cloud, const float* __restrict__ xyz,
+                  const float* __restrict__ new_xyz, const float* __restrict__ points,
+                  const int* __restrict__ idx, int xyz_lo, int feat_lo, float* __restrict__ out,
+                  float* __restrict__ grouped_xyz) {
+    constexpr int RPW = 32 / LPR;  // rows per warp per pass
+    const int lane = threadIdx.x & 31, g = lane % LPR, sub = lane / LPR;
+    const unsigned cloud = blockIdx.y;
+    const int w = c + (HAS_XYZ ? 3 : 0);
+    const unsigned warps = (gridDim.x * kCopyThreads) >> 5;
+    const unsigned warp = (blockIdx.x * kCopyThreads + threadIdx.x) >> 5;
+    const size_t cloud_row0 = (size_t)cloud * rows_per_cloud;
+    const int* __restrict__ cidx = idx + cloud_row0;
+    const float* __restrict__ cpts = points ? points + (size_t)cloud * n * c : nullptr;
+    const float* __restrict__ cxyz = HAS_XYZ ? xyz + (size_t)cloud * n * 3 : nullptr;
+    for (unsigned r = warp * RPW + sub; r < rows_per_cloud; r += warps * RPW) {
+        const int a = __ldg(cidx + r);
+        float* __restrict__ dst = out + (cloud_row0 + r) * w;
+        if (HAS_XYZ) {
+            if (g < 3) {
+                const size_t ctr = (size_t)cloud * (rows_per_cloud / (unsigned)nsample) + r / (unsigned)nsample;  // global centroid index
+                const float v = __fsub_rn(__ldg(cxyz + (size_t)a * 3 + g), __ldg(new_xyz + ctr * 3 + g));
+                __stcs(dst + xyz_lo + g, v);
+                if (grouped_xyz) __stcs(grouped_xyz + (cloud_row0 + r) * 3 + g, v);
             }
         }
-        if (e0 + 3 < total) {
-            st_stream_f4(reinterpret_cast<float4*>(out + e0), make_float4(v[0], v[1], v[2], v[3]));
-        } else {
-            for (int t = 0; t < 4 && e0 + t < total; ++t) out[e0 + t] = v[t];
+        if (c > 0) {
+            const float* __restrict__ src = cpts + (size_t)a * c;
+            float* __restrict__ d = dst + feat_lo;
+#pragma unroll 4
+            for (int l = g; l < c; l += LPR) __stcs(d + l, __ldg(src + l));
         }
     }
+}
+
+// Narrow rows (w <= 4 floats, e.g. group_point(xyz) and the C=0 sample_and_group tail): one thread
+// per output row — the per-row index/centroid work is the cost, not the copy.
+template <bool HAS_XYZ>
+__global__ void __launch_bounds__(kCopyThreads)
+group_narrow_kernel(int n, int c, int nsample, unsigned rows_per_cloud, const float* __restrict__ xyz,
+                    const float* __restrict__ new_xyz, const float* __restrict__ points,
+                    const int* __restrict__ idx, float* __restrict__ out, float* __restrict__ grouped_xyz) {
+    const unsigned cloud = blockIdx.y;
+    const size_t cloud_row0 = (size_t)cloud * rows_per_cloud;
+    const int* __restrict__ cidx = idx + cloud_row0;
+    const unsigned m = rows_per_cloud / (unsigned)nsample;
+    for (unsigned r = blockIdx.x * kCopyThreads + threadIdx.x; r < rows_per_cloud; r += gridDim.x * kCopyThreads) {
+        const int a = __ldg(cidx + r);
+        if (HAS_XYZ) {  // c == 0: the row is the centred xyz
+            const float* __restrict__ s = xyz + ((size_t)cloud * n + a) * 3;
+            const float* __restrict__ ctr = new_xyz + ((size_t)cloud * m + r / (unsigned)nsample) * 3;
+            const float v0 = __fsub_rn(__ldg(s), __ldg(ctr)), v1 = __fsub_rn(__ldg(s + 1), __ldg(ctr + 1)),
+                        v2 = __fsub_rn(__ldg(s + 2), __ldg(ctr + 2));
+            float* __restrict__ d = out + (cloud_row0 + r) * 3;
+            __stcs(d, v0); __stcs(d + 1, v1); __stcs(d + 2, v2);
+            if (grouped_xyz) {
+                float* __restrict__ gq = grouped_xyz + (cloud_row0 + r) * 3;
+                __stcs(gq, v0); __stcs(gq + 1, v1); __stcs(gq + 2, v2);
+            }
+        } else {
+            const float* __restrict__ s = points + ((size_t)cloud * n + a) * c;
+            float* __restrict__ d = out + (cloud_row0 + r) * c;
+            for (int l = 0; l < c; ++l) __stcs(d + l, __ldg(s + l));
+        }
+    }
+}
+
+template <bool HAS_XYZ>
+static int launch_group_rows(int b, int n, int c, int m, int nsample, const float* xyz, const float* new_xyz,
+                             const float* points, const int* idx, int xyz_lo, int feat_lo, float* out,
+                             float* grouped_xyz, cudaStream_t st) {
+    const unsigned rpc = (unsigned)m * (unsigned)nsample;
+    const int w = c + (HAS_XYZ ? 3 : 0);
+    if (w <= 4 && (!HAS_XYZ || c == 0)) {
+        unsigned gx = (rpc + kCopyThreads - 1) / kCopyThreads;
+        const unsigned cap = (148u * 16u + b - 1) / b;
+        if (gx > cap) gx = cap;
+        group_narrow_kernel<HAS_XYZ><<<dim3(gx, b, 1), kCopyThreads, 0, st>>>(n, c, nsample, rpc, xyz, new_xyz, points, idx, out,
+                                                                                grouped_xyz);
+        return finish_launch();
+    }
+    const int lpr = w <= 4 ? 4 : (w <= 8 ? 8 : (w <= 16 ? 16 : 32));
+    const unsigned rows_per_block = (kCopyThreads / 32) * (32 / lpr);
+    unsigned gx = (rpc + rows_per_block - 1) / rows_per_block;
+    const unsigned cap = (148u * 32u + b - 1) / b;  // enough CTAs to fill the machine, then grid-stride
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, b, 1);
+#define PN2_GROUP_ROWS(L) \
+    group_rows_kernel<L, HAS_XYZ><<<grid, kCopyThreads, 0, st>>>(n, c, nsample, rpc, xyz, new_xyz, points, idx, xyz_lo, feat_lo, out, grouped_xyz)
+    if (lpr == 4) PN2_GROUP_ROWS(4);
+    else if (lpr == 8) PN2_GROUP_ROWS(8);
+    else if (lpr == 16) PN2_GROUP_ROWS(16);
+    else PN2_GROUP_ROWS(32);
+#undef PN2_GROUP_ROWS
+    return finish_launch();
 }
 
 // ---- group_point_grad: atomic scatter-add (vector red.global.add.v4.f32 when c % 4 == 0) -------
@@ -124,53 +200,6 @@ group_point_grad_scalar_kernel(int n, int c, IndexT rows_per_cloud, IndexT total
         const IndexT cloud = row / rows_per_cloud;
         const int a = __ldg(idx + row);
         atomicAdd(grad_points + ((size_t)cloud * n + a) * c + l, __ldcs(grad_out + e));
-    }
-}
-
-// ---- fused sample_and_group tail -----------------------------------------------------------------
-// out[row, :] = xyz_first ? [xyz[a]-ctr, points[a]] : [points[a], xyz[a]-ctr]   (a = idx[row],
-// ctr = new_xyz[row / nsample]); optional grouped_xyz[row,:] = xyz[a]-ctr.
-// One thread per 4 consecutive floats of the flat (rows x (3+c)) output.
-template <typename IndexT>
-__global__ void __launch_bounds__(kCopyThreads)
-group_concat_kernel(int n, int c, int nsample, IndexT rows_per_cloud, IndexT total, const float* __restrict__ xyz,
-                    const float* __restrict__ new_xyz, const float* __restrict__ points,
-                    const int* __restrict__ idx, int xyz_first, float* __restrict__ out,
-                    float* __restrict__ grouped_xyz) {
-    const int w = c + 3;
-    const int xyz_lo = xyz_first ? 0 : c;  // channel range [xyz_lo, xyz_lo+3) holds the centred xyz
-    const IndexT stride = (IndexT)gridDim.x * kCopyThreads * 4;
-    for (IndexT e0 = ((IndexT)blockIdx.x * kCopyThreads + threadIdx.x) * 4; e0 < total; e0 += stride) {
-        IndexT row = e0 / (IndexT)w;
-        int l = (int)(e0 - row * (IndexT)w);
-        float v[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            v[t] = 0.f;
-            if (e0 + t < total) {
-                const IndexT cloud = row / rows_per_cloud;
-                const int a = __ldg(idx + row);
-                const int lx = l - xyz_lo;
-                if (lx >= 0 && lx < 3) {
-                    const float ctr = __ldg(new_xyz + (size_t)(row / (IndexT)nsample) * 3 + lx);
-                    const float val = __fsub_rn(__ldg(xyz + ((size_t)cloud * n + a) * 3 + lx), ctr);
-                    v[t] = val;
-                    if (grouped_xyz) grouped_xyz[(size_t)row * 3 + lx] = val;
-                } else {
-                    const int lp = xyz_first ? l - 3 : l;
-                    v[t] = __ldg(points + ((size_t)cloud * n + a) * c + lp);
-                }
-            }
-            if (++l == w) {
-                l = 0;
-                ++row;
-            }
-        }
-        if (e0 + 3 < total) {
-            st_stream_f4(reinterpret_cast<float4*>(out + e0), make_float4(v[0], v[1], v[2], v[3]));
-        } else {
-            for (int t = 0; t < 4 && e0 + t < total; ++t) out[e0 + t] = v[t];
-        }
     }
 }
 
@@ -280,13 +309,8 @@ int pn2_group_point(int b, int n, int c, int m, int nsample, const float* points
             group_point_vec4_kernel<unsigned long long><<<grid, kCopyThreads, 0, st>>>(
                 n, c / 4, rpc, tv, (const float4*)points, idx, (float4*)out);
     } else {
-        const unsigned grid = grid_for((total + 3) / 4, kCopyThreads);
-        if (total < (1ull << 31) && aligned16(out))
-            group_point_scalar_kernel<unsigned><<<grid, kCopyThreads, 0, st>>>(n, c, (unsigned)rpc, (unsigned)total, points, idx, out);
-        else if (aligned16(out))
-            group_point_scalar_kernel<unsigned long long><<<grid, kCopyThreads, 0, st>>>(n, c, rpc, total, points, idx, out);
-        else
-            return (int)cudaErrorMisalignedAddress;  // outputs come from the allocator: always 256-byte aligned
+        if (rpc >= (1ull << 32) || b > 65535) return (int)cudaErrorInvalidValue;
+        return launch_group_rows<false>(b, n, c, m, nsample, nullptr, nullptr, points, idx, 0, 0, out, nullptr, st);
     }
     return finish_launch();
 }
@@ -325,21 +349,13 @@ int pn2_group_concat(int b, int n, int c, int m, int nsample, const float* xyz, 
                      void* stream) {
     using namespace pn2;
     if (b < 0 || n <= 0 || c < 0 || m < 0 || nsample < 0) return (int)cudaErrorInvalidValue;
-    const unsigned long long rows = (unsigned long long)b * m * nsample;
-    const unsigned long long total = rows * (unsigned long long)(c + 3);
-    if (total == 0) return 0;
-    if (!xyz || !new_xyz || !idx || !out || (c > 0 && !points)) return (int)cudaErrorInvalidValue;
-    if (!aligned16(out)) return (int)cudaErrorMisalignedAddress;
-    cudaStream_t st = as_stream(stream);
     const unsigned long long rpc = (unsigned long long)m * nsample;
-    const unsigned grid = grid_for((total + 3) / 4, kCopyThreads);
-    if (total < (1ull << 31))
-        group_concat_kernel<unsigned><<<grid, kCopyThreads, 0, st>>>(n, c, nsample, (unsigned)rpc, (unsigned)total, xyz, new_xyz,
-                                                                      points, idx, xyz_first, out, grouped_xyz);
-    else
-        group_concat_kernel<unsigned long long><<<grid, kCopyThreads, 0, st>>>(n, c, nsample, rpc, total, xyz, new_xyz, points, idx,
-                                                                                xyz_first, out, grouped_xyz);
-    return finish_launch();
+    if (b == 0 || rpc == 0) return 0;
+    if (!xyz || !new_xyz || !idx || !out || (c > 0 && !points)) return (int)cudaErrorInvalidValue;
+    if (rpc >= (1ull << 32) || b > 65535) return (int)cudaErrorInvalidValue;
+    const int xyz_lo = xyz_first ? 0 : c, feat_lo = xyz_first ? 3 : 0;
+    return launch_group_rows<true>(b, n, c, m, nsample, xyz, new_xyz, points, idx, xyz_lo, feat_lo, out, grouped_xyz,
+                                   as_stream(stream));
 }
 
 int pn2_selection_sort(int b, int n, int m, int k, const float* dist, int* outi, float* out, void* stream) {
