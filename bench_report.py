@@ -95,6 +95,8 @@ def fps_sweep(out_path=None):
         variants += [(t, p, -1) for p in ps]
     for t, ps in ((128, (2, 4, 8, 16, 32)), (256, (2, 4, 8, 16, 32)), (512, (2, 4, 8, 16))):
         variants += [(t, p, -2) for p in ps]
+    for t, ps in ((128, (4, 8, 16, 32)), (256, (4, 8, 16, 32)), (512, (4, 8, 16))):
+        variants += [(t, p, -3) for p in ps]
     for C in (2, 4, 8, 16):
         for (t, p) in [(512, 1), (512, 2), (512, 4), (512, 8), (512, 16), (512, 32), (1024, 2), (1024, 4), (1024, 8)]:
             variants.append((t, p, C))
@@ -127,6 +129,15 @@ def fps_sweep(out_path=None):
             ok = bool(torch.equal(ref, idx))
             row = dict(b=b, n=n, m=m, cfg=[t, p, c], ms=ms, us_per_iter=1e3 * ms / (m - 1), same_as_default=ok,
                        pairs_per_s=b * (m - 1) * n / (ms * 1e-3))
+            if c < 0 and m * 2 <= 8192:  # separate setup (sort) from the per-step cost: time 2m picks too
+                m2 = 2 * m
+                idx2 = torch.empty((b, m2), dtype=torch.int32, device=dev)
+                nx2 = torch.empty((b, m2, 3), dtype=torch.float32, device=dev)
+                lib.pn2_set_fps_config(t, p, c)
+                ms2 = timeit_batch(torch, lambda: lib.pn2_fps_gather(b, n, m2, xyz.data_ptr(), idx2.data_ptr(), nx2.data_ptr(), None))
+                lib.pn2_set_fps_config(0, 0, 0)
+                row["us_per_iter_marginal"] = 1e3 * (ms2 - ms) / m
+                row["setup_ms"] = ms - (ms2 - ms) * (m - 1) / m
             rows.append(row)
             print(json.dumps(row), flush=True)
     if out_path:

@@ -20,6 +20,9 @@
 //     (up to 16 CTAs); the per-step cross-CTA argmax is exchanged through distributed shared
 //     memory with st.async + mbarrier transaction counts (no cluster-wide barrier per step);
 //   * anything larger still falls back to a global-scratch kernel (the reference's layout).
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "pn2_common.cuh"
 
 namespace pn2 {
@@ -394,20 +397,37 @@ __device__ __forceinline__ float warp_max_f(float v) {
     return v;
 }
 
-// ascending bitonic sort of s_key[0..len) in segments of `seg` (seg a power of two dividing len)
+// ascending bitonic sort of s_key[0..len) in segments of `seg` (seg a power of two dividing len).
+// One thread owns a compare-exchange PAIR (i, i|j) per step and handles 4 independent pairs per
+// batch (loads first, then stores) so the shared-memory latency of the few setup warps overlaps.
 template <int T>
 __device__ __forceinline__ void bitonic_sort_smem(unsigned* s_key, int len, int seg, int tid) {
+    const int half = len >> 1;
     for (int kk = 2; kk <= seg; kk <<= 1) {
         for (int j = kk >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < len; i += T) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const unsigned a = s_key[i], b = s_key[ixj];
-                    // the last level of a segmented sort must be ascending in EVERY segment
-                    const bool up = ((i & kk) == 0) || (kk == seg);
-                    if ((a > b) == up) {
-                        s_key[i] = b;
-                        s_key[ixj] = a;
+            for (int p0 = tid; p0 < half; p0 += 4 * T) {
+                unsigned a[4], b[4];
+                int ia[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int p = p0 + u * T;
+                    ia[u] = -1;
+                    if (p < half) {
+                        const int i = 2 * p - (p & (j - 1));  // bit j of i is clear; partner is i + j
+                        ia[u] = i;
+                        a[u] = s_key[i];
+                        b[u] = s_key[i + j];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (ia[u] >= 0) {
+                        // the last level of a segmented sort must be ascending in EVERY segment
+                        const bool up = ((ia[u] & kk) == 0) || (kk == seg);
+                        if ((a[u] > b[u]) == up) {
+                            s_key[ia[u]] = b[u];
+                            s_key[ia[u] + j] = a[u];
+                        }
                     }
                 }
             }
@@ -582,6 +602,269 @@ fps_bucket_kernel(int n, int m, int npad, const float* __restrict__ xyz, int* __
         bool top = in && (e.x == gh);
         const unsigned gbal = __ballot_sync(kFullMask, top);
         if (gbal & (gbal - 1u)) {  // several buckets share the maximum: explicit tie-break (rare)
+            const unsigned lo = top ? ~__float_as_uint(s_sorted[e.y].w) : 0u;
+            const unsigned gl = warp_max_u32(lo);
+            top = top && (lo == gl);
+        }
+        const unsigned wpos = warp_max_u32(top ? e.y : 0u);
+        const float4 c = s_sorted[wpos];
+        x1 = c.x;
+        y1 = c.y;
+        z1 = c.z;
+        if (tid == 0) {
+            out[it] = (int)tb_decode(__float_as_uint(c.w));
+            if (oxyz) {
+                oxyz[3 * it + 0] = x1;
+                oxyz[3 * it + 1] = y1;
+                oxyz[3 * it + 2] = z1;
+            }
+        }
+    }
+}
+
+// =================================================================================================
+// fps_prune_kernel — bucketed FPS with SUB-BUCKETS: few fat warps (the configuration that wins on
+// the ALU pipe / barrier side) AND fine pruning granularity.
+//
+// Warp w owns the w-th run of 32*P Morton-sorted points, split into SB = P/4 sub-buckets of 128
+// points (4 per lane, registers 4s..4s+3).  Lane s < SB keeps sub-bucket s's bounding box and
+// current maximum; one lane-parallel box test + one ballot per step tells the warp which
+// sub-buckets the new pick can touch, and only those are updated (each costs 4 fused
+// distance/min updates per lane and one redux for its new maximum).  Every thread caches its best
+// (value, register index) per sub-bucket, so the warp argmax after an update is a short tree over
+// SB cached values instead of a rescan of P points.  Exactness argument as in fps_bucket_kernel.
+// =================================================================================================
+template <int P, int T>
+__global__ void __launch_bounds__(T, 1)
+fps_prune_kernel(int n, int m, int npad, const float* __restrict__ xyz, int* __restrict__ idx_out,
+                 float* __restrict__ new_xyz) {
+    static_assert(P % 4 == 0 && P >= 4, "sub-buckets hold 4 points per lane");
+    constexpr int NW = T / 32;
+    constexpr int BUCKET = 32 * P;
+    constexpr int SB = P / 4;   // sub-buckets per warp
+    constexpr int SUB = 128;    // points per sub-bucket
+    static_assert(SB <= 32 && NW <= 32, "one lane per sub-bucket, one table entry per lane");
+    __shared__ uint2 s_tab[2][32];  // per warp: (max running minimum as float bits, sorted position of its argmax)
+    __shared__ float s_red[6][32];
+    extern __shared__ float4 s_dyn4[];  // [n] sorted points (x, y, z, tb bits), then [npad] u32 sort keys
+    float4* s_sorted = s_dyn4;
+    unsigned* s_key = reinterpret_cast<unsigned*>(s_dyn4 + n);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cloud = blockIdx.x;
+    const float* __restrict__ pts = xyz + (size_t)cloud * n * 3;
+    int* __restrict__ out = idx_out + (size_t)cloud * m;
+    float* __restrict__ oxyz = new_xyz ? new_xyz + (size_t)cloud * m * 3 : nullptr;
+
+    // ---- bounding box of the cloud, Morton sort, per-sub-bucket tie-break sort (as fps_bucket_kernel)
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int k = tid; k < n; k += T) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = __ldg(pts + 3 * (size_t)k + c);
+            mn[c] = fminf(mn[c], v);
+            mx[c] = fmaxf(mx[c], v);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float a = warp_min_f(mn[c]), b = warp_max_f(mx[c]);
+        if (lane == 0) {
+            s_red[c][warp] = a;
+            s_red[3 + c][warp] = b;
+        }
+    }
+    __syncthreads();
+    float scale[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        mn[c] = warp_min_f(lane < NW ? s_red[c][lane] : INFINITY);
+        mx[c] = warp_max_f(lane < NW ? s_red[3 + c][lane] : -INFINITY);
+        const float ext = mx[c] - mn[c];
+        scale[c] = (ext > 0.f && ext < 3.0e38f) ? 64.0f / ext : 0.0f;
+    }
+    for (int k = tid; k < npad; k += T) {
+        unsigned key = 0xffffffffu;
+        if (k < n) {
+            unsigned q[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float f = (__ldg(pts + 3 * (size_t)k + c) - mn[c]) * scale[c];
+                f = fminf(fmaxf(f, 0.f), 63.f);
+                q[c] = (unsigned)f;
+            }
+            const unsigned mort = morton_part(q[0]) | (morton_part(q[1]) << 1) | (morton_part(q[2]) << 2);
+            key = (mort << 14) | (unsigned)k;  // k < 16384
+        }
+        s_key[k] = key;
+    }
+    __syncthreads();
+    bitonic_sort_smem<T>(s_key, npad, npad, tid);
+    for (int p = tid; p < npad; p += T) {
+        const unsigned key = s_key[p];
+        s_key[p] = (key == 0xffffffffu) ? 0xffffffffu : tb_encode(key & 0x3fffu);
+    }
+    __syncthreads();
+    bitonic_sort_smem<T>(s_key, npad, npad >= SUB ? SUB : npad, tid);
+    for (int p = tid; p < n; p += T) {
+        const unsigned tbk = s_key[p];
+        const unsigned k = tb_decode(tbk);
+        s_sorted[p] = make_float4(__ldg(pts + 3 * (size_t)k), __ldg(pts + 3 * (size_t)k + 1), __ldg(pts + 3 * (size_t)k + 2),
+                                  __uint_as_float(tbk));
+    }
+    __syncthreads();
+
+    // ---- registers: point r = 4*s + j of this lane is sorted position warp*BUCKET + s*SUB + lane*4 + j
+    const int wbase = warp * BUCKET;
+    float px[P], py[P], pz[P], td[P];
+    float tbv[SB];        // this thread's best running minimum inside sub-bucket s
+    unsigned tbj = 0u;    // its register offset j (2 bits per sub-bucket)
+    float blo[3] = {INFINITY, INFINITY, INFINITY}, bhi[3] = {-INFINITY, -INFINITY, -INFINITY};  // lane s: box of sub-bucket s
+    float smax = -1.0f;   // lane s: current maximum of sub-bucket s (-1: empty)
+#pragma unroll
+    for (int s = 0; s < SB; ++s) {
+        float lo3[3] = {INFINITY, INFINITY, INFINITY}, hi3[3] = {-INFINITY, -INFINITY, -INFINITY};
+        tbv[s] = -1.0f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int r = 4 * s + j;
+            const int pos = wbase + s * SUB + lane * 4 + j;
+            px[r] = py[r] = pz[r] = 0.f;
+            td[r] = -1.0f;
+            if (pos < n) {
+                const float4 v = s_sorted[pos];
+                px[r] = v.x; py[r] = v.y; pz[r] = v.z;
+                td[r] = 1e38f;
+                if (tbv[s] < 0.f) tbv[s] = 1e38f;  // first valid point of the thread in tie-break order: j stays 0
+                lo3[0] = fminf(lo3[0], v.x); hi3[0] = fmaxf(hi3[0], v.x);
+                lo3[1] = fminf(lo3[1], v.y); hi3[1] = fmaxf(hi3[1], v.y);
+                lo3[2] = fminf(lo3[2], v.z); hi3[2] = fmaxf(hi3[2], v.z);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float a = warp_min_f(lo3[c]), b = warp_max_f(hi3[c]);
+            if (lane == s) {
+                blo[c] = a;
+                bhi[c] = b;
+            }
+        }
+        if (lane == s && wbase + s * SUB < n) smax = 1e38f;
+    }
+    // initial table entry: the warp's first valid point in tie-break order among maximal (1e38) values.
+    // Sub-buckets are Morton runs, not tie-break runs, so the earliest key must be searched: every
+    // sub-bucket's first position holds its smallest key.
+    {
+        unsigned best_lo = 0u, best_pos = (unsigned)min(wbase, n - 1);
+#pragma unroll
+        for (int s = 0; s < SB; ++s) {
+            const int pos = wbase + s * SUB;
+            if (pos < n) {
+                const unsigned lo = ~__float_as_uint(s_sorted[pos].w);
+                if (lo > best_lo) {
+                    best_lo = lo;
+                    best_pos = (unsigned)pos;
+                }
+            }
+        }
+        if (lane == 0) s_tab[0][warp] = make_uint2(wbase < n ? __float_as_uint(1e38f) : 0u, best_pos);
+    }
+    float x1 = __ldg(pts + 0), y1 = __ldg(pts + 1), z1 = __ldg(pts + 2);
+    if (tid == 0) {
+        out[0] = 0;
+        if (oxyz) {
+            oxyz[0] = x1;
+            oxyz[1] = y1;
+            oxyz[2] = z1;
+        }
+    }
+    __syncthreads();
+
+    for (int it = 1; it < m; ++it) {
+        const int buf = it & 1;
+        // lane s: can the pick lower any running minimum of sub-bucket s?
+        const float gx = fmaxf(fmaxf(__fsub_rn(blo[0], x1), __fsub_rn(x1, bhi[0])), 0.f);
+        const float gy = fmaxf(fmaxf(__fsub_rn(blo[1], y1), __fsub_rn(y1, bhi[1])), 0.f);
+        const float gz = fmaxf(fmaxf(__fsub_rn(blo[2], z1), __fsub_rn(z1, bhi[2])), 0.f);
+        const float lb = __fmaf_rn(gz, gz, __fmaf_rn(gx, gx, __fmul_rn(gy, gy)));
+        const unsigned amask = __ballot_sync(kFullMask, lb < smax);  // lanes >= SB: smax = -1, never set
+        if (amask != 0u) {
+#pragma unroll
+            for (int s = 0; s < SB; ++s) {
+                if (amask & (1u << s)) {  // warp-uniform
+                    float bv = -1.0f;
+                    unsigned bj = 0u;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = 4 * s + j;
+                        const float d = d2_fma_pattern(px[r], py[r], pz[r], x1, y1, z1);
+                        const float d2 = fminf(d, td[r]);
+                        td[r] = d2;
+                        if (d2 > bv) {  // register order == tie-break order inside the sub-bucket
+                            bv = d2;
+                            bj = (unsigned)j;
+                        }
+                    }
+                    tbv[s] = bv;
+                    tbj = (tbj & ~(3u << (2 * s))) | (bj << (2 * s));
+                    const unsigned mhs = warp_max_u32(bv >= 0.f ? __float_as_uint(bv) : 0u);
+                    if (lane == s) smax = __uint_as_float(mhs);  // an active sub-bucket is non-empty
+                }
+            }
+            // this thread's best over its sub-buckets: ties between sub-buckets are NOT in tie-break
+            // order (sub-buckets are spatial), so carry the candidate's key only when needed below
+            float best = tbv[0];
+            int bs = 0;
+#pragma unroll
+            for (int s = 1; s < SB; ++s) {
+                if (tbv[s] > best) {
+                    best = tbv[s];
+                    bs = s;
+                }
+            }
+            const bool has = best >= 0.0f;
+            const unsigned hi = has ? __float_as_uint(best) : 0u;
+            const unsigned mh = warp_max_u32(hi);
+            bool mine = (hi == mh);
+            // exact tie-break needs the key whenever the maximum may be shared: between lanes, or
+            // between sub-buckets of one thread
+            bool thread_tie = false;
+#pragma unroll
+            for (int s = 0; s < SB; ++s) thread_tie |= (s != bs) && (tbv[s] == best);
+            const unsigned bal = __ballot_sync(kFullMask, mine);
+            const bool any_tt = __any_sync(kFullMask, mine && thread_tie);
+            unsigned pos = (unsigned)min(wbase + bs * SUB + lane * 4 + (int)((tbj >> (2 * bs)) & 3u), n - 1);
+            if ((bal & (bal - 1u)) || any_tt) {  // rare: resolve by the reference key explicitly
+                unsigned lo = 0u;
+                if (mine && has) {
+#pragma unroll
+                    for (int s = 0; s < SB; ++s) {
+                        if (tbv[s] == best) {
+                            const unsigned ps = (unsigned)min(wbase + s * SUB + lane * 4 + (int)((tbj >> (2 * s)) & 3u), n - 1);
+                            const unsigned ls = ~__float_as_uint(s_sorted[ps].w);
+                            if (ls > lo) {
+                                lo = ls;
+                                pos = ps;
+                            }
+                        }
+                    }
+                }
+                const unsigned ml = warp_max_u32(lo);
+                mine = mine && (lo == ml);
+                const unsigned bal2 = __ballot_sync(kFullMask, mine);
+                mine = mine && (lane == __ffs(bal2) - 1);
+            }
+            if (mine) s_tab[buf][warp] = make_uint2(mh, pos);
+        } else {
+            s_tab[buf][warp] = s_tab[buf ^ 1][warp];
+        }
+        __syncthreads();
+        const bool in = lane < NW;
+        const uint2 e = in ? s_tab[buf][lane] : make_uint2(0u, 0u);
+        const unsigned gh = warp_max_u32(e.x);
+        bool top = in && (e.x == gh);
+        const unsigned gbal = __ballot_sync(kFullMask, top);
+        if (gbal & (gbal - 1u)) {
             const unsigned lo = top ? ~__float_as_uint(s_sorted[e.y].w) : 0u;
             const unsigned gl = warp_max_u32(lo);
             top = top && (lo == gl);
@@ -848,6 +1131,21 @@ static int launch_bucket(int b, int n, int m, const float* inp, int* out, float*
     return finish_launch();
 }
 
+template <int P, int T>
+static int launch_prune(int b, int n, int m, const float* inp, int* out, float* new_xyz, cudaStream_t st) {
+    auto kern = fps_prune_kernel<P, T>;
+    int npad = 1;
+    while (npad < n) npad <<= 1;
+    size_t dyn = (size_t)n * sizeof(float4) + (size_t)npad * sizeof(unsigned);
+    if (dyn > 220 * 1024 || n > 16384) return (int)cudaErrorInvalidValue;
+    if (dyn > 40 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return (int)e;
+    }
+    kern<<<b, T, dyn, st>>>(n, m, npad, inp, out, new_xyz);
+    return finish_launch();
+}
+
 template <int P, int T, bool XYZ_SMEM>
 static int launch_cluster(int C, int b, int n, int m, const float* inp, int* out, float* new_xyz, cudaStream_t st) {
     auto kern = fps_cluster_kernel<P, T, XYZ_SMEM>;
@@ -880,7 +1178,7 @@ static int launch_cluster(int C, int b, int n, int m, const float* inp, int* out
 }
 
 struct FpsPlan {
-    int threads, ppt, cluster;  // cluster == 0: global-scratch fallback; 1: single CTA; -1: bucketed single CTA; -2: single CTA, packed-math variant
+    int threads, ppt, cluster;  // cluster == 0: global-scratch fallback; 1: single CTA; -1: bucketed single CTA; -2: single CTA, packed-math variant; -3: bucketed with sub-buckets (fps_prune_kernel)
     bool xyz_smem;
 };
 
@@ -892,6 +1190,19 @@ static int pow2_floor(int v) {
 
 static FpsPlan plan_fps(int b, int n) {
     FpsPlan p{0, 0, 0, false};
+    static bool env_read = false;
+    if (!env_read) {  // PN2_FPS_CFG="threads,points_per_thread,cluster": profiling/tuning override
+        env_read = true;
+        const char* e = getenv("PN2_FPS_CFG");
+        if (e) {
+            int t = 0, pp = 0, c = 0;
+            if (sscanf(e, "%d,%d,%d", &t, &pp, &c) == 3) {
+                g_cfg_threads = t;
+                g_cfg_ppt = pp;
+                g_cfg_cluster = c;
+            }
+        }
+    }
     if (g_cfg_threads > 0) {
         p.threads = g_cfg_threads;
         p.ppt = g_cfg_ppt;
@@ -950,9 +1261,25 @@ static int fps_dispatch(int b, int n, int m, const float* inp, float* temp, int*
     if (b == 0 || m == 0) return 0;
     if (!inp || !out) return (int)cudaErrorInvalidValue;
     FpsPlan plan = plan_fps(b, n);
-    if (plan.cluster >= 1 || plan.cluster == -1 || plan.cluster == -2) {
+    if (plan.cluster >= 1 || plan.cluster == -1 || plan.cluster == -2 || plan.cluster == -3) {
         long long cap = (long long)plan.threads * plan.ppt * (plan.cluster < 0 ? 1 : plan.cluster);
         if (cap < n) return (int)cudaErrorInvalidValue;
+    }
+    if (plan.cluster == -3) {
+#define PN2_TRY_PRN(PP, TT) \
+    if (plan.ppt == PP && plan.threads == TT) return launch_prune<PP, TT>(b, n, m, inp, out, new_xyz, st);
+        PN2_TRY_PRN(4, 128)
+        PN2_TRY_PRN(8, 128)
+        PN2_TRY_PRN(16, 128)
+        PN2_TRY_PRN(32, 128)
+        PN2_TRY_PRN(4, 256)
+        PN2_TRY_PRN(8, 256)
+        PN2_TRY_PRN(16, 256)
+        PN2_TRY_PRN(32, 256)
+        PN2_TRY_PRN(4, 512)
+        PN2_TRY_PRN(8, 512)
+        PN2_TRY_PRN(16, 512)
+        return (int)cudaErrorInvalidValue;
     }
     if (plan.cluster == -2) {
 #define PN2_TRY_CTA2(PP, TT) \
