@@ -232,6 +232,8 @@ def run_b200_arm(args, cfg):
     cnt = torch.empty((b, m), dtype=torch.int32, device=dev)
     grouped = torch.empty((b, m, s, 3), dtype=torch.float32, device=dev)
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    bq_ws_bytes = int(lib.pn2_query_ball_point_workspace_bytes(b, n))  # caller-provided scratch for the grid path
+    bq_ws = torch.empty(bq_ws_bytes, dtype=torch.uint8, device=dev) if bq_ws_bytes else None
     st = torch.cuda.current_stream(dev)
     sp = st.cuda_stream
 
@@ -241,7 +243,8 @@ def run_b200_arm(args, cfg):
         rc = lib.pn2_fps_gather(b, n, m, xyz.data_ptr(), fps_idx.data_ptr(), new_xyz.data_ptr(), sp)
         if ev:
             ev[1].record(st)
-        rc |= lib.pn2_query_ball_point(b, n, m, r, s, xyz.data_ptr(), new_xyz.data_ptr(), idx.data_ptr(), cnt.data_ptr(), sp)
+        rc |= lib.pn2_query_ball_point_ws(b, n, m, r, s, xyz.data_ptr(), new_xyz.data_ptr(), idx.data_ptr(), cnt.data_ptr(),
+                                          bq_ws.data_ptr() if bq_ws is not None else None, bq_ws_bytes, sp)
         if ev:
             ev[2].record(st)
         rc |= lib.pn2_group_point(b, n, 3, m, s, xyz.data_ptr(), idx.data_ptr(), grouped.data_ptr(), sp)

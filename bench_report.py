@@ -159,6 +159,15 @@ def bq_sweep(out_path=None):
         lib.pn2_fps_gather(b, n, m, xyz.data_ptr(), fi.data_ptr(), nx.data_ptr(), None)
         idx = torch.empty((b, m, s), dtype=torch.int32, device=dev)
         cnt = torch.empty((b, m), dtype=torch.int32, device=dev)
+        wsb = int(lib.pn2_query_ball_point_workspace_bytes(b, n))
+        if wsb:
+            ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+            ms = timeit(torch, flush, lambda: lib.pn2_query_ball_point_ws(b, n, m, r, s, xyz.data_ptr(), nx.data_ptr(), idx.data_ptr(),
+                                                                          cnt.data_ptr(), ws.data_ptr(), wsb, None), reps=7)
+            row = dict(gen=gen, b=b, n=n, m=m, r=r, s=s, group=-1, ms=ms, mean_cnt=float(cnt.float().mean()),
+                       GBps=W.bytes_ball_query(b, n, m, s) / (ms * 1e-3) / 1e9, grid_flags=int(ws.view(torch.int32)[::(len(ws) // 4) // b][:b].sum()))
+            rows.append(row)
+            print(json.dumps(row), flush=True)
         for g in (0, 1, 2, 4, 8, 16, 32):
             lib.pn2_set_bq_group(g)
             ms = timeit(torch, flush, lambda: lib.pn2_query_ball_point(b, n, m, r, s, xyz.data_ptr(), nx.data_ptr(),
@@ -201,8 +210,16 @@ def report(out_path):
         add(tag, "fps+gather", ms, W.bytes_fps(b, n, m, True), dict(pairs_per_s=b * (m - 1) * n / (ms * 1e-3), us_per_iter=1e3 * ms / max(m - 1, 1)))
         idx = torch.empty((b, m, s), dtype=torch.int32, device=dev)
         cnt = torch.empty((b, m), dtype=torch.int32, device=dev)
-        ms = timeit(torch, flush, lambda: lib.pn2_query_ball_point(b, n, m, r, s, xyz.data_ptr(), nx.data_ptr(), idx.data_ptr(), cnt.data_ptr(), None))
+        wsb = int(lib.pn2_query_ball_point_workspace_bytes(b, n))
+        ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
+        ms = timeit(torch, flush, lambda: lib.pn2_query_ball_point_ws(b, n, m, r, s, xyz.data_ptr(), nx.data_ptr(), idx.data_ptr(), cnt.data_ptr(),
+                                                                      ws.data_ptr() if wsb else None, wsb, None))
         add(tag, f"query_ball_point r={r} S={s}", ms, W.bytes_ball_query(b, n, m, s), dict(mean_cnt=float(cnt.float().mean())))
+        lib.pn2_set_bq_mode(1)
+        ms = timeit(torch, flush, lambda: lib.pn2_query_ball_point_ws(b, n, m, r, s, xyz.data_ptr(), nx.data_ptr(), idx.data_ptr(), cnt.data_ptr(),
+                                                                      ws.data_ptr() if wsb else None, wsb, None))
+        lib.pn2_set_bq_mode(0)
+        add(tag, f"query_ball_point (brute force only) r={r} S={s}", ms, W.bytes_ball_query(b, n, m, s))
         g = torch.empty((b, m, s, 3), dtype=torch.float32, device=dev)
         ms = timeit(torch, flush, lambda: lib.pn2_group_point(b, n, 3, m, s, xyz.data_ptr(), idx.data_ptr(), g.data_ptr(), None))
         add(tag, f"group_point C=3 S={s}", ms, W.bytes_group(b, n, m, s, 3))

@@ -59,6 +59,16 @@ int pn2_gather_point_grad(int b, int n, int m, const float* out_g, const int* id
 int pn2_query_ball_point(int b, int n, int m, float radius, int nsample, const float* xyz1,
                          const float* xyz2, int* idx, int* pts_cnt, void* stream);
 
+/* Same operation and bit-identical results, with a caller-provided device workspace of at least
+ * pn2_query_ball_point_workspace_bytes(b, n) bytes: clouds whose balls are sparse are binned into
+ * a uniform grid (cell edge >= 1.01 radius) and each query only tests its 3x3x3 cell neighbourhood;
+ * the other clouds (dense or badly skewed ones, and any call with workspace == NULL or n < 2048)
+ * take the brute-force path above.  workspace_bytes == 0 from the size query means "not applicable". */
+size_t pn2_query_ball_point_workspace_bytes(int b, int n);
+int pn2_query_ball_point_ws(int b, int n, int m, float radius, int nsample, const float* xyz1,
+                            const float* xyz2, int* idx, int* pts_cnt, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
 /* groupPointLauncher(b,n,c,m,nsample,points,idx,out), tf_grouping_g.cu:133-136.
  * points (b,n,c); idx (b,m,nsample); out (b,m,nsample,c). */
 int pn2_group_point(int b, int n, int c, int m, int nsample, const float* points, const int* idx,
@@ -143,6 +153,8 @@ void pn2_set_fps_config(int threads, int points_per_thread, int cluster);
 int pn2_fps_plan(int b, int n, int* threads, int* points_per_thread, int* cluster);
 /* tuning override: lanes cooperating on one ball query (1,2,4,..,32); 0 restores the heuristic */
 void pn2_set_bq_group(int lanes_per_query);
+/* tuning override for pn2_query_ball_point_ws: 0 = automatic, 1 = brute force only, 2 = same as 0 */
+void pn2_set_bq_mode(int mode);
 
 #ifdef __cplusplus
 }

@@ -20,6 +20,8 @@ _SIGNATURES = {
     "pn2_gather_point": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P]),
     "pn2_gather_point_grad": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P]),
     "pn2_query_ball_point": (c_int, [c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P]),
+    "pn2_query_ball_point_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "pn2_query_ball_point_ws": (c_int, [c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
     "pn2_group_point": (c_int, [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
     "pn2_group_point_grad": (c_int, [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
     "pn2_selection_sort": (c_int, [c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
@@ -37,6 +39,7 @@ _SIGNATURES = {
     "pn2_fps_plan": (c_int, [c_int, c_int, _P, _P, _P]),
     "pn2_set_fps_config": (None, [c_int, c_int, c_int]),
     "pn2_set_bq_group": (None, [c_int]),
+    "pn2_set_bq_mode": (None, [c_int]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

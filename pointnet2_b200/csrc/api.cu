@@ -7,7 +7,7 @@ unsigned long long g_launch_count = 0;
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct SaLayout {
-    size_t xyz, new_xyz, idx, cnt, grouped, total;
+    size_t xyz, new_xyz, idx, cnt, grouped, bq_ws, bq_ws_bytes, total;
 };
 
 static SaLayout sa_layout(int b, int n, int m, int nsample) {
@@ -18,6 +18,8 @@ static SaLayout sa_layout(int b, int n, int m, int nsample) {
     L.idx = off;     off = align_up(off + sizeof(int) * (size_t)b * m * nsample, 256);
     L.cnt = off;     off = align_up(off + sizeof(int) * (size_t)b * m, 256);
     L.grouped = off; off = align_up(off + sizeof(float) * (size_t)b * m * nsample * 3, 256);
+    L.bq_ws_bytes = pn2_query_ball_point_workspace_bytes(b, n);  // 0 when the grid path does not apply
+    L.bq_ws = off;   off = align_up(off + L.bq_ws_bytes, 256);
     L.total = off;
     return L;
 }
@@ -58,7 +60,8 @@ int pn2_sa_layer_host(int b, int n, int m, float radius, int nsample, const floa
     int rc = pn2_fps_gather(b, n, m, d_xyz, d_idx /*scratch for the fps indices*/, d_new, stream);
     if (rc) return rc;
     // the fps indices themselves are not an output of sample_and_group; d_idx is overwritten next
-    rc = pn2_query_ball_point(b, n, m, radius, nsample, d_xyz, d_new, d_idx, d_cnt, stream);
+    rc = pn2_query_ball_point_ws(b, n, m, radius, nsample, d_xyz, d_new, d_idx, d_cnt,
+                                 L.bq_ws_bytes ? ws + L.bq_ws : nullptr, L.bq_ws_bytes, stream);
     if (rc) return rc;
     rc = pn2_group_point(b, n, 3, m, nsample, d_xyz, d_idx, d_grp, stream);
     if (rc) return rc;

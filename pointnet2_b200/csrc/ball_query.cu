@@ -60,7 +60,10 @@ __device__ __forceinline__ unsigned long long bq_fma2(unsigned long long a, unsi
 template <int G>
 __global__ void __launch_bounds__(kBqThreads)
 ball_query_kernel(int n, int m, float thr, int nsample, const float* __restrict__ xyz1,
-                  const float* __restrict__ xyz2, int* __restrict__ idx, int* __restrict__ pts_cnt) {
+                  const float* __restrict__ xyz2, int* __restrict__ idx, int* __restrict__ pts_cnt,
+                  const int* __restrict__ grid_params, int grid_stride) {
+    // clouds the uniform-grid path serves (flag written by bq_grid_build_kernel) are skipped here
+    if (grid_params && grid_params[(size_t)blockIdx.y * grid_stride] != 0) return;
     constexpr int QPB = kBqThreads / G;      // queries per CTA
     constexpr int STEP = G * kBqUnroll;      // pairs consumed per unrolled step by one group
     // pair layout: s_xy[i] = (x0, x1, y0, y1) of points 2i, 2i+1; s_z[i] = (z0, z1)
@@ -162,10 +165,10 @@ ball_query_kernel(int n, int m, float thr, int nsample, const float* __restrict_
 
 template <int G>
 static int launch_bq(int b, int n, int m, float thr, int nsample, const float* xyz1, const float* xyz2, int* idx,
-                     int* pts_cnt, cudaStream_t st) {
+                     int* pts_cnt, const int* grid_params, int grid_stride, cudaStream_t st) {
     constexpr int QPB = kBqThreads / G;
     dim3 grid((m + QPB - 1) / QPB, b, 1);
-    ball_query_kernel<G><<<grid, kBqThreads, 0, st>>>(n, m, thr, nsample, xyz1, xyz2, idx, pts_cnt);
+    ball_query_kernel<G><<<grid, kBqThreads, 0, st>>>(n, m, thr, nsample, xyz1, xyz2, idx, pts_cnt, grid_params, grid_stride);
     return finish_launch();
 }
 
@@ -185,6 +188,18 @@ static int pick_group(int b, int m) {
     int G = 1;
     while (G < 32 && queries * G < 148LL * 2048) G *= 2;
     return G;
+}
+
+int launch_ball_query_brute(int b, int n, int m, float thr, int nsample, const float* xyz1, const float* xyz2,
+                            int* idx, int* pts_cnt, const int* grid_params, int grid_stride, cudaStream_t st) {
+    switch (pick_group(b, m)) {
+        case 1: return launch_bq<1>(b, n, m, thr, nsample, xyz1, xyz2, idx, pts_cnt, grid_params, grid_stride, st);
+        case 2: return launch_bq<2>(b, n, m, thr, nsample, xyz1, xyz2, idx, pts_cnt, grid_params, grid_stride, st);
+        case 4: return launch_bq<4>(b, n, m, thr, nsample, xyz1, xyz2, idx, pts_cnt, grid_params, grid_stride, st);
+        case 8: return launch_bq<8>(b, n, m, thr, nsample, xyz1, xyz2, idx, pts_cnt, grid_params, grid_stride, st);
+        case 16: return launch_bq<16>(b, n, m, thr, nsample, xyz1, xyz2, idx, pts_cnt, grid_params, grid_stride, st);
+        default: return launch_bq<32>(b, n, m, thr, nsample, xyz1, xyz2, idx, pts_cnt, grid_params, grid_stride, st);
+    }
 }
 
 }  // namespace pn2
@@ -224,14 +239,7 @@ int pn2_query_ball_point(int b, int n, int m, float radius, int nsample, const f
         if (e == cudaSuccess) e = cudaMemsetAsync(pts_cnt, 0, sizeof(int) * (size_t)b * m, st);
         return (int)e;
     }
-    switch (pick_group(b, m)) {
-        case 1: return launch_bq<1>(b, n, m, thr, nsample, xyz1, xyz2, idx, pts_cnt, st);
-        case 2: return launch_bq<2>(b, n, m, thr, nsample, xyz1, xyz2, idx, pts_cnt, st);
-        case 4: return launch_bq<4>(b, n, m, thr, nsample, xyz1, xyz2, idx, pts_cnt, st);
-        case 8: return launch_bq<8>(b, n, m, thr, nsample, xyz1, xyz2, idx, pts_cnt, st);
-        case 16: return launch_bq<16>(b, n, m, thr, nsample, xyz1, xyz2, idx, pts_cnt, st);
-        default: return launch_bq<32>(b, n, m, thr, nsample, xyz1, xyz2, idx, pts_cnt, st);
-    }
+    return launch_ball_query_brute(b, n, m, thr, nsample, xyz1, xyz2, idx, pts_cnt, nullptr, 0, st);
 }
 
 }  // extern "C"

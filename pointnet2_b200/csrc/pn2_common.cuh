@@ -49,6 +49,11 @@ __device__ __forceinline__ void warp_max_pair(unsigned& hi, unsigned& lo) {
     lo = ml;
 }
 
+// brute-force ball query launcher (ball_query.cu); clouds whose grid_params[cloud*grid_stride] != 0
+// are skipped (they are served by the uniform-grid kernels of ball_query_grid.cu)
+int launch_ball_query_brute(int b, int n, int m, float thr, int nsample, const float* xyz1, const float* xyz2,
+                            int* idx, int* pts_cnt, const int* grid_params, int grid_stride, cudaStream_t st);
+
 // ---- streaming memory ops ---------------------------------------------------------------------
 __device__ __forceinline__ void st_stream_f4(float4* p, float4 v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream_i4(int4* p, int4 v) { __stcs(p, v); }

@@ -46,9 +46,16 @@ def query_ball_point(radius: float, nsample: int, xyz1: torch.Tensor, xyz2: torc
     idx = torch.empty((b, m, nsample), dtype=torch.int32, device=xyz1.device)
     pts_cnt = torch.empty((b, m), dtype=torch.int32, device=xyz1.device)
     if b * m:
+        lib = _lib.load()
         with on_device(xyz1):
-            rc = _lib.load().pn2_query_ball_point(b, n, m, radius, nsample, ptr(xyz1), ptr(xyz2), ptr(idx),
-                                                  ptr(pts_cnt), stream_ptr(xyz1.device))
+            ws_bytes = int(lib.pn2_query_ball_point_workspace_bytes(b, n))
+            if ws_bytes:  # sparse balls are served through a uniform grid built in this scratch
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xyz1.device)
+                rc = lib.pn2_query_ball_point_ws(b, n, m, radius, nsample, ptr(xyz1), ptr(xyz2), ptr(idx), ptr(pts_cnt),
+                                                 ptr(ws), ws_bytes, stream_ptr(xyz1.device))
+            else:
+                rc = lib.pn2_query_ball_point(b, n, m, radius, nsample, ptr(xyz1), ptr(xyz2), ptr(idx),
+                                              ptr(pts_cnt), stream_ptr(xyz1.device))
         _lib.check(rc, "pn2_query_ball_point")
     return idx, pts_cnt
 

@@ -181,6 +181,38 @@ def _set_bq_group(g):
     _lib.load().pn2_set_bq_group(g)
 
 
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("gen,b,n,m,r,s", BQ_CASES + [("U", 4, 4096, 512, 0.1, 32), ("D", 3, 4096, 256, 0.1, 32), ("S", 4, 2048, 300, 0.15, 16),
+                                                     ("D", 2, 8192, 200, 0.05, 8), ("U", 2, 16384, 100, 0.06, 64), ("U", 2, 300, 40, 0.02, 4)])
+def test_ball_query_grid_path_matches_oracle(dev, mode, gen, b, n, m, r, s):
+    """The workspace entry point (uniform grid for sparse balls, in-kernel ordered scan for dense
+    ones, brute force for flagged clouds) against the oracle; mode 1 forces brute force."""
+    xyz = W.DISTRIBUTIONS[gen](b, n, 46)
+    new_xyz = O.oracle_gather_point(xyz, O.oracle_fps(m, xyz))
+    lib = _lib.load()
+    lib.pn2_set_bq_mode(mode)
+    try:
+        idx, cnt = query_ball_point(r, s, T(xyz, dev), T(new_xyz, dev))
+    finally:
+        lib.pn2_set_bq_mode(0)
+    oi, oc = O.oracle_query_ball_point(r, s, xyz, new_xyz)
+    np.testing.assert_array_equal(N(cnt), oc)
+    np.testing.assert_array_equal(N(idx), oi)
+
+
+def test_ball_query_grid_free_queries_outside_the_box(dev):
+    """Queries outside the data's bounding box (some within the radius of border points, some far
+    away) through the grid path."""
+    xyz = W.cloud_uniform(2, 2000, 47)
+    q = (W.cloud_uniform(2, 300, 48) * 1.5 - 0.25).astype(np.float32)
+    q[:, :20] += 5.0
+    idx, cnt = query_ball_point(0.08, 16, T(xyz, dev), T(q, dev))
+    oi, oc = O.oracle_query_ball_point(0.08, 16, xyz, q)
+    np.testing.assert_array_equal(N(cnt), oc)
+    np.testing.assert_array_equal(N(idx), oi)
+    assert (oc == 0).any() and (oc > 0).any()
+
+
 def test_ball_query_free_queries_and_empty_rows(dev):
     """Queries that are not data points: empty balls give zero rows and pts_cnt 0."""
     xyz = W.cloud_uniform(2, 300, 42)
