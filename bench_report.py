@@ -88,6 +88,8 @@ def fps_sweep(out_path=None):
              (8, 16384, 4096), (8, 65536, 2048), (1, 65536, 2048), (8, 262144, 512), (1, 262144, 512)]
     if os.environ.get("PN2_SWEEP_SMALL"):
         cases = [c for c in cases if c[1] <= 8192]
+    if os.environ.get("PN2_SWEEP_LARGE"):
+        cases = [(16, 8192, 1024), (2, 8192, 1024), (8, 16384, 4096), (1, 16384, 4096), (8, 65536, 2048), (1, 65536, 2048)]
     variants = [(128, 1, 1), (256, 1, 1), (512, 1, 1), (512, 2, 1), (512, 4, 1), (512, 8, 1), (512, 16, 1), (1024, 1, 1),
                 (1024, 2, 1), (1024, 4, 1), (1024, 8, 1)]
     variants += [(128, p, 1) for p in (2, 4, 8, 16, 32)] + [(256, p, 1) for p in (2, 4, 8, 16, 32)]
@@ -98,8 +100,10 @@ def fps_sweep(out_path=None):
     for t, ps in ((128, (4, 8, 16, 32)), (256, (4, 8, 16, 32)), (512, (4, 8, 16))):
         variants += [(t, p, -3) for p in ps]
     for C in (2, 4, 8, 16):
-        for (t, p) in [(512, 1), (512, 2), (512, 4), (512, 8), (512, 16), (512, 32), (1024, 2), (1024, 4), (1024, 8)]:
-            variants.append((t, p, C))
+        for (t, p) in [(512, 1), (512, 2), (512, 4), (512, 8), (512, 16), (512, 32), (1024, 2), (1024, 4), (1024, 8),
+                       (256, 2), (256, 4), (256, 8), (256, 16), (256, 32), (128, 4), (128, 8), (128, 16), (128, 32)]:
+            if (C * t) % 512 == 0:
+                variants.append((t, p, C))
     for (b, n, m) in cases:
         xyz = torch.from_numpy(W.cloud_uniform(b, n, 100)).to(dev)
         idx = torch.empty((b, m), dtype=torch.int32, device=dev)

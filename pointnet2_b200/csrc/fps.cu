@@ -887,7 +887,7 @@ fps_prune_kernel(int n, int m, int npad, const float* __restrict__ xyz, int* __r
 
 // =================================================================================================
 // One thread-block CLUSTER per cloud (C = 2..16 CTAs).  Thread t of CTA r owns points
-// k = t + T*(r + C*j): slot k mod 512 == t mod 512 again (T % 512 == 0).
+// k = t + T*(r + C*j): all in one reference slot (k mod 512) whenever C*T % 512 == 0.
 // Per step: CTA-local argmax as above, then warp 0 pushes the CTA's 8-byte key into slot r of
 // EVERY CTA's exchange buffer with st.async (which also completes 8 tx-bytes on that CTA's
 // mbarrier); all threads wait on their own CTA's mbarrier (expecting 8*C bytes), read the C keys
@@ -899,7 +899,9 @@ template <int P, int T, bool XYZ_SMEM>
 __global__ void __launch_bounds__(T, 1)
 fps_cluster_kernel(int n, int m, const float* __restrict__ xyz, int* __restrict__ idx_out,
                    float* __restrict__ new_xyz) {
-    static_assert(T % 512 == 0, "slot order needs T % 512 == 0");
+    // slot order: thread t of CTA r owns k = t + T*(r + C*j); all of them share the reference slot
+    // k mod 512 as long as C*T is a multiple of 512 (checked by the host dispatch)
+    static_assert(T % 512 == 0 || 512 % T == 0, "T must divide or be a multiple of 512");
     constexpr int NW = T / 32;
     __shared__ uint2 s_keys[2][32];
     __shared__ __align__(8) unsigned long long s_xkeys[2][16];
@@ -1207,7 +1209,7 @@ static FpsPlan plan_fps(int b, int n) {
         p.threads = g_cfg_threads;
         p.ppt = g_cfg_ppt;
         p.cluster = g_cfg_cluster;
-        p.xyz_smem = (g_cfg_ppt >= 32);
+        p.xyz_smem = (g_cfg_ppt >= 32 && g_cfg_threads >= 512);
         return p;
     }
     // single CTA, register-resident (cluster = 1).  Measured on B200 (profiles/r1_fps_sweep*.json):
@@ -1223,30 +1225,38 @@ static FpsPlan plan_fps(int b, int n) {
     if (n <= 2048) return {128, 16, 1, false};
     if (n <= 4096) return {256, 16, 1, false};
     if (n <= 8192) return {256, 32, 1, false};
-    // cluster: as many CTAs per cloud as keeps all clouds co-resident on the 148 SMs
+    // cluster: as many CTAs per cloud as keeps all clouds co-resident on the 148 SMs; inside each CTA
+    // again few fat warps (measured: N=16384 x8 clouds 0.72 -> 0.54 us/step, N=65536 1.05 -> 0.81)
     int cmax = pow2_floor(148 / (b > 148 ? 148 : b));
     if (cmax > 16) cmax = 16;
     if (cmax < 2) cmax = 2;
+    auto pick = [](long long per, int C, FpsPlan& out) -> bool {
+        const int t = (C >= 4) ? 128 : 256;  // C*T must be a multiple of 512
+        const int pmin = (t == 128) ? 4 : 2;
+        for (int pp = pmin; pp <= 32; pp *= 2) {
+            if (per <= (long long)t * pp) {
+                out = {t, pp, C, false};
+                return true;
+            }
+        }
+        if (per <= 256LL * 32) {
+            out = {256, 32, C, false};
+            return true;
+        }
+        if (per <= 512LL * 32) {
+            out = {512, 32, C, true};  // coordinates in shared memory, running minimum in registers
+            return true;
+        }
+        return false;
+    };
     for (int C = cmax; C >= 2; C /= 2) {
-        long long per = ((long long)n + C - 1) / C;  // points per CTA
-        if (per < 512 && C > 2) continue;            // too thin: fewer CTAs
-        if (per <= 512 * 1) return {512, 1, C, false};
-        if (per <= 512 * 2) return {512, 2, C, false};
-        if (per <= 512 * 4) return {512, 4, C, false};
-        if (per <= 512 * 8) return {512, 8, C, false};
-        if (per <= 512 * 16) return {512, 16, C, false};
-        if (per <= 512 * 32 && C == cmax) return {512, 32, C, true};
+        const long long per = ((long long)n + C - 1) / C;  // points per CTA
+        if (per < 512 && C > 2) continue;                  // too thin: fewer CTAs
+        if (pick(per, C, p)) return p;
         break;
     }
     // widest cluster regardless of co-residency
-    {
-        long long per = ((long long)n + 15) / 16;
-        if (per <= 512 * 16) {
-            int ppt = per <= 512 ? 1 : per <= 1024 ? 2 : per <= 2048 ? 4 : per <= 4096 ? 8 : 16;
-            return {512, ppt, 16, false};
-        }
-        if (per <= 512 * 32) return {512, 32, 16, true};
-    }
+    if (pick(((long long)n + 15) / 16, 16, p)) return p;
     return {1024, 0, 0, false};
 }
 
@@ -1352,6 +1362,16 @@ static int fps_dispatch(int b, int n, int m, const float* inp, float* temp, int*
     }
     if (plan.cluster >= 2) {
         if (plan.cluster > 16 || (plan.cluster & (plan.cluster - 1))) return (int)cudaErrorInvalidValue;
+        if (((long long)plan.cluster * plan.threads) % 512 != 0) return (int)cudaErrorInvalidValue;
+        PN2_TRY_CLU(4, 128, false)
+        PN2_TRY_CLU(8, 128, false)
+        PN2_TRY_CLU(16, 128, false)
+        PN2_TRY_CLU(32, 128, false)
+        PN2_TRY_CLU(2, 256, false)
+        PN2_TRY_CLU(4, 256, false)
+        PN2_TRY_CLU(8, 256, false)
+        PN2_TRY_CLU(16, 256, false)
+        PN2_TRY_CLU(32, 256, false)
         PN2_TRY_CLU(1, 512, false)
         PN2_TRY_CLU(2, 512, false)
         PN2_TRY_CLU(4, 512, false)

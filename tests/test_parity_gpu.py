@@ -46,6 +46,7 @@ def test_fps_matches_oracle(dev, gen, b, n, m):
 
 @pytest.mark.parametrize("cfg", [(512, 2, 2), (512, 1, 4), (512, 4, 2), (512, 8, 4), (1024, 2, 2), (512, 2, 8),
                                  (512, 1, 16), (512, 16, 2), (512, 32, 2), (1024, 4, 1), (512, 8, 1), (512, 16, 1),
+                                 (256, 2, 2), (256, 8, 4), (256, 32, 2), (128, 4, 4), (128, 16, 8), (128, 32, 16), (256, 16, 16),
                                  (128, 2, 1), (128, 8, 1), (128, 32, 1), (256, 2, 1), (256, 4, 1), (256, 16, 1), (256, 32, 1),
                                  (128, 4, -3), (128, 8, -3), (128, 16, -3), (128, 32, -3), (256, 4, -3), (256, 8, -3), (256, 16, -3),
                                  (256, 32, -3), (512, 4, -3), (512, 8, -3), (512, 16, -3),

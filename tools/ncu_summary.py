@@ -31,6 +31,30 @@ def summarise(path):
     return txt
 
 
+
+
+def traffic_json(path, out_json):
+    """dram bytes (read + write) per launch of the first captured kernel -> profiles/ncu_traffic.json"""
+    import json
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units, vals = rows[0], rows[1], rows[2]
+
+    def get(name):
+        i = hdr.index(name)
+        v = float(vals[i])
+        u = units[i].lower()
+        mult = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+        return v * mult
+    d = {"kernel": vals[hdr.index("Kernel Name")], "fps_dram_bytes_per_launch": get("dram__bytes_read.sum") + get("dram__bytes_write.sum"),
+         "source": path, "note": "one ncu --set full capture of the FPS kernel inside bench.py (cfg2)"}
+    json.dump(d, open(out_json, "w"), indent=1)
+    print(d)
+
+
 if __name__ == "__main__":
-    for p in sys.argv[1:]:
-        print(summarise(p))
+    if len(sys.argv) > 1 and sys.argv[1] == "--traffic":
+        traffic_json(sys.argv[2], sys.argv[3])
+    else:
+        for p in sys.argv[1:]:
+            print(summarise(p))
