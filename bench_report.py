@@ -233,6 +233,16 @@ def report(out_path):
             ms = timeit(torch, flush, lambda: lib.pn2_group_point(b, n, c, m, s, feats.data_ptr(), idx.data_ptr(), gf.data_ptr(), None))
             add(tag, f"group_point C={c} S={s}", ms, W.bytes_group(b, n, m, s, c))
             del gf
+        if c:  # backward of the gather: atomic scatter-add (the caller's zero-fill is part of the op)
+            go = torch.randn((b, m, s, c), dtype=torch.float32, device=dev)
+            gp = torch.empty((b, n, c), dtype=torch.float32, device=dev)
+
+            def grad():
+                gp.zero_()
+                lib.pn2_group_point_grad(b, n, c, m, s, go.data_ptr(), idx.data_ptr(), gp.data_ptr(), None)
+            ms = timeit(torch, flush, grad)
+            add(tag, f"group_point_grad C={c} S={s} (incl. zero-fill)", ms, 4 * b * m * s + 4 * b * m * s * c + 2 * 4 * b * n * c)
+            del go, gp
         out = torch.empty((b, m, s, 3 + c), dtype=torch.float32, device=dev)
         ms = timeit(torch, flush, lambda: lib.pn2_group_concat(b, n, c, m, s, xyz.data_ptr(), nx.data_ptr(), feats.data_ptr() if c else None,
                                                                idx.data_ptr(), 1 if xyz_first else 0, out.data_ptr(), None, None))
@@ -275,6 +285,14 @@ def report(out_path):
             o = torch.empty((b, n_, c_), dtype=torch.float32, device=dev)
             ms = timeit(torch, flush, lambda: lib.pn2_three_interpolate(b, m_, c_, n_, p2.data_ptr(), i.data_ptr(), w.data_ptr(), o.data_ptr(), None))
             add(f"cfg4[B={b}].FP{n_}<-{m_}", f"three_interpolate C={c_}", ms, W.bytes_three_interpolate(b, n_, m_, c_))
+            go = torch.randn((b, n_, c_), dtype=torch.float32, device=dev)
+            gp = torch.empty((b, m_, c_), dtype=torch.float32, device=dev)
+
+            def igrad():
+                gp.zero_()
+                lib.pn2_three_interpolate_grad(b, n_, c_, m_, go.data_ptr(), i.data_ptr(), w.data_ptr(), gp.data_ptr(), None)
+            ms = timeit(torch, flush, igrad)
+            add(f"cfg4[B={b}].FP{n_}<-{m_}", f"three_interpolate_grad C={c_} (incl. zero-fill)", ms, 2 * 4 * b * m_ * c_ + 24 * b * n_ + 4 * b * n_ * c_)
             ms = timeit(torch, flush, lambda: lib.pn2_three_nn_interpolate(b, n_, m_, c_, x1.data_ptr(), x2.data_ptr(), p2.data_ptr(), o.data_ptr(), None, None, None, None))
             add(f"cfg4[B={b}].FP{n_}<-{m_}", f"three_nn_interpolate (fused) C={c_}", ms, 12 * b * n_ + 12 * b * m_ + 4 * b * m_ * c_ + 4 * b * n_ * c_)
     # cfg5 sweep: FPS + gather + ball query, B=8 and the per-GPU shards

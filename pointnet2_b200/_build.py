@@ -24,6 +24,10 @@ HEADERS = [os.path.join(CSRC, "pn2_common.cuh"), os.path.join(INCLUDE, "pn2_api.
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
+    # no implicit mul+add contraction anywhere (front end AND ptxas, which otherwise fuses even
+    # mul.rn.f32x2 + add.rn.f32x2): every fused multiply-add in this library is written explicitly,
+    # because bit-exactness with the reference depends on where the roundings are
+    "-fmad=false",
     "-Xcompiler", "-fPIC",
     "-I", INCLUDE, "-I", CSRC,
 ]

@@ -17,7 +17,7 @@
 namespace pn2 {
 
 constexpr int kNnThreads = 128;
-constexpr int kNnTile = 2048;  // known points per shared-memory tile (32 KB as float4)
+constexpr int kNnTile = 2048;  // known points per shared-memory tile (24 KB as pairs)
 
 struct Top3 {
     float d1, d2, d3;
@@ -29,51 +29,99 @@ __device__ __forceinline__ void top3_init(Top3& t) {
     t.i1 = t.i2 = t.i3 = 0;
 }
 
+// Branch-free insertion (selects only): the reference's strict '<' cascade (tf_interpolate.cpp:74-89).
+// A candidate that is not < d3 leaves the state untouched.
 __device__ __forceinline__ void top3_insert(Top3& t, float d, int k) {
-    if (d < t.d1) {
-        t.d3 = t.d2; t.i3 = t.i2;
-        t.d2 = t.d1; t.i2 = t.i1;
-        t.d1 = d;    t.i1 = k;
-    } else if (d < t.d2) {
-        t.d3 = t.d2; t.i3 = t.i2;
-        t.d2 = d;    t.i2 = k;
-    } else if (d < t.d3) {
-        t.d3 = d;    t.i3 = k;
-    }
+    const bool c3 = d < t.d3, c2 = d < t.d2, c1 = d < t.d1;  // c1 => c2 => c3 (d1 <= d2 <= d3)
+    const float nd3 = c2 ? t.d2 : d;
+    const int ni3 = c2 ? t.i2 : k;
+    const float nd2 = c1 ? t.d1 : d;
+    const int ni2 = c1 ? t.i1 : k;
+    t.d3 = c3 ? nd3 : t.d3;
+    t.i3 = c3 ? ni3 : t.i3;
+    t.d2 = c2 ? nd2 : t.d2;
+    t.i2 = c2 ? ni2 : t.i2;
+    t.d1 = c1 ? d : t.d1;
+    t.i1 = c1 ? k : t.i1;
 }
 
-// Stage `tn` known points starting at `base` into float4-padded shared memory; the tail up to a
-// multiple of 4 is +inf (distance +inf never passes a strict '<').
-__device__ __forceinline__ int stage_known(float4* s_pts, const float* __restrict__ known, int base, int m, int tid,
+// packed FP32x2 helpers (SASS FADD2 / FMUL2): two known points per instruction for the differences
+// and the squares, IEEE round-to-nearest per half
+__device__ __forceinline__ unsigned long long nn_pack(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void nn_unpack(unsigned long long v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long nn_sub2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long nn_mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+constexpr int kNnPairs = kNnTile / 2;
+
+// Shared-memory tile of known points stored as PAIRS: s_xy[i] = (x0, x1, y0, y1) of points 2i, 2i+1,
+// s_z[i] = (z0, z1).  The tail up to a multiple of 2 pairs is +inf (distance +inf never passes '<').
+struct KnownTile {
+    ulonglong2 xy[kNnPairs];
+    unsigned long long z[kNnPairs];
+};
+
+__device__ __forceinline__ int stage_known(KnownTile& tile, const float* __restrict__ known, int base, int m, int tid,
                                            int nthreads) {
     const int tn = min(kNnTile, m - base);
-    const int tn_pad = (tn + 3) & ~3;
-    for (int p = tid; p < tn_pad; p += nthreads) {
-        float4 v = make_float4(INFINITY, INFINITY, INFINITY, 0.f);
+    const int tp_pad = (((tn + 1) >> 1) + 1) & ~1;  // pairs, rounded up to an even count
+    float* sxy = reinterpret_cast<float*>(tile.xy);
+    float* sz = reinterpret_cast<float*>(tile.z);
+    for (int p = tid; p < 2 * tp_pad; p += nthreads) {
+        float x = INFINITY, y = INFINITY, z = INFINITY;
         if (p < tn) {
             const float* s = known + (size_t)(base + p) * 3;
-            v.x = s[0];
-            v.y = s[1];
-            v.z = s[2];
+            x = s[0];
+            y = s[1];
+            z = s[2];
         }
-        s_pts[p] = v;
+        const int pi = p >> 1, par = p & 1;
+        sxy[4 * pi + par] = x;
+        sxy[4 * pi + 2 + par] = y;
+        sz[2 * pi + par] = z;
     }
-    return tn_pad;
+    return tp_pad;
 }
 
-__device__ __forceinline__ void scan_tile(Top3& t, const float4* s_pts, int tn_pad, int base, float ux, float uy,
+// Scan one tile.  Candidates are offered in ascending known index; the (rare, per-lane) insertion
+// sits behind a warp-uniform vote so the common path is distance math + one compare per point.
+__device__ __forceinline__ void scan_tile(Top3& t, const KnownTile& tile, int tp_pad, int base, float ux, float uy,
                                           float uz) {
-    for (int p = 0; p < tn_pad; p += 4) {
+    const unsigned long long UX = nn_pack(ux, ux), UY = nn_pack(uy, uy), UZ = nn_pack(uz, uz);
+    for (int p = 0; p < tp_pad; p += 2) {
         float d[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const float4 v = s_pts[p + u];
-            d[u] = d2_nofma(v.x, v.y, v.z, ux, uy, uz);
+        for (int u = 0; u < 2; ++u) {
+            const ulonglong2 xy = tile.xy[p + u];
+            const unsigned long long zz = tile.z[p + u];
+            const unsigned long long dx = nn_sub2(xy.x, UX), dy = nn_sub2(xy.y, UY), dz = nn_sub2(zz, UZ);
+            // squares packed, sums scalar: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2
+            // (CUDA 12.9, even with -fmad=false or when the add is spelled fma(a,1,b)), which would
+            // skip the rounding of the products that the reference's x86 code performs; the scalar
+            // __fadd_rn intrinsic is never contracted
+            float xx0, xx1, yy0, yy1, zz0, zz1;
+            nn_unpack(nn_mul2(dx, dx), xx0, xx1);
+            nn_unpack(nn_mul2(dy, dy), yy0, yy1);
+            nn_unpack(nn_mul2(dz, dz), zz0, zz1);
+            d[2 * u] = __fadd_rn(__fadd_rn(xx0, yy0), zz0);
+            d[2 * u + 1] = __fadd_rn(__fadd_rn(xx1, yy1), zz1);
         }
-        const float dmin = fminf(fminf(d[0], d[1]), fminf(d[2], d[3]));
-        if (dmin < t.d3) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) top3_insert(t, d[u], base + p + u);
+        for (int u = 0; u < 4; ++u) {
+            if (__any_sync(kFullMask, d[u] < t.d3)) top3_insert(t, d[u], base + 2 * p + u);
         }
     }
 }
@@ -82,7 +130,7 @@ __device__ __forceinline__ void scan_tile(Top3& t, const float4* s_pts, int tn_p
 __global__ void __launch_bounds__(kNnThreads)
 three_nn_kernel(int n, int m, const float* __restrict__ xyz1, const float* __restrict__ xyz2,
                 float* __restrict__ dist, int* __restrict__ idx) {
-    __shared__ float4 s_pts[kNnTile];
+    __shared__ KnownTile s_tile;
     const int tid = threadIdx.x;
     const int cloud = blockIdx.y;
     const int j = blockIdx.x * kNnThreads + tid;
@@ -99,9 +147,9 @@ three_nn_kernel(int n, int m, const float* __restrict__ xyz1, const float* __res
     top3_init(t);
     for (int base = 0; base < m; base += kNnTile) {
         if (base) __syncthreads();
-        const int tn_pad = stage_known(s_pts, known, base, m, tid, kNnThreads);
+        const int tp_pad = stage_known(s_tile, known, base, m, tid, kNnThreads);
         __syncthreads();
-        scan_tile(t, s_pts, tn_pad, base, ux, uy, uz);
+        scan_tile(t, s_tile, tp_pad, base, ux, uy, uz);
     }
     if (valid) {
         float* dd = dist + ((size_t)cloud * n + j) * 3;
@@ -209,7 +257,7 @@ __global__ void __launch_bounds__(kNnThreads)
 three_nn_interp_kernel(int n, int m, int c, const float* __restrict__ xyz1, const float* __restrict__ xyz2,
                        const float* __restrict__ points2, float* __restrict__ out, float* __restrict__ dist_o,
                        int* __restrict__ idx_o, float* __restrict__ weight_o) {
-    __shared__ float4 s_pts[kNnTile];
+    __shared__ KnownTile s_tile;
     __shared__ int s_i[kNnThreads][3];
     __shared__ float s_w[kNnThreads][3];
     const int tid = threadIdx.x;
@@ -229,9 +277,9 @@ three_nn_interp_kernel(int n, int m, int c, const float* __restrict__ xyz1, cons
     top3_init(t);
     for (int base = 0; base < m; base += kNnTile) {
         if (base) __syncthreads();
-        const int tn_pad = stage_known(s_pts, known, base, m, tid, kNnThreads);
+        const int tp_pad = stage_known(s_tile, known, base, m, tid, kNnThreads);
         __syncthreads();
-        scan_tile(t, s_pts, tn_pad, base, ux, uy, uz);
+        scan_tile(t, s_tile, tp_pad, base, ux, uy, uz);
     }
     // dist = max(dist, 1e-10); norm = sum(1/dist); weight = (1/dist)/norm   (pointnet_util.py:212-215)
     const float r1 = __fdiv_rn(1.0f, fmaxf(t.d1, 1e-10f));
