@@ -12,6 +12,8 @@
 // is treated as one flat array: consecutive lanes write consecutive 16-byte vectors (streaming
 // stores, the output is write-once), and read the matching 16 bytes of the source row (rows are
 // served from L2: the source tensor is at most tens of MB).
+#include <stdlib.h>
+
 #include "pn2_common.cuh"
 
 namespace pn2 {
@@ -49,18 +51,71 @@ gather_point_grad_kernel(int n, int m, long long total, const float* __restrict_
 
 // ---- group_point, vector path: c % 4 == 0, 16-byte aligned bases -------------------------------
 // One thread per output float4.  rows = b*m*nsample flat rows, rows_per_cloud = m*nsample.
-template <typename IndexT>
+template <typename IndexT, int U>
 __global__ void __launch_bounds__(kCopyThreads)
 group_point_vec4_kernel(int n, int c4, IndexT rows_per_cloud, IndexT total_vec, const float4* __restrict__ points,
                         const int* __restrict__ idx, float4* __restrict__ out) {
+    // U independent 16-byte gathers in flight per thread (all loads first, then the streaming stores)
     const IndexT stride = (IndexT)gridDim.x * kCopyThreads;
-    for (IndexT v = (IndexT)blockIdx.x * kCopyThreads + threadIdx.x; v < total_vec; v += stride) {
-        const IndexT row = v / (IndexT)c4;
-        const int l = (int)(v - row * (IndexT)c4);
-        const IndexT cloud = row / rows_per_cloud;
-        const int a = __ldg(idx + row);
-        const float4 val = __ldg(points + ((size_t)cloud * n + a) * c4 + l);
-        st_stream_f4(out + v, val);
+    for (IndexT v0 = (IndexT)blockIdx.x * kCopyThreads + threadIdx.x; v0 < total_vec; v0 += stride * U) {
+        float4 val[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const IndexT v = v0 + (IndexT)u * stride;
+            if (v < total_vec) {
+                const IndexT row = v / (IndexT)c4;
+                const int l = (int)(v - row * (IndexT)c4);
+                const IndexT cloud = row / rows_per_cloud;
+                const int a = __ldg(idx + row);
+                val[u] = __ldg(points + ((size_t)cloud * n + a) * c4 + l);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const IndexT v = v0 + (IndexT)u * stride;
+            if (v < total_vec) st_stream_f4(out + v, val[u]);
+        }
+    }
+}
+
+// ---- group_point, vector path, row-batched: LPR lanes per row, R rows in flight per lane-group ----
+// No per-vector integer division and no load->load dependency per vector: the R row indices of a
+// batch are fetched first (one broadcast load each), then every lane issues R independent 16-byte
+// gathers per channel step and streams them out.  cfg3 layer 2 (C=320): see profiles/.
+template <int LPR, int R>
+__global__ void __launch_bounds__(kCopyThreads)
+group_rows_vec4_kernel(int n, int c4, unsigned rows_per_cloud, const float4* __restrict__ points,
+                       const int* __restrict__ idx, float4* __restrict__ out) {
+    constexpr int RPW = 32 / LPR;  // row slots per warp
+    const int lane = threadIdx.x & 31, g = lane % LPR, sub = lane / LPR;
+    const unsigned cloud = blockIdx.y;
+    const unsigned warps = (gridDim.x * kCopyThreads) >> 5;
+    const unsigned warp = (blockIdx.x * kCopyThreads + threadIdx.x) >> 5;
+    const size_t cloud_row0 = (size_t)cloud * rows_per_cloud;
+    const int* __restrict__ cidx = idx + cloud_row0;
+    const float4* __restrict__ cpts = points + (size_t)cloud * n * c4;
+    // this lane-group walks rows r = (warp*RPW + sub)*R + rr, stride warps*RPW*R
+    for (unsigned r0 = (warp * RPW + sub) * R; r0 < rows_per_cloud; r0 += warps * RPW * R) {
+        const float4* __restrict__ src[R];
+        float4* __restrict__ dst[R];
+        bool ok[R];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const unsigned r = r0 + rr;
+            ok[rr] = r < rows_per_cloud;
+            const int a = ok[rr] ? __ldg(cidx + r) : 0;
+            src[rr] = cpts + (size_t)a * c4;
+            dst[rr] = out + (cloud_row0 + r) * c4;
+        }
+        for (int l = g; l < c4; l += LPR) {
+            float4 v[R];
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr)
+                if (ok[rr]) v[rr] = __ldg(src[rr] + l);
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr)
+                if (ok[rr]) st_stream_f4(dst[rr] + l, v[rr]);
+        }
     }
 }
 
@@ -78,7 +133,8 @@ group_rows_kernel(int n, int c, int nsample, unsigned rows_per_cloud, const floa
                   const float* __restrict__ new_xyz, const float* __restrict__ points,
                   const int* __restrict__ idx, int xyz_lo, int feat_lo, float* __restrict__ out,
                   float* __restrict__ grouped_xyz) {
-    constexpr int RPW = 32 / LPR;  // rows per warp per pass
+    constexpr int RPW = 32 / LPR;  // row slots per warp
+    constexpr int R = 4;           // rows in flight per lane-group
     const int lane = threadIdx.x & 31, g = lane % LPR, sub = lane / LPR;
     const unsigned cloud = blockIdx.y;
     const int w = c + (HAS_XYZ ? 3 : 0);
@@ -88,22 +144,39 @@ group_rows_kernel(int n, int c, int nsample, unsigned rows_per_cloud, const floa
     const int* __restrict__ cidx = idx + cloud_row0;
     const float* __restrict__ cpts = points ? points + (size_t)cloud * n * c : nullptr;
     const float* __restrict__ cxyz = HAS_XYZ ? xyz + (size_t)cloud * n * 3 : nullptr;
-    for (unsigned r = warp * RPW + sub; r < rows_per_cloud; r += warps * RPW) {
-        const int a = __ldg(cidx + r);
-        float* __restrict__ dst = out + (cloud_row0 + r) * w;
+    const unsigned m = rows_per_cloud / (unsigned)nsample;
+    for (unsigned r0 = (warp * RPW + sub) * R; r0 < rows_per_cloud; r0 += warps * RPW * R) {
+        int a[R];
+        bool ok[R];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            ok[rr] = (r0 + rr) < rows_per_cloud;
+            a[rr] = ok[rr] ? __ldg(cidx + r0 + rr) : 0;
+        }
         if (HAS_XYZ) {
             if (g < 3) {
-                const size_t ctr = (size_t)cloud * (rows_per_cloud / (unsigned)nsample) + r / (unsigned)nsample;  // global centroid index
-                const float v = __fsub_rn(__ldg(cxyz + (size_t)a * 3 + g), __ldg(new_xyz + ctr * 3 + g));
-                __stcs(dst + xyz_lo + g, v);
-                if (grouped_xyz) __stcs(grouped_xyz + (cloud_row0 + r) * 3 + g, v);
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) {
+                    if (ok[rr]) {
+                        const unsigned r = r0 + rr;
+                        const size_t ctr = (size_t)cloud * m + r / (unsigned)nsample;  // global centroid index
+                        const float v = __fsub_rn(__ldg(cxyz + (size_t)a[rr] * 3 + g), __ldg(new_xyz + ctr * 3 + g));
+                        __stcs(out + (cloud_row0 + r) * w + xyz_lo + g, v);
+                        if (grouped_xyz) __stcs(grouped_xyz + (cloud_row0 + r) * 3 + g, v);
+                    }
+                }
             }
         }
         if (c > 0) {
-            const float* __restrict__ src = cpts + (size_t)a * c;
-            float* __restrict__ d = dst + feat_lo;
-#pragma unroll 4
-            for (int l = g; l < c; l += LPR) __stcs(d + l, __ldg(src + l));
+            for (int l = g; l < c; l += LPR) {
+                float v[R];
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr)
+                    if (ok[rr]) v[rr] = __ldg(cpts + (size_t)a[rr] * c + l);
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr)
+                    if (ok[rr]) __stcs(out + (cloud_row0 + r0 + rr) * w + feat_lo + l, v[rr]);
+            }
         }
     }
 }
@@ -155,9 +228,9 @@ static int launch_group_rows(int b, int n, int c, int m, int nsample, const floa
         return finish_launch();
     }
     const int lpr = w <= 4 ? 4 : (w <= 8 ? 8 : (w <= 16 ? 16 : 32));
-    const unsigned rows_per_block = (kCopyThreads / 32) * (32 / lpr);
+    const unsigned rows_per_block = (kCopyThreads / 32) * (32 / lpr) * 4;  // 4 rows in flight per lane-group
     unsigned gx = (rpc + rows_per_block - 1) / rows_per_block;
-    const unsigned cap = (148u * 32u + b - 1) / b;  // enough CTAs to fill the machine, then grid-stride
+    const unsigned cap = (148u * 16u + b - 1) / b;  // enough CTAs to fill the machine, then grid-stride
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
     dim3 grid(gx, b, 1);
@@ -301,13 +374,36 @@ int pn2_group_point(int b, int n, int c, int m, int nsample, const float* points
     const unsigned long long rpc = (unsigned long long)m * nsample;
     if (c % 4 == 0 && aligned16(points) && aligned16(out)) {
         const unsigned long long tv = total / 4;
-        const unsigned grid = grid_for(tv, kCopyThreads);
+        static int mode = -1, ctas_per_sm = 0;
+        if (mode < 0) {  // tuning hooks: PN2_GROUP_MODE 0 = row-batched (default), 1 = flat one-vector-per-thread
+            const char* e = getenv("PN2_GROUP_MODE");
+            mode = e ? atoi(e) : 0;
+            const char* gq = getenv("PN2_GROUP_CTAS");
+            ctas_per_sm = gq ? atoi(gq) : 16;
+        }
+        if (mode == 0 && rpc < (1ull << 32) && b <= 65535) {
+            const int c4 = c / 4;
+            const int lpr = c4 <= 4 ? 4 : (c4 <= 8 ? 8 : (c4 <= 16 ? 16 : 32));
+            constexpr int R = 4;
+            const unsigned rows_per_block = (kCopyThreads / 32) * (32 / lpr) * R;
+            unsigned gx = (unsigned)((rpc + rows_per_block - 1) / rows_per_block);
+            const unsigned cap = (148u * (unsigned)ctas_per_sm + b - 1) / b;
+            if (gx > cap) gx = cap;
+            if (gx < 1) gx = 1;
+            dim3 grid(gx, b, 1);
+            if (lpr == 4) group_rows_vec4_kernel<4, R><<<grid, kCopyThreads, 0, st>>>(n, c4, (unsigned)rpc, (const float4*)points, idx, (float4*)out);
+            else if (lpr == 8) group_rows_vec4_kernel<8, R><<<grid, kCopyThreads, 0, st>>>(n, c4, (unsigned)rpc, (const float4*)points, idx, (float4*)out);
+            else if (lpr == 16) group_rows_vec4_kernel<16, R><<<grid, kCopyThreads, 0, st>>>(n, c4, (unsigned)rpc, (const float4*)points, idx, (float4*)out);
+            else group_rows_vec4_kernel<32, R><<<grid, kCopyThreads, 0, st>>>(n, c4, (unsigned)rpc, (const float4*)points, idx, (float4*)out);
+            return finish_launch();
+        }
+        unsigned long long blocks = (tv + kCopyThreads - 1) / kCopyThreads;
+        const unsigned long long cap = 148ull * (unsigned long long)ctas_per_sm;
+        const unsigned grid = (unsigned)(blocks > cap ? cap : (blocks < 1 ? 1 : blocks));
         if (tv < (1ull << 31))
-            group_point_vec4_kernel<unsigned><<<grid, kCopyThreads, 0, st>>>(
-                n, c / 4, (unsigned)rpc, (unsigned)tv, (const float4*)points, idx, (float4*)out);
+            group_point_vec4_kernel<unsigned, 1><<<grid, kCopyThreads, 0, st>>>(n, c / 4, (unsigned)rpc, (unsigned)tv, (const float4*)points, idx, (float4*)out);
         else
-            group_point_vec4_kernel<unsigned long long><<<grid, kCopyThreads, 0, st>>>(
-                n, c / 4, rpc, tv, (const float4*)points, idx, (float4*)out);
+            group_point_vec4_kernel<unsigned long long, 1><<<grid, kCopyThreads, 0, st>>>(n, c / 4, rpc, tv, (const float4*)points, idx, (float4*)out);
     } else {
         if (rpc >= (1ull << 32) || b > 65535) return (int)cudaErrorInvalidValue;
         return launch_group_rows<false>(b, n, c, m, nsample, nullptr, nullptr, points, idx, 0, 0, out, nullptr, st);
