@@ -133,8 +133,7 @@ group_rows_kernel(int n, int c, int nsample, unsigned rows_per_cloud, const floa
                   const float* __restrict__ new_xyz, const float* __restrict__ points,
                   const int* __restrict__ idx, int xyz_lo, int feat_lo, float* __restrict__ out,
                   float* __restrict__ grouped_xyz) {
-    constexpr int RPW = 32 / LPR;  // row slots per warp
-    constexpr int R = 4;           // rows in flight per lane-group
+    constexpr int RPW = 32 / LPR;  // rows per warp per pass
     const int lane = threadIdx.x & 31, g = lane % LPR, sub = lane / LPR;
     const unsigned cloud = blockIdx.y;
     const int w = c + (HAS_XYZ ? 3 : 0);
@@ -144,39 +143,22 @@ group_rows_kernel(int n, int c, int nsample, unsigned rows_per_cloud, const floa
     const int* __restrict__ cidx = idx + cloud_row0;
     const float* __restrict__ cpts = points ? points + (size_t)cloud * n * c : nullptr;
     const float* __restrict__ cxyz = HAS_XYZ ? xyz + (size_t)cloud * n * 3 : nullptr;
-    const unsigned m = rows_per_cloud / (unsigned)nsample;
-    for (unsigned r0 = (warp * RPW + sub) * R; r0 < rows_per_cloud; r0 += warps * RPW * R) {
-        int a[R];
-        bool ok[R];
-#pragma unroll
-        for (int rr = 0; rr < R; ++rr) {
-            ok[rr] = (r0 + rr) < rows_per_cloud;
-            a[rr] = ok[rr] ? __ldg(cidx + r0 + rr) : 0;
-        }
+    for (unsigned r = warp * RPW + sub; r < rows_per_cloud; r += warps * RPW) {
+        const int a = __ldg(cidx + r);
+        float* __restrict__ dst = out + (cloud_row0 + r) * w;
         if (HAS_XYZ) {
             if (g < 3) {
-#pragma unroll
-                for (int rr = 0; rr < R; ++rr) {
-                    if (ok[rr]) {
-                        const unsigned r = r0 + rr;
-                        const size_t ctr = (size_t)cloud * m + r / (unsigned)nsample;  // global centroid index
-                        const float v = __fsub_rn(__ldg(cxyz + (size_t)a[rr] * 3 + g), __ldg(new_xyz + ctr * 3 + g));
-                        __stcs(out + (cloud_row0 + r) * w + xyz_lo + g, v);
-                        if (grouped_xyz) __stcs(grouped_xyz + (cloud_row0 + r) * 3 + g, v);
-                    }
-                }
+                const size_t ctr = (size_t)cloud * (rows_per_cloud / (unsigned)nsample) + r / (unsigned)nsample;  // global centroid index
+                const float v = __fsub_rn(__ldg(cxyz + (size_t)a * 3 + g), __ldg(new_xyz + ctr * 3 + g));
+                __stcs(dst + xyz_lo + g, v);
+                if (grouped_xyz) __stcs(grouped_xyz + (cloud_row0 + r) * 3 + g, v);
             }
         }
         if (c > 0) {
-            for (int l = g; l < c; l += LPR) {
-                float v[R];
-#pragma unroll
-                for (int rr = 0; rr < R; ++rr)
-                    if (ok[rr]) v[rr] = __ldg(cpts + (size_t)a[rr] * c + l);
-#pragma unroll
-                for (int rr = 0; rr < R; ++rr)
-                    if (ok[rr]) __stcs(out + (cloud_row0 + r0 + rr) * w + feat_lo + l, v[rr]);
-            }
+            const float* __restrict__ src = cpts + (size_t)a * c;
+            float* __restrict__ d = dst + feat_lo;
+#pragma unroll 4
+            for (int l = g; l < c; l += LPR) __stcs(d + l, __ldg(src + l));
         }
     }
 }
@@ -228,9 +210,9 @@ static int launch_group_rows(int b, int n, int c, int m, int nsample, const floa
         return finish_launch();
     }
     const int lpr = w <= 4 ? 4 : (w <= 8 ? 8 : (w <= 16 ? 16 : 32));
-    const unsigned rows_per_block = (kCopyThreads / 32) * (32 / lpr) * 4;  // 4 rows in flight per lane-group
+    const unsigned rows_per_block = (kCopyThreads / 32) * (32 / lpr);
     unsigned gx = (rpc + rows_per_block - 1) / rows_per_block;
-    const unsigned cap = (148u * 16u + b - 1) / b;  // enough CTAs to fill the machine, then grid-stride
+    const unsigned cap = (148u * 32u + b - 1) / b;  // enough CTAs to fill the machine, then grid-stride
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
     dim3 grid(gx, b, 1);
