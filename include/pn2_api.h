@@ -69,6 +69,16 @@ int pn2_query_ball_point_ws(int b, int n, int m, float radius, int nsample, cons
                             const float* xyz2, int* idx, int* pts_cnt, void* workspace,
                             size_t workspace_bytes, void* stream);
 
+/* pn2_query_ball_point_ws in two halves: the grid build needs only the data points (xyz1), so it can
+ * run on a second stream while farthest point sampling is still producing the queries; the second
+ * half needs the queries.  Both return cudaErrorInvalidValue where pn2_query_ball_point_ws would
+ * have fallen back to brute force (no workspace / n < 2048 / radius <= 1e-20). */
+int pn2_ball_grid_build(int b, int n, float radius, int nsample, const float* xyz1, void* workspace,
+                        size_t workspace_bytes, void* stream);
+int pn2_query_ball_point_prebuilt(int b, int n, int m, float radius, int nsample, const float* xyz1,
+                                  const float* xyz2, int* idx, int* pts_cnt, const void* workspace,
+                                  size_t workspace_bytes, void* stream);
+
 /* groupPointLauncher(b,n,c,m,nsample,points,idx,out), tf_grouping_g.cu:133-136.
  * points (b,n,c); idx (b,m,nsample); out (b,m,nsample,c). */
 int pn2_group_point(int b, int n, int c, int m, int nsample, const float* points, const int* idx,

@@ -287,6 +287,39 @@ size_t pn2_query_ball_point_workspace_bytes(int b, int n) {
     return sizeof(int) * (size_t)b * pn2::grid_ws_ints_per_cloud(n);
 }
 
+// Split form of pn2_query_ball_point_ws: the grid build only needs the data points, so a caller can
+// run it on a second stream while farthest point sampling is still producing the queries.
+int pn2_ball_grid_build(int b, int n, float radius, int nsample, const float* xyz1, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+    using namespace pn2;
+    if (b <= 0 || n <= 0 || nsample <= 0 || !(radius > 0.0f) || !xyz1 || !workspace) return (int)cudaErrorInvalidValue;
+    const size_t need = pn2_query_ball_point_workspace_bytes(b, n);
+    if (need == 0 || workspace_bytes < need || b > 65535) return (int)cudaErrorInvalidValue;
+    bq_grid_build_kernel<<<b, kGbThreads, 0, as_stream(stream)>>>(n, radius, nsample, xyz1, static_cast<int*>(workspace),
+                                                                   grid_ws_ints_per_cloud(n));
+    return finish_launch();
+}
+
+int pn2_query_ball_point_prebuilt(int b, int n, int m, float radius, int nsample, const float* xyz1, const float* xyz2,
+                                  int* idx, int* pts_cnt, const void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace pn2;
+    if (b < 0 || n <= 0 || m < 0 || nsample <= 0 || !(radius > 0.0f)) return (int)cudaErrorInvalidValue;
+    if (b == 0 || m == 0) return 0;
+    if (!xyz1 || !xyz2 || !idx || !pts_cnt || !workspace) return (int)cudaErrorInvalidValue;
+    const size_t need = pn2_query_ball_point_workspace_bytes(b, n);
+    const float thr = pn2_ball_threshold(radius);
+    if (need == 0 || workspace_bytes < need || b > 65535 || thr < 0.0f) return (int)cudaErrorInvalidValue;
+    cudaStream_t st = as_stream(stream);
+    const int* ws = static_cast<const int*>(workspace);
+    const size_t stride = grid_ws_ints_per_cloud(n);
+    dim3 grid((m + kGqThreads / 32 - 1) / (kGqThreads / 32), b, 1);
+    bq_grid_query_kernel<<<grid, kGqThreads, 0, st>>>(n, m, thr, nsample, xyz1, xyz2, idx, pts_cnt, ws, stride);
+    int rc = finish_launch();
+    if (rc) return rc;
+    // clouds the build kernel did not flag for the grid are done by the brute-force kernel
+    return launch_ball_query_brute(b, n, m, thr, nsample, xyz1, xyz2, idx, pts_cnt, ws, (int)stride, st);
+}
+
 int pn2_query_ball_point_ws(int b, int n, int m, float radius, int nsample, const float* xyz1, const float* xyz2,
                             int* idx, int* pts_cnt, void* workspace, size_t workspace_bytes, void* stream) {
     using namespace pn2;
@@ -297,18 +330,9 @@ int pn2_query_ball_point_ws(int b, int n, int m, float radius, int nsample, cons
     const float thr = pn2_ball_threshold(radius);
     if (g_bq_mode == 1 || !workspace || need == 0 || workspace_bytes < need || thr < 0.0f || b > 65535)
         return pn2_query_ball_point(b, n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt, stream);
-    cudaStream_t st = as_stream(stream);
-    int* ws = static_cast<int*>(workspace);
-    const size_t stride = grid_ws_ints_per_cloud(n);
-    bq_grid_build_kernel<<<b, kGbThreads, 0, st>>>(n, radius, nsample, xyz1, ws, stride);
-    int rc = finish_launch();
+    int rc = pn2_ball_grid_build(b, n, radius, nsample, xyz1, workspace, workspace_bytes, stream);
     if (rc) return rc;
-    dim3 grid((m + kGqThreads / 32 - 1) / (kGqThreads / 32), b, 1);
-    bq_grid_query_kernel<<<grid, kGqThreads, 0, st>>>(n, m, thr, nsample, xyz1, xyz2, idx, pts_cnt, ws, stride);
-    rc = finish_launch();
-    if (rc) return rc;
-    // clouds the build kernel did not flag for the grid are done by the brute-force kernel
-    return launch_ball_query_brute(b, n, m, thr, nsample, xyz1, xyz2, idx, pts_cnt, ws, (int)stride, st);
+    return pn2_query_ball_point_prebuilt(b, n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"
