@@ -194,12 +194,16 @@ def report(out_path):
     peak, kind = measured_peaks()
     rows = []
 
+    lane_rate = 148 * 128 * 1.965e9  # FP32 lanes x max SM clock: the secondary bound for the pair-evaluation kernels
+
     def add(cfg, kernel, ms, nbytes, extra=None):
         gbps = nbytes / (ms * 1e-3) / 1e9
         row = dict(config=cfg, kernel=kernel, ms=ms, algorithmic_MB=nbytes / 1e6, GBps=gbps, frac_of_peak=gbps / peak,
                    peak=f"{peak} GB/s of {kind}")
         if extra:
             row.update(extra)
+            if "pairs_per_s" in extra:  # point-pair evaluations per FP32-lane-cycle (1 = one pair per lane per clock)
+                row["pairs_per_lane_cycle"] = extra["pairs_per_s"] / lane_rate
         rows.append(row)
         print(json.dumps(row), flush=True)
 

@@ -17,7 +17,10 @@
  *     like the reference (tf_sampling.cpp:174, tf_grouping.cpp:204, tf_interpolate.cpp:258).
  *   - return value: 0 on success, otherwise a cudaError_t (argument errors return
  *     cudaErrorInvalidValue = 1).  pn2_error_string() translates.
- *   - limits: every tensor must have fewer than 2^31 elements per batch entry; n, m < 2^31.
+ *   - limits: every tensor must have fewer than 2^31 elements per batch entry; n, m < 2^31;
+ *     ops that put the batch on gridDim.y (ball query, three_nn, the row kernels) take b <= 65535.
+ *   - the pn2_set_* tuning hooks write process-wide state without locking: call them before use,
+ *     not concurrently with launches.
  */
 #ifndef PN2_API_H_
 #define PN2_API_H_

@@ -74,7 +74,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 os.remove(os.path.join(BUILD_DIR, f))
     with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(lambda s: _compile_one(nvcc, s, verbose), SOURCES))
-    tmp = LIB_PATH + ".tmp"
+    tmp = LIB_PATH + f".tmp{os.getpid()}"
     cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

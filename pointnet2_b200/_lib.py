@@ -59,7 +59,22 @@ def load() -> ctypes.CDLL:
     if _lib is not None:
         return _lib
     path = _build.LIB_PATH
-    if _build.is_stale():
+    world = int(os.environ.get("WORLD_SIZE", "1") or "1")
+    local_rank = int(os.environ.get("LOCAL_RANK", "0") or "0")
+    if world > 1:
+        # one process per GPU: never race on the build tree.  A present library is used as is; a
+        # missing one is built by local rank 0 while the other ranks wait for it to appear.
+        if not os.path.exists(path):
+            if local_rank == 0:
+                _build.build()
+            else:
+                import time
+                deadline = time.time() + 600
+                while not os.path.exists(path) and time.time() < deadline:
+                    time.sleep(0.5)
+                if not os.path.exists(path):
+                    raise ImportError("libpn2_b200.so was not built by local rank 0 within 10 minutes")
+    elif _build.is_stale():
         try:
             _build.build()
         except Exception as e:  # stale-but-present library on a box without nvcc is still usable

@@ -74,6 +74,16 @@ def test_fps_every_kernel_variant_matches_oracle(dev, cfg, gen):
     np.testing.assert_array_equal(got, O.oracle_fps(150, xyz))
 
 
+def test_fps_cfg1_plumbing_matches_cpu_restatement(dev):
+    """BASELINE.json configs[0]: B=8 N=1024 npoint=512 — the GPU kernels against the CPU FPS
+    restatement (the reference has no CPU FPS) on the survey's input recipe."""
+    c = W.CFG1_FPS_CPU
+    xyz = W.cloud_uniform(c["b"], c["n"], c["seed"])
+    idx = farthest_point_sample(c["npoint"], T(xyz, dev))
+    assert idx.dtype == torch.int32 and tuple(idx.shape) == (8, 512)
+    np.testing.assert_array_equal(N(idx), O.oracle_fps(c["npoint"], xyz))
+
+
 def test_fps_tie_break_lower_slot_wins(dev):
     n = 600
     xyz = np.zeros((1, n, 3), np.float32)
