@@ -12,9 +12,14 @@ clouds).  Prints ONE JSON line (rank 0).
 
   value      whole-job points/s (B*N per rank per step, summed over ranks / max-over-ranks time),
              inputs resident in HBM, CUDA-event timed per step, L2 flushed between steps.
+             One batch at a time (each step waits for the previous one).
   e2e        the same metric through the host-buffer C-ABI call (pn2_sa_layer_host): pinned host
-             xyz -> H2D -> 3 kernels -> D2H of new_xyz/idx/pts_cnt/grouped_xyz, all inside the
-             timed region.
+             xyz -> H2D -> 3 kernels -> D2H of new_xyz/idx/pts_cnt/grouped_xyz, every step, all
+             inside the timed region.  Headline: a stream of batches through
+             SetAbstractionPipeline (--e2e-depth in flight, default 3: copy-in/sampling of the next
+             batch overlaps copy-out of the previous); e2e.serial is one batch in flight.
+  device_batches_in_flight   secondary: `value`'s graph with --in-flight batches on separate
+             streams (one FPS launch occupies only b of the 148 SMs).
   roofline   dominant kernel (FPS): algorithmic bytes / its CUDA-event time vs the measured HBM peak.
   cpu_baseline  the same workload on the host cores (FPS: oracle port — the reference has no CPU
              FPS; ball query + group: the reference's own CPU functions when oracle/_ref travelled).
@@ -214,7 +219,7 @@ def run_b200_arm(args, cfg):
     import torch.distributed as dist
 
     from pointnet2_b200 import _lib, workloads as W
-    from pointnet2_b200.host import SetAbstractionHost
+    from pointnet2_b200.host import SetAbstractionHost, SetAbstractionPipeline
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -355,6 +360,74 @@ def run_b200_arm(args, cfg):
     torch.cuda.synchronize(dev)
     same_dev = bool(torch.equal(chk_idx, idx)) and bool(torch.equal(chk_new, new_xyz))
 
+    # ---- secondary: the same graph with several batches in flight.  One FPS launch keeps one SM
+    #      per cloud busy (b of 148), so independent batches on separate streams fill the GPU; this
+    #      is reported beside `value` (which stays one batch at a time), never instead of it.
+    inflight = None
+    if graph is not None and args.in_flight > 1:
+        try:
+            lanes = []
+            for _ in range(args.in_flight):
+                bufs = dict(fps_idx=torch.empty_like(fps_idx), new_xyz=torch.empty_like(new_xyz), idx=torch.empty_like(idx),
+                            cnt=torch.empty_like(cnt), grouped=torch.empty_like(grouped),
+                            ws=torch.empty(bq_ws_bytes, dtype=torch.uint8, device=dev) if bq_ws_bytes else None)
+                ls, sd = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+                fe, je = torch.cuda.Event(), torch.cuda.Event()
+
+                def lane_step(cur, bufs=bufs, sd=sd, fe=fe, je=je):
+                    sc, rc = cur.cuda_stream, 0
+                    if bufs["ws"] is not None:
+                        fe.record(cur)
+                        sd.wait_event(fe)
+                        rc |= lib.pn2_ball_grid_build(b, n, r, s, xyz.data_ptr(), bufs["ws"].data_ptr(), bq_ws_bytes, sd.cuda_stream)
+                        je.record(sd)
+                    rc |= lib.pn2_fps_gather(b, n, m, xyz.data_ptr(), bufs["fps_idx"].data_ptr(), bufs["new_xyz"].data_ptr(), sc)
+                    if bufs["ws"] is not None:
+                        cur.wait_event(je)
+                        rc |= lib.pn2_query_ball_point_prebuilt(b, n, m, r, s, xyz.data_ptr(), bufs["new_xyz"].data_ptr(),
+                                                                bufs["idx"].data_ptr(), bufs["cnt"].data_ptr(),
+                                                                bufs["ws"].data_ptr(), bq_ws_bytes, sc)
+                    else:
+                        rc |= lib.pn2_query_ball_point(b, n, m, r, s, xyz.data_ptr(), bufs["new_xyz"].data_ptr(),
+                                                       bufs["idx"].data_ptr(), bufs["cnt"].data_ptr(), sc)
+                    rc |= lib.pn2_group_point(b, n, 3, m, s, xyz.data_ptr(), bufs["idx"].data_ptr(), bufs["grouped"].data_ptr(), sc)
+                    if rc:
+                        raise RuntimeError(f"kernel launch failed rc={rc}")
+
+                lg = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(lg, stream=ls):
+                    lane_step(torch.cuda.current_stream(dev))
+                lanes.append((lg, ls, bufs))
+
+            def run_lanes(steps, t0=None):
+                for lg, ls, _ in lanes:
+                    if t0 is not None:
+                        ls.wait_event(t0)
+                for k in range(steps):
+                    lg, ls, _ = lanes[k % len(lanes)]
+                    with torch.cuda.stream(ls):
+                        flush.zero_()
+                        lg.replay()
+
+            run_lanes(max(args.warmup, len(lanes)))
+            q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            q0.record(st)
+            run_lanes(args.steps, q0)
+            for _, ls, _ in lanes:
+                st.wait_stream(ls)
+            q1.record(st)
+            barrier()
+            launches += launches_per_step * args.steps
+            fl_ms = max_over_ranks(q0.elapsed_time(q1))
+            lanes_same = all(bool(torch.equal(bf["idx"], idx)) and bool(torch.equal(bf["grouped"], grouped)) for _, _, bf in lanes)
+            inflight = {"batches_in_flight": len(lanes), "value": world * b * n * args.steps / (fl_ms * 1e-3), "unit": UNIT,
+                        "ms_per_step": fl_ms / args.steps, "outputs_match_sequential": lanes_same,
+                        "timing": "one event pair around all steps, L2 flush inside"}
+        except Exception as e:  # noqa: BLE001 — secondary number only
+            inflight = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.synchronize(dev)
+
     # ---- end-to-end leg: host buffers through the C-ABI host call --------------------------
     sess = SetAbstractionHost(b, n, m, r, s, device=dev)
     sess.h_xyz.numpy()[...] = xyz_np
@@ -371,8 +444,45 @@ def run_b200_arm(args, cfg):
         e2e_ev[k][1].record(st)
     barrier()
     launches += _lib.launch_count() - launches1
-    e2e_ms = max_over_ranks(sum(a.elapsed_time(bb) for a, bb in e2e_ev))
+    e2e_serial_ms = max_over_ranks(sum(a.elapsed_time(bb) for a, bb in e2e_ev))
+    e2e_serial_value = world * b * n * args.steps / (e2e_serial_ms * 1e-3)
+
+    # ---- end-to-end, the headline: the same host-buffer call for a STREAM of batches — a ring of
+    #      `depth` sessions on private streams (SetAbstractionPipeline), so batch k+1's copy-in and
+    #      sampling overlap batch k's copy-out.  Every step still copies its input from pinned host
+    #      memory and its four results back; the L2 flush runs inside the timed region.
+    pipe = SetAbstractionPipeline(b, n, m, r, s, depth=args.e2e_depth, device=dev)
+    for sl in pipe.slots:
+        sl.h_xyz.numpy()[...] = xyz_np
+
+    def run_pipe(steps, t0=None):
+        if t0 is not None:
+            for ps in pipe.streams:
+                ps.wait_event(t0)
+        for _ in range(steps):
+            if pipe.full():
+                pipe.collect()
+            with torch.cuda.stream(pipe.streams[pipe._next]):
+                flush.zero_()
+            pipe.submit()
+        while pipe.pending():
+            pipe.collect()
+
+    run_pipe(max(args.warmup, pipe.depth))
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches2 = _lib.launch_count()
+    barrier()
+    p0.record(st)
+    run_pipe(args.steps, p0)
+    for ev in pipe.done:
+        st.wait_event(ev)
+    p1.record(st)
+    barrier()
+    launches += _lib.launch_count() - launches2
+    e2e_ms = max_over_ranks(p0.elapsed_time(p1))
     e2e_value = world * b * n * args.steps / (e2e_ms * 1e-3)
+    same_pipe = all(bool((sl.h_idx.to(dev) == idx).all()) and bool((sl.h_grouped_xyz.to(dev) == grouped).all())
+                    for sl in pipe.slots)
     clocks = sampler.stop() if rank == 0 else None
     # sanity: the e2e outputs must equal the device-resident outputs
     same = bool((sess.h_idx.to(dev) == idx).all()) and bool((sess.h_new_xyz.to(dev) == new_xyz).all())
@@ -400,7 +510,10 @@ def run_b200_arm(args, cfg):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": dict(workload_config(cfg, world), launch=launch_mode),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": sess.h2d_bytes, "d2h_bytes_per_step": sess.d2h_bytes,
-                    "ms_per_step": e2e_ms / args.steps, "outputs_match_device_leg": same},
+                    "ms_per_step": e2e_ms / args.steps, "outputs_match_device_leg": same and same_pipe,
+                    "mode": f"stream of batches, {pipe.depth} in flight (SetAbstractionPipeline); one event pair around all steps, L2 flush inside",
+                    "serial": {"value": e2e_serial_value, "ms_per_step": e2e_serial_ms / args.steps,
+                               "mode": "one batch in flight (SetAbstractionHost); per-step event pairs, L2 flush between"}},
             "gpu_launches": int(launches),  # this library's kernels inside the two timed regions (3 per step each)
             "roofline": {"bound": "hbm", "kernel": fps_kernel + " (FPS + fused gather_point)", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_kind": f"of {peak_kind}",
@@ -414,6 +527,7 @@ def run_b200_arm(args, cfg):
                            "graph_outputs_match_sequential": same_dev,
                            "GBps": {"query_ball_point": W.bytes_ball_query(b, n, m, s) / (statistics.mean(t_bq) * 1e-3) / 1e9,
                                     "group_point": W.bytes_group(b, n, m, s, 3) / (statistics.mean(t_grp) * 1e-3) / 1e9}},
+            "device_batches_in_flight": inflight,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -432,6 +546,8 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
+    ap.add_argument("--in-flight", type=int, default=4, help="batches in flight in the secondary device-resident leg")
+    ap.add_argument("--e2e-depth", type=int, default=3, help="batches in flight in the end-to-end leg")
     ap.add_argument("--report", type=str, default=None, help="write per-kernel tables for all BASELINE configs to this file")
     ap.add_argument("--fps-sweep", action="store_true")
     ap.add_argument("--bq-sweep", action="store_true")

@@ -23,6 +23,6 @@ from .pointnet_util import (  # noqa: F401
     sample_and_group,
     sample_and_group_all,
 )
-from .host import SetAbstractionHost  # noqa: F401
+from .host import SetAbstractionHost, SetAbstractionPipeline  # noqa: F401
 
 __version__ = "0.1.0"

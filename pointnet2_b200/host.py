@@ -6,9 +6,16 @@ for one SSG sampling+grouping layer (farthest_point_sample + gather_point + quer
 group_point(xyz), utils/pointnet_util.py:40-45): it owns pinned host staging buffers and a device
 workspace, and each ``run`` issues H2D copy -> 4 kernels -> D2H copies on one stream through the
 C-ABI ``pn2_sa_layer_host``.
+
+``SetAbstractionPipeline`` is the same call for a STREAM of batches (the reference's training loop
+feeds one batch per ``sess.run`` while its input queue prepares the next, train.py:207-231): a ring
+of ``depth`` such sessions, each on its own CUDA stream, so batch k+1's copy-in and sampling overlap
+batch k's grouping and copy-out.  One FPS launch occupies one SM per cloud (32 of 148 at the
+benchmark's batch size), so consecutive batches really do run side by side.
 """
 from __future__ import annotations
 
+import collections
 import ctypes
 
 import numpy as np
@@ -60,3 +67,77 @@ class SetAbstractionHost:
         torch.cuda.current_stream(self.device).synchronize()
         return (self.h_new_xyz.numpy().copy(), self.h_idx.numpy().copy(), self.h_pts_cnt.numpy().copy(),
                 self.h_grouped_xyz.numpy().copy())
+
+
+class SetAbstractionPipeline:
+    """A ring of ``depth`` SetAbstractionHost sessions on private streams.
+
+    Usage::
+        pipe = SetAbstractionPipeline(b, n, npoint, radius, nsample, depth=2)
+        for batch in batches:
+            if pipe.full():
+                new_xyz, idx, pts_cnt, grouped_xyz = pipe.collect()   # oldest batch, in order
+            pipe.input_buffer()[...] = batch                          # fill the pinned slot
+            pipe.submit()
+        while pipe.pending():
+            ... = pipe.collect()
+
+    ``collect`` returns numpy views of the slot's pinned output buffers; they stay valid until the
+    next ``submit`` that reuses the slot (``depth`` submits later).
+    """
+
+    def __init__(self, b: int, n: int, npoint: int, radius: float, nsample: int, depth: int = 2, device=None):
+        if depth < 1:
+            raise ValueError("SetAbstractionPipeline expects depth >= 1")
+        self.slots = [SetAbstractionHost(b, n, npoint, radius, nsample, device=device) for _ in range(int(depth))]
+        self.device = self.slots[0].device
+        self.streams = [torch.cuda.Stream(self.device) for _ in self.slots]
+        self.done = [torch.cuda.Event() for _ in self.slots]
+        self._next = 0
+        self._inflight: collections.deque[int] = collections.deque()
+        self.h2d_bytes, self.d2h_bytes = self.slots[0].h2d_bytes, self.slots[0].d2h_bytes
+
+    @property
+    def depth(self) -> int:
+        return len(self.slots)
+
+    def pending(self) -> int:
+        return len(self._inflight)
+
+    def full(self) -> bool:
+        return len(self._inflight) == len(self.slots)
+
+    def input_buffer(self) -> np.ndarray:
+        """The pinned (b,n,3) float32 input of the slot the next ``submit`` will use."""
+        if self.full():
+            raise RuntimeError("SetAbstractionPipeline is full: collect() the oldest batch first")
+        return self.slots[self._next].h_xyz.numpy()
+
+    def submit(self, xyz: np.ndarray | None = None, after: torch.cuda.Event | None = None) -> int:
+        """Enqueue one batch (``xyz`` is copied into the slot's pinned input when given; otherwise
+        whatever ``input_buffer()`` holds is used). Returns the slot index. Never blocks."""
+        if self.full():
+            raise RuntimeError("SetAbstractionPipeline is full: collect() the oldest batch first")
+        i = self._next
+        slot = self.slots[i]
+        if xyz is not None:
+            xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+            if xyz.shape != (slot.b, slot.n, 3):
+                raise ValueError(f"expected xyz of shape {(slot.b, slot.n, 3)}, got {xyz.shape}")
+            slot.h_xyz.numpy()[...] = xyz
+        if after is not None:
+            self.streams[i].wait_event(after)
+        slot.launch(self.streams[i])
+        self.done[i].record(self.streams[i])
+        self._inflight.append(i)
+        self._next = (i + 1) % len(self.slots)
+        return i
+
+    def collect(self):
+        """Wait for the OLDEST submitted batch; returns (new_xyz, idx, pts_cnt, grouped_xyz) views."""
+        if not self._inflight:
+            raise RuntimeError("SetAbstractionPipeline.collect() with nothing submitted")
+        i = self._inflight.popleft()
+        self.done[i].synchronize()
+        s = self.slots[i]
+        return s.h_new_xyz.numpy(), s.h_idx.numpy(), s.h_pts_cnt.numpy(), s.h_grouped_xyz.numpy()

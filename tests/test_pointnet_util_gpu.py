@@ -6,7 +6,7 @@ import torch
 
 from oracle import oracle as O
 from pointnet2_b200 import workloads as W
-from pointnet2_b200.host import SetAbstractionHost
+from pointnet2_b200.host import SetAbstractionHost, SetAbstractionPipeline
 from pointnet2_b200.pointnet_util import (pointnet_fp_module, pointnet_sa_module, pointnet_sa_module_msg,
                                           sample_and_group, sample_and_group_all)
 
@@ -131,3 +131,45 @@ def test_host_buffer_sa_layer_matches_device_path(dev):
     np.testing.assert_array_equal(grouped, O.oracle_group_point(xyz, widx))
     assert (cnt == O.oracle_query_ball_point(0.2, 16, xyz, wn)[1]).all()
     assert sess.h2d_bytes == xyz.nbytes and sess.d2h_bytes == new_xyz.nbytes + idx.nbytes + cnt.nbytes + grouped.nbytes
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3])
+def test_host_pipeline_returns_every_batch_in_order(dev, depth):
+    """A stream of different batches through the ring: each comes back in submission order and
+    equals the oracle, with up to `depth` batches in flight on separate streams."""
+    b, n, m, r, s = 3, 2048, 96, 0.15, 12
+    batches = [W.DISTRIBUTIONS["UDS"[k % 3]](b, n, 300 + k) for k in range(7)]
+    pipe = SetAbstractionPipeline(b, n, m, r, s, depth=depth)
+    got = []
+    for x in batches:
+        if pipe.full():
+            got.append(tuple(a.copy() for a in pipe.collect()))
+        pipe.input_buffer()[...] = x
+        pipe.submit()
+    while pipe.pending():
+        got.append(tuple(a.copy() for a in pipe.collect()))
+    assert len(got) == len(batches)
+    for x, (new_xyz, idx, cnt, grouped) in zip(batches, got):
+        wn, _, widx, _ = oracle_sample_and_group(m, r, s, x, None)
+        np.testing.assert_array_equal(new_xyz, wn)
+        np.testing.assert_array_equal(idx, widx)
+        np.testing.assert_array_equal(grouped, O.oracle_group_point(x, widx))
+        assert (cnt == O.oracle_query_ball_point(r, s, x, wn)[1]).all()
+
+
+def test_host_pipeline_refuses_overflow_and_empty_collect(dev):
+    pipe = SetAbstractionPipeline(1, 256, 16, 0.2, 4, depth=2)
+    with pytest.raises(RuntimeError):
+        pipe.collect()
+    x = W.cloud_uniform(1, 256, 9)
+    pipe.submit(x)
+    pipe.submit(x)
+    with pytest.raises(RuntimeError):
+        pipe.submit(x)
+    with pytest.raises(RuntimeError):
+        pipe.input_buffer()
+    a = pipe.collect()
+    b2 = pipe.collect()
+    np.testing.assert_array_equal(a[1], b2[1])
+    with pytest.raises(ValueError):
+        pipe.submit(np.zeros((2, 256, 3), np.float32))
