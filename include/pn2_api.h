@@ -46,6 +46,14 @@ int pn2_fps(int b, int n, int m, const float* inp, float* temp, int* out, void* 
  * the pair sample_and_group always issues, utils/pointnet_util.py:40). new_xyz may be NULL. */
 int pn2_fps_gather(int b, int n, int m, const float* inp, int* out, float* new_xyz, void* stream);
 
+/* probsampleLauncher(b,n,m,inp_p,inp_r,temp,out), tf_sampling_g.cu:198-201 (ProbSample op,
+ * tf_sampling.cpp:66-92).  inp_p (b,n) f32 unnormalised probabilities; inp_r (b,m) f32 uniform
+ * draws in [0,1]; temp (b,n) f32 caller-provided scratch that receives the cumulative sums (the
+ * reference's allocate_temp, tf_sampling.cpp:86); out (b,m) i32 = index of the first cumulative sum
+ * >= inp_r * sum.  The float32 cumulative sum keeps the reference's association, so indices are
+ * bit-exact.  One CTA per row: b <= 2^31-1. */
+int pn2_prob_sample(int b, int n, int m, const float* inp_p, const float* inp_r, float* temp, int* out, void* stream);
+
 /* gatherpointLauncher(b,n,m,inp,idx,out), tf_sampling_g.cu:206-208. out (b,m,3). */
 int pn2_gather_point(int b, int n, int m, const float* inp, const int* idx, float* out, void* stream);
 

@@ -25,6 +25,32 @@ from oracle import oracle as O  # noqa: E402
 from pointnet2_b200 import workloads as W  # noqa: E402
 
 
+def prob_cases():
+    """ProbSample inputs: (probabilities (b,n), uniform draws (b,m))."""
+    rng = np.random.RandomState(150)
+    cases = {}
+    for name, n, m in (("prob_n5", 5, 64), ("prob_n1000", 1000, 256), ("prob_two_chunks", 9000, 256)):
+        p = rng.random_sample((2, n)).astype(np.float32)
+        if n >= 1000:
+            p[:, rng.randint(0, n, n // 3)] = 0.0  # plateaus in the cumulative sum
+        r = rng.random_sample((2, m)).astype(np.float32)
+        r[:, 0], r[:, 1] = 0.0, 1.0
+        cases[name] = (p, r)
+    return cases
+
+
+def main_prob(outdir: str) -> None:
+    """Only the ProbSample fixtures (added after the first fixture set was committed)."""
+    import torch
+    assert torch.cuda.is_available()
+    dev = torch.device("cuda:0")
+    os.makedirs(outdir, exist_ok=True)
+    for name, (p, r) in prob_cases().items():
+        out, cum = O.refcuda_prob_sample(torch.from_numpy(p).to(dev), torch.from_numpy(r).to(dev), return_cumsum=True)
+        np.savez_compressed(os.path.join(outdir, name + ".npz"), inp=p, inpr=r, cumsum=cum.cpu().numpy(), out=out.cpu().numpy())
+        print("wrote", name)
+
+
 def main(outdir: str) -> None:
     import torch
     assert torch.cuda.is_available(), "gen_golden.py needs a GPU: the reference's FPS/ball-query kernels are GPU-only"
@@ -112,8 +138,13 @@ def main(outdir: str) -> None:
     gi = O.refcuda_gather_point_grad(xyz.shape, fidx, t(og))
     save("grads", xyz=xyz, fps_idx=fidx.cpu().numpy(), idx=idx.cpu().numpy(), feats=feats, grad_out=go,
          grad_points=gp.cpu().numpy(), out_g=og, inp_g=gi.cpu().numpy())
+    main_prob(outdir)
     print("golden vectors written to", outdir)
 
 
 if __name__ == "__main__":
+    if "--prob-only" in sys.argv:
+        sys.argv.remove("--prob-only")
+        main_prob(sys.argv[1] if len(sys.argv) > 1 else os.path.join(os.path.dirname(HERE), "gpurun_out", "golden"))
+        sys.exit(0)
     main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(os.path.dirname(HERE), "gpurun_out", "golden"))

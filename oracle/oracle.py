@@ -104,6 +104,24 @@ def oracle_fps(npoint: int, xyz, keyorder: bool = False):
     return out
 
 
+def oracle_prob_cumsum(inp):
+    inp = _f(inp)
+    b, n = inp.shape
+    out = np.empty((b, n), _F)
+    lib().oracle_prob_cumsum(c_int(b), c_int(n), _p(inp), _p(out))
+    return out
+
+
+def oracle_prob_sample(inp, inpr):
+    inp, inpr = _f(inp), _f(inpr)
+    b, n = inp.shape
+    m = inpr.shape[1]
+    temp = np.empty((b, n), _F)
+    out = np.empty((b, m), _I)
+    lib().oracle_prob_sample(c_int(b), c_int(n), c_int(m), _p(inp), _p(inpr), _p(temp), _p(out))
+    return out
+
+
 def oracle_gather_point(inp, idx):
     inp, idx = _f(inp), _i(idx)
     b, n, _ = inp.shape
@@ -281,6 +299,19 @@ def refcuda_fps(npoint: int, xyz):
         c_int(b), c_int(n), c_int(npoint), _tp(xyz), _tp(temp), _tp(out))
     torch.cuda.synchronize()
     return out
+
+
+def refcuda_prob_sample(inp, inpr, return_cumsum: bool = False):
+    """probsampleLauncher, tf_sampling_g.cu:198 — needs the b*n float scratch."""
+    import torch
+    b, n = inp.shape
+    m = inpr.shape[1]
+    temp = torch.empty((b, n), dtype=torch.float32, device=inp.device)
+    out = torch.zeros((b, m), dtype=torch.int32, device=inp.device)
+    torch.cuda.synchronize()
+    refcuda()[0]._Z18probsampleLauncheriiiPKfS0_PfPi(c_int(b), c_int(n), c_int(m), _tp(inp), _tp(inpr), _tp(temp), _tp(out))
+    torch.cuda.synchronize()
+    return (out, temp) if return_cumsum else out
 
 
 def refcuda_gather_point(inp, idx):

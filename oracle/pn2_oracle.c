@@ -340,3 +340,94 @@ void oracle_selection_sort(int b, int n, int m, int k, const float *dist, int *o
         }
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * prob_sample: inverse-CDF sampling.  Restates probsampleLauncher, tf_sampling_g.cu:198-201 =
+ * cumsumKernel (:7-89) followed by binarysearchKernel (:91-104).
+ *
+ * The cumulative sum is a float32 sum whose ASSOCIATION matters for bit-exact indices, so the
+ * restatement keeps the reference's addition tree:
+ *   - the row is cut into chunks of 8192 values, each chunk into groups of four;
+ *   - inside a complete group the inclusive prefixes are a, a+b, (a+b)+c, (c+d)+(a+b);
+ *     an incomplete last group is summed left to right starting from 0 and its last prefix is
+ *     its total;
+ *   - the group totals go through a Brent-Kung scan (up-sweep pairing at strides 1,2,4,..,
+ *     then the fill-in sweep back down), giving each group the inclusive total of the groups
+ *     before it, which is added to the in-group prefixes (nothing is added to group 0);
+ *   - the carry from earlier chunks is added last; the carry itself is kept as a compensated
+ *     (two-float) running sum across chunks.
+ * The search is the reference's descending power-of-two walk from r = n-1 over q = u * cum[n-1]:
+ * step back by k whenever cum[r-k] >= q.
+ * ------------------------------------------------------------------------------------------ */
+void oracle_prob_cumsum(int b, int n, const float *inp, float *out) {
+    enum { CHUNK = 8192 };
+    float *pre = (float *)malloc(sizeof(float) * CHUNK);
+    float *tot = (float *)malloc(sizeof(float) * (CHUNK / 4));
+    for (int i = 0; i < b; ++i) {
+        const float *src = inp + (size_t)i * n;
+        float *dst = out + (size_t)i * n;
+        float carry = 0.f, carry_lo = 0.f;
+        for (int j = 0; j < n; j += CHUNK) {
+            const int len = n - j < CHUNK ? n - j : CHUNK;
+            const int groups = (len + 3) / 4;
+            for (int g = 0; g < groups; ++g) {
+                const float *v = src + j + 4 * g;
+                float *p = pre + 4 * g;
+                if (4 * g + 3 < len) {
+                    const float ab = v[1] + v[0];
+                    float cd = v[3] + v[2];
+                    const float abc = v[2] + ab;
+                    cd = cd + ab;
+                    p[0] = v[0]; p[1] = ab; p[2] = abc; p[3] = cd;
+                    tot[g] = cd;
+                } else {
+                    float acc = 0.f;
+                    int t = 4 * g;
+                    for (; t < len; ++t) { acc += src[j + t]; pre[t] = acc; }
+                    for (; t < 4 * groups; ++t) pre[t] = acc;
+                    tot[g] = acc;
+                }
+            }
+            int lvl = 0;
+            for (; (2 << lvl) <= groups; ++lvl)
+                for (int k = 0; k < (groups >> (lvl + 1)); ++k)
+                    tot[((2 * k + 2) << lvl) - 1] += tot[((2 * k + 1) << lvl) - 1];
+            for (--lvl; lvl >= 0; --lvl) {
+                const int cnt = (groups - (1 << lvl)) >> (lvl + 1);
+                for (int k = 0; k < cnt; ++k)
+                    tot[((2 * k + 3) << lvl) - 1] += tot[((2 * k + 2) << lvl) - 1];
+            }
+            for (int t = 0; t < len; ++t) {
+                float p = pre[t];
+                if (t >= 4) p += tot[t / 4 - 1];
+                dst[j + t] = p + carry;
+            }
+            const float t = tot[groups - 1] + carry_lo;
+            const float next = carry + t;
+            carry_lo = t - (next - carry);
+            carry = next;
+        }
+    }
+    free(pre);
+    free(tot);
+}
+
+void oracle_prob_search(int b, int n, int m, const float *cum, const float *query, int *result) {
+    int top = 1;
+    while (top < n) top <<= 1;
+    for (int i = 0; i < b; ++i) {
+        const float *c = cum + (size_t)i * n;
+        for (int j = 0; j < m; ++j) {
+            const float q = query[(size_t)i * m + j] * c[n - 1];
+            int r = n - 1;
+            for (int k = top; k >= 1; k >>= 1)
+                if (r >= k && c[r - k] >= q) r -= k;
+            result[(size_t)i * m + j] = r;
+        }
+    }
+}
+
+void oracle_prob_sample(int b, int n, int m, const float *inp_p, const float *inp_r, float *temp, int *out) {
+    oracle_prob_cumsum(b, n, inp_p, temp);
+    oracle_prob_search(b, n, m, temp, inp_r, out);
+}

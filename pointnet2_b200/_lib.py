@@ -17,6 +17,7 @@ _SIGNATURES = {
     # name: (restype, argtypes)   — mirrors include/pn2_api.h
     "pn2_fps": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P]),
     "pn2_fps_gather": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P]),
+    "pn2_prob_sample": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "pn2_gather_point": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P]),
     "pn2_gather_point_grad": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P]),
     "pn2_query_ball_point": (c_int, [c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P]),

@@ -21,6 +21,37 @@ def _check_xyz(t: torch.Tensor, name: str, op: str) -> None:
         raise ValueError(f"{op} expects (batch_size,num_points,3) {name} shape, got {tuple(t.shape)}")
 
 
+def prob_sample(inp: torch.Tensor, inpr: torch.Tensor) -> torch.Tensor:
+    """
+    input:
+        batch_size * ncategory float32   (unnormalised probabilities)
+        batch_size * npoints   float32   (uniform draws in [0,1])
+    returns:
+        batch_size * npoints   int32     (sampled category per draw)
+    Reference: tf_sampling.py:13-21 -> ProbSampleGpuOp (tf_sampling.cpp:66-92) ->
+    probsampleLauncher (tf_sampling_g.cu:198-201): cumulative sum, then the first index whose
+    cumulative sum reaches inpr * total.  No gradient (ops.NoGradient, tf_sampling.py:22).
+    """
+    inp = require_cuda(inp, "inp", torch.float32)
+    inpr = require_cuda(inpr, "inpr", torch.float32)
+    same_device(inp, inpr)
+    if inp.dim() != 2:
+        raise ValueError(f"ProbSample expects (batch_size,num_choices) inp shape, got {tuple(inp.shape)}")
+    if inpr.dim() != 2 or inpr.shape[0] != inp.shape[0]:
+        raise ValueError(f"ProbSample expects (batch_size,num_points) inpr shape, got {tuple(inpr.shape)}")
+    b, n = inp.shape
+    m = inpr.shape[1]
+    if n <= 0 and b * m:
+        raise ValueError("ProbSample expects a non-empty inp")
+    out = torch.empty((b, m), dtype=torch.int32, device=inp.device)
+    if b * m:
+        temp = torch.empty((b, n), dtype=torch.float32, device=inp.device)  # the op's allocate_temp
+        with on_device(inp):
+            rc = _lib.load().pn2_prob_sample(b, n, m, ptr(inp), ptr(inpr), ptr(temp), ptr(out), stream_ptr(inp.device))
+        _lib.check(rc, "pn2_prob_sample")
+    return out
+
+
 def farthest_point_sample(npoint: int, inp: torch.Tensor) -> torch.Tensor:
     """
     input:

@@ -134,3 +134,29 @@ def test_ball_threshold_is_exact_boundary(r):
 def test_ball_threshold_degenerate_radius():
     assert O.oracle_ball_threshold(1e-21) < 0
     assert O.oracle_ball_threshold(1e-20) < 0
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 8, 9, 63, 100, 1000, 8191, 8192, 8193, 20001])
+def test_prob_sample_restatement_is_an_inverse_cdf(n):
+    """oracle_prob_sample: a monotone float32 cumulative sum close to the float64 one, and the
+    lower-bound index of u*total in it (tf_sampling_g.cu:7-104)."""
+    rng = np.random.RandomState(n)
+    p = rng.random_sample((3, n)).astype(np.float32)
+    r = rng.random_sample((3, 40)).astype(np.float32)
+    r[:, 0], r[:, 1] = 0.0, 1.0
+    c = O.oracle_prob_cumsum(p)
+    ref = np.cumsum(p.astype(np.float64), axis=1)
+    assert np.abs(c - ref).max() <= 4e-7 * ref.max()
+    assert (c[:, 1:] >= c[:, :-1]).all()
+    idx = O.oracle_prob_sample(p, r)
+    for i in range(3):
+        q = (r[i] * c[i, -1]).astype(np.float32)
+        np.testing.assert_array_equal(idx[i], np.searchsorted(c[i], q, side="left").clip(0, n - 1))
+
+
+def test_prob_sample_known_answer():
+    # exact binary fractions: every association gives the same sums
+    p = np.array([[0.5, 0.25, 0.0, 0.25, 1.0]], np.float32)
+    np.testing.assert_array_equal(O.oracle_prob_cumsum(p), [[0.5, 0.75, 0.75, 1.0, 2.0]])
+    r = np.array([[0.0, 0.25, 0.3, 0.375, 0.4, 0.5, 0.75, 1.0]], np.float32)
+    np.testing.assert_array_equal(O.oracle_prob_sample(p, r), [[0, 0, 1, 1, 3, 3, 4, 4]])

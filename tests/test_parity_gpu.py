@@ -15,7 +15,7 @@ from oracle import oracle as O
 from pointnet2_b200 import _lib, workloads as W
 from pointnet2_b200.tf_grouping import group_point, knn_point, query_ball_point, select_top_k
 from pointnet2_b200.tf_interpolate import three_interpolate, three_nn, three_nn_interpolate
-from pointnet2_b200.tf_sampling import farthest_point_sample, farthest_point_sample_and_gather, gather_point
+from pointnet2_b200.tf_sampling import farthest_point_sample, farthest_point_sample_and_gather, gather_point, prob_sample
 
 pytestmark = pytest.mark.gpu
 
@@ -491,3 +491,47 @@ def test_kernels_launch_and_library_is_in_tree(dev):
     farthest_point_sample(4, xyz)
     assert _lib.launch_count() == before + 1
     assert os.path.dirname(_lib.lib_path()).endswith("pointnet2_b200")
+
+
+# ------------------------------------------------------------------------------- prob_sample
+@pytest.mark.parametrize("b,n,m", [(1, 1, 5), (3, 5, 64), (4, 1000, 300), (2, 8192, 100), (2, 8193, 100), (3, 30000, 1000),
+                                   (40, 257, 33)])
+def test_prob_sample_matches_oracle(dev, b, n, m):
+    rng = np.random.RandomState(n + m)
+    p = rng.random_sample((b, n)).astype(np.float32)
+    if n > 100:
+        p[:, rng.randint(0, n, n // 3)] = 0.0
+    r = rng.random_sample((b, m)).astype(np.float32)
+    r[:, 0] = 0.0
+    r[:, -1] = 1.0
+    np.testing.assert_array_equal(N(prob_sample(T(p, dev), T(r, dev))), O.oracle_prob_sample(p, r))
+
+
+@pytest.mark.parametrize("name", golden_names("prob_"))
+def test_prob_sample_matches_reference_golden(dev, name):
+    g = load_golden(name)
+    np.testing.assert_array_equal(N(prob_sample(T(g["inp"], dev), T(g["inpr"], dev))), g["out"])
+    lib = _lib.load()
+    p = T(g["inp"], dev)
+    temp = torch.empty_like(p)
+    assert lib.pn2_prob_sample(p.shape[0], p.shape[1], 0, p.data_ptr(), None, temp.data_ptr(), None, None) == 0
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(N(temp), g["cumsum"])  # the scratch holds the reference's cumulative sums
+
+
+@pytest.mark.skipif(not O.have_refcuda(), reason="oracle/_ref CUDA libraries did not travel")
+@pytest.mark.parametrize("b,n,m", [(8, 4096, 2048), (2, 100000, 4096), (33, 777, 100)])
+def test_prob_sample_matches_reference_cuda_kernel(dev, b, n, m):
+    rng = np.random.RandomState(b + n)
+    p = T(rng.random_sample((b, n)).astype(np.float32), dev)
+    r = T(rng.random_sample((b, m)).astype(np.float32), dev)
+    assert torch.equal(prob_sample(p, r), O.refcuda_prob_sample(p, r))
+
+
+def test_prob_sample_rejects_bad_shapes(dev):
+    with pytest.raises(ValueError):
+        prob_sample(torch.zeros(4, device=dev), torch.zeros(1, 4, device=dev))
+    with pytest.raises(ValueError):
+        prob_sample(torch.zeros(2, 4, device=dev), torch.zeros(3, 4, device=dev))
+    with pytest.raises(TypeError):
+        prob_sample(torch.zeros(2, 4, device=dev, dtype=torch.float64), torch.zeros(2, 4, device=dev))
