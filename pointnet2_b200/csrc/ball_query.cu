@@ -63,7 +63,9 @@ ball_query_kernel(int n, int m, float thr, int nsample, const float* __restrict_
                   const float* __restrict__ xyz2, int* __restrict__ idx, int* __restrict__ pts_cnt,
                   const int* __restrict__ grid_params, int grid_stride) {
     // clouds the uniform-grid path serves (flag written by bq_grid_build_kernel) are skipped here
-    if (grid_params && grid_params[(size_t)blockIdx.y * grid_stride] != 0) return;
+    if (grid_params && grid_params[(size_t)blockIdx.y * grid_stride] != 0 &&
+        batch_uses_grid(grid_params, (size_t)grid_stride, (int)gridDim.y))
+        return;
     constexpr int QPB = kBqThreads / G;      // queries per CTA
     constexpr int STEP = G * kBqUnroll;      // pairs consumed per unrolled step by one group
     // pair layout: s_xy[i] = (x0, x1, y0, y1) of points 2i, 2i+1; s_z[i] = (z0, z1)

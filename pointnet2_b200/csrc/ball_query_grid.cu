@@ -24,6 +24,7 @@ constexpr int kGqThreads = 256;    // query: 8 warps, one query per warp
 constexpr int kGridMaxDim = 16;    // cells per axis
 constexpr int kGridMaxN = 1 << 20;   // workspace sizing only: larger clouds take the brute-force path
 constexpr int kGridMinN = 2048;      // below this the brute-force kernel is already latency-bound
+constexpr float kGridDenseFrac = 0.9f;  // local-density estimate of points per ball above this fraction of nsample: early-exit scan wins
 constexpr int kHitCap = 128;       // hits buffered per query before falling back to the ordered scan
 // per-cloud parameter block (ints): [0] use_grid flag, [1..3] dims, [4] origin.x bits, [5] origin.y, [6] origin.z, [7] inv_h bits
 constexpr int kGridParamInts = 8;
@@ -128,10 +129,20 @@ bq_grid_build_kernel(int n, float radius, int nsample, const float* __restrict__
         const int per = (ncell + T - 1) / T;
         const int c0 = min(tid * per, ncell), c1 = min(c0 + per, ncell);
         int local = 0, heavy = 0;
+        float sq = 0.f;
         for (int c = c0; c < c1; ++c) {
-            local += s_cnt[c];
-            heavy |= (s_cnt[c] > 256) ? 1 : 0;  // a crowded cell (duplicate-heavy data): its neighbourhoods degenerate to scans
+            const int cntc = s_cnt[c];
+            local += cntc;
+            sq += (float)cntc * (float)cntc;
+            heavy |= (cntc > 256) ? 1 : 0;  // a crowded cell (duplicate-heavy data): its neighbourhoods degenerate to scans
         }
+        // density-aware estimate of the points per ball: a point of cell i sees about
+        // c_i * (ball volume / cell volume) neighbours, so the mean over points is
+        // sum(c_i^2)/n * 4.19 (r/h)^3.  Surface-like clouds fill few cells densely: their balls
+        // fill up and the early-exit scan wins even though the box-uniform estimate says sparse.
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(kFullMask, sq, o);
+        if (lane == 0) s_red[0][warp] = sq;
         if (heavy) s_heavy = 1;
         int incl = local;
 #pragma unroll
@@ -158,7 +169,12 @@ bq_grid_build_kernel(int n, float radius, int nsample, const float* __restrict__
         }
         if (tid == 0) cell_start[ncell] = n;
         __syncthreads();
-        use_grid = (s_heavy == 0);
+        float sqsum = (lane < NW) ? s_red[0][lane] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sqsum += __shfl_xor_sync(kFullMask, sqsum, o);
+        const float rh = radius * inv_h;
+        const float expect_local = 4.18879f * rh * rh * rh * sqsum / (float)n;
+        use_grid = (s_heavy == 0) && (expect_local < kGridDenseFrac * (float)nsample);
         if (use_grid) {
             // pass 2: scatter (order inside a cell does not matter: hits are rank-sorted by index later)
             for (int k = tid; k < n; k += T) {
@@ -188,7 +204,8 @@ bq_grid_query_kernel(int n, int m, float thr, int nsample, const float* __restri
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cloud = blockIdx.y;
     const int* __restrict__ params = ws + (size_t)cloud * ws_stride;
-    if (params[0] == 0) return;  // this cloud is served by the brute-force kernel
+    // this cloud is served by the brute-force kernel (its own flag, or the batch-level rule)
+    if (params[0] == 0 || !batch_uses_grid(ws, ws_stride, (int)gridDim.y)) return;
     const int q = blockIdx.x * (kGqThreads / 32) + warp;
     if (q >= m) return;  // warp-uniform; no CTA-wide barriers below
     const int dx = params[1], dy = params[2], dz = params[3];

@@ -39,6 +39,21 @@ __device__ __forceinline__ float d2_nofma(float ax, float ay, float az, float bx
 }
 
 // ---- warp helpers ----------------------------------------------------------------------------
+// Batch-level rule of the uniform-grid ball query, evaluated identically by the grid kernel and by
+// the brute-force kernel (each warp on its own, no barrier): the two kernels run back to back on one
+// stream, so splitting a batch between them only pays when the grid serves a fair share of it
+// (measured: 10 of 32 clouds pays, 2 of 32 costs 20 us).  `flags` is
+// the per-cloud flag word written by bq_grid_build_kernel, one every `stride` ints; batches larger
+// than 1024 clouds are judged on their first 1024.
+__device__ __forceinline__ bool batch_uses_grid(const int* __restrict__ flags, size_t stride, int b) {
+    const int lane = threadIdx.x & 31;
+    const int bb = b < 1024 ? b : 1024;
+    int cnt = 0;
+    for (int c = lane; c < bb; c += 32) cnt += (__ldg(flags + (size_t)c * stride) != 0) ? 1 : 0;
+    cnt = __reduce_add_sync(kFullMask, cnt);
+    return 4 * cnt >= bb;
+}
+
 __device__ __forceinline__ unsigned warp_max_u32(unsigned v) { return __reduce_max_sync(kFullMask, v); }
 
 // Lexicographic max of (hi, lo) pairs over the warp; every lane gets the result.

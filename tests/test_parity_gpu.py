@@ -211,6 +211,30 @@ def test_ball_query_grid_path_matches_oracle(dev, mode, gen, b, n, m, r, s):
     np.testing.assert_array_equal(N(idx), oi)
 
 
+@pytest.mark.parametrize("sparse_clouds", [0, 1, 2, 5, 8])
+def test_ball_query_mixed_batches_follow_the_batch_rule(dev, sparse_clouds):
+    """Batches mixing grid-friendly (sparse, uniform) and grid-hostile (dense surface / duplicate
+    heavy) clouds: the grid serves its clouds only when >= 1/4 of the batch qualifies, otherwise
+    everything goes to the brute-force kernel — either way the output is the oracle's."""
+    n, m, r, s = 4096, 300, 0.08, 24
+    parts = [W.cloud_uniform(1, n, 60 + i) for i in range(sparse_clouds)]
+    parts += [(W.cloud_surface(1, n, 70 + i) * 0.25 if i % 2 else W.cloud_duplicates(1, n, 80 + i)) for i in range(8 - sparse_clouds)]
+    xyz = np.concatenate(parts, 0).astype(np.float32)
+    new_xyz = O.oracle_gather_point(xyz, O.oracle_fps(m, xyz))
+    lib = _lib.load()
+    t = T(xyz, dev)
+    ws_bytes = int(lib.pn2_query_ball_point_workspace_bytes(8, n))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    assert lib.pn2_ball_grid_build(8, n, r, s, t.data_ptr(), ws.data_ptr(), ws_bytes, None) == 0
+    torch.cuda.synchronize()
+    flags = ws.view(torch.int32)[:: ws_bytes // 32][:8].cpu().numpy() != 0
+    assert flags[:sparse_clouds].all() and not flags[sparse_clouds:].any(), flags
+    idx, cnt = query_ball_point(r, s, t, T(new_xyz, dev))
+    oi, oc = O.oracle_query_ball_point(r, s, xyz, new_xyz)
+    np.testing.assert_array_equal(N(cnt), oc)
+    np.testing.assert_array_equal(N(idx), oi)
+
+
 def test_ball_query_grid_free_queries_outside_the_box(dev):
     """Queries outside the data's bounding box (some within the radius of border points, some far
     away) through the grid path."""
