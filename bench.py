@@ -364,7 +364,9 @@ def run_b200_arm(args, cfg):
     #      per cloud busy (b of 148), so independent batches on separate streams fill the GPU; this
     #      is reported beside `value` (which stays one batch at a time), never instead of it.
     inflight = None
-    if graph is not None and args.in_flight > 1:
+    # rank-uniform switch: the leg runs only if the graph was captured on EVERY rank
+    graph_everywhere = max_over_ranks(0.0 if graph is not None else 1.0) == 0.0
+    if graph_everywhere and args.in_flight > 1:
         try:
             lanes = []
             for _ in range(args.in_flight):
@@ -411,22 +413,28 @@ def run_b200_arm(args, cfg):
 
             run_lanes(max(args.warmup, len(lanes)))
             q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            barrier()
+            torch.cuda.synchronize(dev)  # no collective inside this try: a failing rank must not strand the others
             q0.record(st)
             run_lanes(args.steps, q0)
             for _, ls, _ in lanes:
                 st.wait_stream(ls)
             q1.record(st)
-            barrier()
+            torch.cuda.synchronize(dev)
             launches += launches_per_step * args.steps
-            fl_ms = max_over_ranks(q0.elapsed_time(q1))
+            fl_local = q0.elapsed_time(q1)
             lanes_same = all(bool(torch.equal(bf["idx"], idx)) and bool(torch.equal(bf["grouped"], grouped)) for _, _, bf in lanes)
-            inflight = {"batches_in_flight": len(lanes), "value": world * b * n * args.steps / (fl_ms * 1e-3), "unit": UNIT,
-                        "ms_per_step": fl_ms / args.steps, "outputs_match_sequential": lanes_same,
+            inflight = {"batches_in_flight": len(lanes), "unit": UNIT, "outputs_match_sequential": lanes_same,
                         "timing": "one event pair around all steps, L2 flush inside"}
         except Exception as e:  # noqa: BLE001 — secondary number only
+            fl_local = float("inf")
             inflight = {"error": f"{type(e).__name__}: {e}"}
             torch.cuda.synchronize(dev)
+        # every rank takes part in the reduction whether or not its own leg succeeded
+        fl_ms = max_over_ranks(fl_local)
+        if fl_ms != float("inf") and "error" not in inflight:
+            inflight.update(value=world * b * n * args.steps / (fl_ms * 1e-3), ms_per_step=fl_ms / args.steps)
+        elif "error" not in inflight:
+            inflight = {"error": "the leg failed on another rank"}
 
     # ---- end-to-end leg: host buffers through the C-ABI host call --------------------------
     sess = SetAbstractionHost(b, n, m, r, s, device=dev)
