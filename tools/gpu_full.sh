@@ -15,7 +15,7 @@ echo "== report + bq sweep"
 timeout 900 python bench.py --report gpurun_out/report.json > gpurun_out/report.log 2>&1; echo "report rc=$?"
 timeout 600 python bench.py --bq-sweep > gpurun_out/bq_sweep.log 2>&1; echo "bq sweep rc=$?"
 echo "== ncu"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv --log-file gpurun_out/launches.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo "ncu list rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1; echo "ncu list rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fps_cta_kernel -s 2 -c 1 -o gpurun_out/prof_fps -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_fps.log 2>&1; echo "ncu fps rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:bq_grid_query_kernel -s 2 -c 1 -o gpurun_out/prof_bq -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bq.log 2>&1; echo "ncu bq rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:group_narrow -s 2 -c 1 -o gpurun_out/prof_group -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_group.log 2>&1; echo "ncu group rc=$?"
