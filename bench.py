@@ -528,6 +528,10 @@ def run_b200_arm(args, cfg):
                          "algorithmic_bytes_per_launch": fps_bytes, "ms_per_launch": fps_ms,
                          "note": "FPS is a serial chain of npoint argmax steps: latency/FP32-issue bound, not HBM bound",
                          "secondary": {"point_pairs_per_s": b * (m - 1) * n / (fps_ms * 1e-3),
+                                       # 10 FP32/ALU instructions per point pair is the minimum for the exact
+                                       # arithmetic contract (SASS: 3 FADD, FMUL, 2 FFMA, FMNMX, FSETP, FSEL, SEL)
+                                       "fp32_issue_frac_of_gpu": b * (m - 1) * n * 10 / (fps_ms * 1e-3) / (148 * 128 * 1.965e9),
+                                       "fp32_issue_frac_of_occupied_sms": b * (m - 1) * n * 10 / (fps_ms * 1e-3) / (min(b, 148) * 128 * 1.965e9),
                                        "whole_layer_GBps": layer_bytes / (statistics.mean(t_step) * 1e-3) / 1e9,
                                        "whole_layer_frac": layer_bytes / (statistics.mean(t_step) * 1e-3) / 1e9 / peak}},
             "kernels_ms": {"fps_gather": fps_ms, "query_ball_point": statistics.mean(t_bq), "group_point": statistics.mean(t_grp),
