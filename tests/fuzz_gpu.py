@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Randomised differential test of every op against the oracle (TEST TOOL, runs on a GPU box).
 
-    python tools/fuzz_gpu.py [--seconds 120] [--seed 0]
+    python tests/fuzz_gpu.py [--seconds 120] [--seed 0]
 
 Draws random shapes / distributions / radii, runs the CUDA op and the C oracle on the same input and
 requires bit-equal outputs (tolerance only where float atomics reorder sums).  Every failing case
@@ -27,7 +27,7 @@ from pointnet2_b200.tf_interpolate import three_interpolate, three_nn, three_nn_
 from pointnet2_b200.tf_sampling import farthest_point_sample_and_gather, gather_point, prob_sample  # noqa: E402
 from pointnet2_b200.pointnet_util import group_and_concat  # noqa: E402
 
-dev = torch.device("cuda:0")
+dev = torch.device("cuda:0")  # only dereferenced when a case runs
 
 
 def T(a):
@@ -166,6 +166,19 @@ def case_prob(rs):
 
 
 CASES = [case_fps, case_ball, case_group, case_interp, case_sort, case_prob]
+
+
+def run(seed: int, iterations: int):
+    """`iterations` random cases (round-robin over the ops); returns (counts, failures)."""
+    rs = np.random.RandomState(seed)
+    counts, fails = {}, []
+    for it in range(iterations):
+        fn = CASES[it % len(CASES)]
+        ok, p = fn(rs)
+        counts[p["op"]] = counts.get(p["op"], 0) + 1
+        if not ok:
+            fails.append(p)
+    return counts, fails
 
 
 def main():
