@@ -559,3 +559,16 @@ def test_prob_sample_rejects_bad_shapes(dev):
         prob_sample(torch.zeros(2, 4, device=dev), torch.zeros(3, 4, device=dev))
     with pytest.raises(TypeError):
         prob_sample(torch.zeros(2, 4, device=dev, dtype=torch.float64), torch.zeros(2, 4, device=dev))
+
+
+@pytest.mark.parametrize("n", [131073, 262144, 262145, 300001])
+def test_fps_at_and_beyond_the_cluster_capacity(dev, n):
+    """The planner's last two regimes as the planner picks them (no forced config): 16-CTA clusters
+    with coordinates in shared memory up to n = 262144, the global-scratch fallback beyond."""
+    xyz = W.cloud_uniform(2, n, 91)
+    want = O.oracle_fps(6, xyz)
+    t = T(xyz, dev)
+    np.testing.assert_array_equal(N(farthest_point_sample(6, t)), want)
+    fi, fx = farthest_point_sample_and_gather(6, t)
+    np.testing.assert_array_equal(N(fi), want)
+    np.testing.assert_array_equal(N(fx), O.oracle_gather_point(xyz, want))
