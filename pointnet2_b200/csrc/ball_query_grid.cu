@@ -72,7 +72,10 @@ bq_grid_build_kernel(int n, float radius, int nsample, const float* __restrict__
         for (int c = 0; c < 3; ++c) {
             const float v = __ldg(pts + 3 * (size_t)k + c);
             mn[c] = fminf(mn[c], v);
-            mx[c] = fmaxf(mx[c], v);
+            // a NaN coordinate (fminf/fmaxf would ignore it) must disable the grid: the reference
+            // counts a NaN point as a hit in EVERY ball (fmaxf(NaN,1e-20f) < radius), which only the
+            // brute-force scan reproduces; an infinite box does that (finite_box below)
+            mx[c] = (v == v) ? fmaxf(mx[c], v) : INFINITY;
         }
     }
 #pragma unroll

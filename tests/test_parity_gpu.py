@@ -572,3 +572,21 @@ def test_fps_at_and_beyond_the_cluster_capacity(dev, n):
     fi, fx = farthest_point_sample_and_gather(6, t)
     np.testing.assert_array_equal(N(fi), want)
     np.testing.assert_array_equal(N(fx), O.oracle_gather_point(xyz, want))
+
+
+@pytest.mark.parametrize("n", [600, 5000])
+def test_ball_query_non_finite_points_follow_the_reference(dev, n):
+    """A NaN point is a hit in every ball, an infinite one in none (tf_grouping_g.cu:24-25 with
+    fmaxf): the uniform-grid path must step aside for such clouds and the scan must agree with
+    the oracle."""
+    xyz = W.cloud_uniform(3, n, 95)
+    xyz[0, 17] = np.nan
+    xyz[0, n // 2, 1] = np.nan
+    xyz[1, 40, 2] = np.inf
+    q = O.oracle_gather_point(xyz[:, ::3].copy(), O.oracle_fps(64, xyz[:, ::3].copy()))
+    q[~np.isfinite(q)] = 0.5
+    idx, cnt = query_ball_point(0.06, 16, T(xyz, dev), T(q, dev))
+    oi, oc = O.oracle_query_ball_point(0.06, 16, xyz, q)
+    np.testing.assert_array_equal(N(cnt), oc)
+    np.testing.assert_array_equal(N(idx), oi)
+    assert (oi[0] == 17).any()
