@@ -17,7 +17,8 @@
  *     like the reference (tf_sampling.cpp:174, tf_grouping.cpp:204, tf_interpolate.cpp:258).
  *   - return value: 0 on success, otherwise a cudaError_t (argument errors return
  *     cudaErrorInvalidValue = 1).  pn2_error_string() translates.
- *   - limits: every tensor must have fewer than 2^31 elements per batch entry; n, m < 2^31;
+ *   - limits: every tensor must have fewer than 2^31 elements per batch entry; n, m < 2^31
+ *     (totals are indexed with 64 bits: gather / concat / interpolate are tested beyond 2^32 elements);
  *     ops that put the batch on gridDim.y (ball query, three_nn, the row kernels) take b <= 65535.
  *   - the pn2_set_* tuning hooks write process-wide state without locking: call them before use,
  *     not concurrently with launches.
@@ -74,7 +75,9 @@ int pn2_query_ball_point(int b, int n, int m, float radius, int nsample, const f
  * pn2_query_ball_point_workspace_bytes(b, n) bytes: clouds whose balls are sparse are binned into
  * a uniform grid (cell edge >= 1.01 radius) and each query only tests its 3x3x3 cell neighbourhood;
  * the other clouds (dense or badly skewed ones, and any call with workspace == NULL or n < 2048)
- * take the brute-force path above.  workspace_bytes == 0 from the size query means "not applicable". */
+ * take the brute-force path above, as does the whole batch when fewer than a quarter of its clouds
+ * qualify and any cloud with a NaN coordinate (the reference counts a NaN point as a hit in every
+ * ball, which only the scan reproduces).  workspace_bytes == 0 from the size query means "not applicable". */
 size_t pn2_query_ball_point_workspace_bytes(int b, int n);
 int pn2_query_ball_point_ws(int b, int n, int m, float radius, int nsample, const float* xyz1,
                             const float* xyz2, int* idx, int* pts_cnt, void* workspace,
