@@ -116,91 +116,96 @@ def cpu_cores() -> int:
         return os.cpu_count() or 1
 
 
-def cpu_pass(xyz: np.ndarray, npoint: int, radius: float, nsample: int, threads: int, use_ref: bool):
-    """One pass of the hot path on the host: per cloud FPS (oracle port) + gather + ball query +
-    group (reference CPU functions if available), clouds spread over `threads` host threads
-    (ctypes releases the GIL)."""
-    from concurrent.futures import ThreadPoolExecutor
+# The CPU legs keep EVERY host core busy: the reference's functions are single-threaded per call, so
+# the unit of parallel work is one cloud (FPS is a serial chain per cloud), and clouds of several
+# batches are in flight at once — worker processes (no GIL), forked before the timed region.
+_CPU = {}
 
-    from oracle import oracle as O
 
-    def one(i):
-        c = xyz[i:i + 1]
-        idx = O.oracle_fps(npoint, c)
-        new_xyz = O.oracle_gather_point(c, idx)
-        if use_ref:
-            bi = O.refcpu_query_ball_point(radius, nsample, c, new_xyz)
-            g = O.refcpu_group_point(c, bi)
-        else:
-            bi, _ = O.oracle_query_ball_point(radius, nsample, c, new_xyz, use_fma=False)
-            g = O.oracle_group_point(c, bi)
-        return g.shape
-
-    if threads <= 1:
-        for i in range(xyz.shape[0]):
-            one(i)
+def _cpu_one_cloud(i: int) -> int:
+    """One cloud through the hot path on the host: FPS (C restatement — the reference registers FPS
+    for the GPU only, tf_sampling.cpp:123) + gather + ball query + group (the reference's own CPU
+    functions from oracle/_ref when they were built, test/query_ball_point.cpp:19-66)."""
+    O, xyz, c = _CPU["O"], _CPU["xyz"], _CPU["cfg"]
+    cl = xyz[i % xyz.shape[0]][None]
+    idx = O.oracle_fps(c["npoint"], cl)
+    new_xyz = O.oracle_gather_point(cl, idx)
+    if _CPU["use_ref"]:
+        bi = O.refcpu_query_ball_point(c["radius"], c["nsample"], cl, new_xyz)
+        g = O.refcpu_group_point(cl, bi)
     else:
-        with ThreadPoolExecutor(max_workers=threads) as ex:
-            list(ex.map(one, range(xyz.shape[0])))
+        bi, _ = O.oracle_query_ball_point(c["radius"], c["nsample"], cl, new_xyz, use_fma=False)
+        g = O.oracle_group_point(cl, bi)
+    return int(g.shape[1])
 
 
-def cpu_baseline(cfg, budget_s: float = 12.0):
+def _cpu_setup(cfg):
     from oracle import oracle as O
     from pointnet2_b200 import workloads as W
-    xyz = W.DISTRIBUTIONS[cfg["dist"]](cfg["b"], cfg["n"], cfg["seed"])
-    cores = cpu_cores()
     use_ref = O.have_refcpu()
     O.lib()
     if use_ref:
         O.refcpu()
-    cpu_pass(xyz[:min(cores, cfg["b"])], cfg["npoint"], cfg["radius"], cfg["nsample"], cores, use_ref)  # warm-up
-    t0 = time.perf_counter()
-    passes = 0
-    while True:
-        cpu_pass(xyz, cfg["npoint"], cfg["radius"], cfg["nsample"], cores, use_ref)
-        passes += 1
+    _CPU.update(O=O, cfg=cfg, use_ref=use_ref, xyz=W.DISTRIBUTIONS[cfg["dist"]](cfg["b"], cfg["n"], cfg["seed"]))
+    return use_ref
+
+
+def cpu_throughput(cfg, steps: int, warmup: int):
+    """points/s of `steps` batches of the workload over all host cores; returns (value, seconds, cores,
+    use_ref, single_core_value)."""
+    import multiprocessing as mp
+    from concurrent.futures import ProcessPoolExecutor
+    use_ref = _cpu_setup(cfg)
+    cores = cpu_cores()
+    b = cfg["b"]
+    t1 = time.perf_counter()  # the faithful single-threaded figure first (also warms the libraries)
+    for i in range(2):
+        _cpu_one_cloud(i)
+    one_core = 2 * cfg["n"] / (time.perf_counter() - t1)
+    with ProcessPoolExecutor(max_workers=cores, mp_context=mp.get_context("fork")) as ex:
+        chunk = max(1, (max(warmup, 1) * b) // (4 * cores))
+        list(ex.map(_cpu_one_cloud, range(max(warmup, 1) * b, ), chunksize=chunk))   # spawn + warm every worker
+        list(ex.map(_cpu_one_cloud, range(cores), chunksize=1))
+        chunk = max(1, (steps * b) // (8 * cores))
+        t0 = time.perf_counter()
+        list(ex.map(_cpu_one_cloud, range(steps * b), chunksize=chunk))
         el = time.perf_counter() - t0
-        if el >= budget_s or passes >= 200:
-            break
-    value = passes * cfg["b"] * cfg["n"] / el
-    # the reference's CPU functions are single-threaded: one pass on one core as the faithful figure
-    t1 = time.perf_counter()
-    cpu_pass(xyz[:4], cfg["npoint"], cfg["radius"], cfg["nsample"], 1, use_ref)
-    one_core = 4 * cfg["n"] / (time.perf_counter() - t1)
-    return {"value": value, "unit": UNIT, "cores": cores, "single_core_value": one_core,
-            "kind": "port",  # FPS dominates the CPU time and the reference has no CPU FPS (GPU-only op)
-            "sample": (f"{passes} pass(es) of the full {cfg['name']} batch ({cfg['b']}x{cfg['n']} pts) in {el:.2f}s on {cores} "
-                       f"host threads (one cloud per task); FPS = oracle C restatement of tf_sampling_g.cu:105-170; "
-                       f"ball query+group = " + ("reference CPU functions test/query_ball_point.cpp:19-66 (oracle/_ref)" if use_ref
-                                                  else "oracle C restatement")),
-            "ms_per_pass": 1e3 * el / passes}
+    return steps * b * cfg["n"] / el, el, cores, use_ref, one_core
+
+
+def _cpu_sample_text(cfg, steps, el, cores, use_ref):
+    return (f"{steps} batches of {cfg['name']} ({cfg['b']}x{cfg['n']} pts each) in {el:.2f}s with all {cores} host cores busy "
+            f"(one cloud per task, {steps * cfg['b']} tasks over {cores} worker processes, batches overlap); FPS = C restatement of "
+            f"tf_sampling_g.cu:105-170 (the reference has no CPU FPS); ball query+group = "
+            + ("the reference's CPU functions test/query_ball_point.cpp:19-66 (oracle/_ref)" if use_ref else "oracle C restatement"))
+
+
+def cpu_baseline(cfg, budget_s: float = 12.0):
+    """The CPU arm as a child process (this process holds a CUDA context: no fork from here)."""
+    steps = 40
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps), "--warmup", "3"],
+                       capture_output=True, text=True, timeout=max(120.0, 20 * budget_s),
+                       env={k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")})
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    if r.returncode != 0 or not lines:
+        return {"error": (r.stderr or "no output")[-300:]}
+    return json.loads(lines[-1])["cpu_baseline"]
 
 
 # ------------------------------------------------------------------------------------------------
 def run_reference_arm(args, cfg):
-    """--impl reference: the reference's CPU implementation of the path on the host cores."""
+    """--impl reference: the reference's CPU implementation of the path on ALL host cores."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # other ranks exit 0 without work
-    from oracle import oracle as O
-    from pointnet2_b200 import workloads as W
-    xyz = W.DISTRIBUTIONS[cfg["dist"]](cfg["b"], cfg["n"], cfg["seed"])
-    cores = cpu_cores()
-    use_ref = O.have_refcpu()
-    for _ in range(max(args.warmup, 1)):
-        cpu_pass(xyz, cfg["npoint"], cfg["radius"], cfg["nsample"], cores, use_ref)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        cpu_pass(xyz, cfg["npoint"], cfg["radius"], cfg["nsample"], cores, use_ref)
-    el = time.perf_counter() - t0
-    value = args.steps * cfg["b"] * cfg["n"] / el
-    sample = (f"each step = the full {cfg['name']} batch ({cfg['b']}x{cfg['n']} pts) on {cores} host threads; FPS = C restatement "
-              f"(the reference has no CPU FPS), ball query+group = " + ("reference CPU code (oracle/_ref)" if use_ref else "oracle port"))
+    value, el, cores, use_ref, one_core = cpu_throughput(cfg, args.steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(cfg, 1),
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "single_core_value": one_core,
+                             "kind": "port",  # FPS dominates the CPU time and the reference has no CPU FPS (GPU-only op)
+                             "sample": _cpu_sample_text(cfg, args.steps, el, cores, use_ref)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
