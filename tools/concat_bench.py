@@ -1,4 +1,4 @@
-"""Time the fused grouping tail (pn2_group_concat) at the BASELINE layer shapes; PN2_CONCAT_TILE=0 selects the row kernel."""
+"""Time the fused grouping tail (pn2_group_concat) at the BASELINE layer shapes."""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -20,5 +20,5 @@ for (b, n, c, m, s) in [(16, 1024, 64, 256, 32), (16, 256, 128, 64, 32), (32, 51
         a.record(); group_and_concat(xyz, new_xyz, pts, idx, xyz_first=False); e.record(); e.synchronize(); ts.append(a.elapsed_time(e))
     ts.sort(); ms = ts[len(ts) // 2]
     by = 4 * b * m * s + 4 * b * min(n, m * s) * (c + 3) + 4 * b * m * s * (c + 3) + 12 * b * m * s
-    rows.append(dict(tile=os.environ.get("PN2_CONCAT_TILE", "1"), b=b, n=n, c=c, m=m, s=s, ms=round(ms, 4), GBps=round(by / ms / 1e6), checksum=float(out.double().sum())))
+    rows.append(dict(b=b, n=n, c=c, m=m, s=s, ms=round(ms, 4), GBps=round(by / ms / 1e6), checksum=float(out.double().sum())))
     print(rows[-1], flush=True)
