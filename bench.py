@@ -245,6 +245,7 @@ def run_reference_arm(args, cfg):
 
 
 def workload_config(cfg, world):
+    """Identical in both arms (the driver compares it key by key)."""
     return {"workload": f"{cfg['name']}: SSG SA layer FPS+gather_point+query_ball_point+group_point(xyz), "
                         f"B={cfg['b']}/GPU N={cfg['n']} npoint={cfg['npoint']} nsample={cfg['nsample']} radius={cfg['radius']}",
             "global_batch": cfg["b"] * world, "points_per_cloud": cfg["n"], "parallelism": f"dp{world} (clouds sharded, no collective)",
@@ -252,11 +253,83 @@ def workload_config(cfg, world):
 
 
 # ------------------------------------------------------------------------------------------------
+def run_reference_cuda_arm(args, cfg):
+    """--impl reference_cuda (child of the product arm, rank 0 only): the reference's OWN CUDA kernels
+    (tf_sampling_g.cu:105-181,203-208; tf_grouping_g.cu:3-57,125-136), rebuilt unmodified for sm_100a
+    into oracle/_ref, timed with CUDA events on this box at the driver line's workload.  A reported
+    comparator like cpu_baseline — never part of the product's timed region."""
+    import torch
+    from ctypes import c_float, c_int, c_void_p
+
+    from oracle import oracle as O
+    from pointnet2_b200 import workloads as W
+    if not O.have_refcuda():
+        print(json.dumps({"reference_cuda": {"unavailable": "oracle/_ref CUDA libraries are not in this tree"}}), flush=True)
+        return
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    samp, grp = O.refcuda()
+    b, n, m, s, r = cfg["b"], cfg["n"], cfg["npoint"], cfg["nsample"], cfg["radius"]
+    xyz = torch.from_numpy(W.DISTRIBUTIONS[cfg["dist"]](b, n, cfg["seed"])).to(dev)
+    temp = torch.empty((32, n), dtype=torch.float32, device=dev)
+    fi = torch.zeros((b, m), dtype=torch.int32, device=dev)
+    nx = torch.empty((b, m, 3), dtype=torch.float32, device=dev)
+    idx = torch.zeros((b, m, s), dtype=torch.int32, device=dev)
+    cnt = torch.zeros((b, m), dtype=torch.int32, device=dev)
+    g = torch.empty((b, m, s, 3), dtype=torch.float32, device=dev)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    P = lambda t: c_void_p(t.data_ptr())  # noqa: E731
+    ops = [
+        ("farthestpointsamplingLauncher", lambda: samp._Z29farthestpointsamplingLauncheriiiPKfPfPi(c_int(b), c_int(n), c_int(m), P(xyz), P(temp), P(fi))),
+        ("gatherpointLauncher", lambda: samp._Z19gatherpointLauncheriiiPKfPKiPf(c_int(b), c_int(n), c_int(m), P(xyz), P(fi), P(nx))),
+        ("queryBallPointLauncher", lambda: grp._Z22queryBallPointLauncheriiifiPKfS0_PiS1_(c_int(b), c_int(n), c_int(m), c_float(r), c_int(s), P(xyz), P(nx), P(idx), P(cnt))),
+        ("groupPointLauncher", lambda: grp._Z18groupPointLauncheriiiiiPKfPKiPf(c_int(b), c_int(n), c_int(3), c_int(m), c_int(s), P(xyz), P(idx), P(g))),
+    ]
+    # the reference launches on the legacy default stream: time there
+    st = torch.cuda.default_stream(dev)
+    steps = max(3, min(args.steps, 10))
+    ms = {k: [] for k, _ in ops}
+    with torch.cuda.stream(st):
+        for it in range(3 + steps):
+            flush.zero_()
+            for name, fn in ops:
+                a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(st)
+                fn()
+                z.record(st)
+                z.synchronize()
+                if it >= 3:
+                    ms[name].append(a.elapsed_time(z))
+    per = {k: statistics.median(v) for k, v in ms.items()}
+    total = sum(per.values())
+    print(json.dumps({"reference_cuda": {
+        "what": "the reference's own CUDA kernels (tf_sampling_g.cu, tf_grouping_g.cu), nvcc -O2 for sm_100a, unmodified, "
+                "legacy default stream, CUDA events, L2 flushed before each step",
+        "kernels_ms": per, "ms_per_step": total, "value": b * n / (total * 1e-3), "unit": UNIT, "steps": steps,
+        "workload": workload_config(cfg, 1)["workload"]}}), flush=True)
+
+
+def child_json(argv, key, timeout=600.0):
+    """Run bench.py in a child process (fresh CUDA context / no fork from a CUDA process) and pick `key` from its JSON line."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__)] + argv, capture_output=True, text=True, timeout=timeout,
+                           env={k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")})
+    except subprocess.TimeoutExpired:
+        return {"error": f"timed out after {timeout:.0f}s"}
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    if r.returncode != 0 or not lines:
+        return {"error": (r.stderr or "no output")[-300:]}
+    return json.loads(lines[-1]).get(key, {"error": f"no {key} in the child's line"})
+
+
+# ------------------------------------------------------------------------------------------------
 def run_b200_arm(args, cfg):
+    import ctypes
+
     import torch
     import torch.distributed as dist
 
-    from pointnet2_b200 import _lib, workloads as W
+    from pointnet2_b200 import _lib, numa, workloads as W
     from pointnet2_b200.host import SetAbstractionHost, SetAbstractionPipeline
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -266,6 +339,7 @@ def run_b200_arm(args, cfg):
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa.bind_cpus(dev)  # one process per GPU: run (and first-touch pinned memory) on the GPU's own socket
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -273,32 +347,46 @@ def run_b200_arm(args, cfg):
     b, n, m, s, r = cfg["b"], cfg["n"], cfg["npoint"], cfg["nsample"], cfg["radius"]
     xyz_np = W.DISTRIBUTIONS[cfg["dist"]](b, n, cfg["seed"] + rank)
     xyz = torch.from_numpy(xyz_np).to(dev)
-    fps_idx = torch.empty((b, m), dtype=torch.int32, device=dev)
-    new_xyz = torch.empty((b, m, 3), dtype=torch.float32, device=dev)
-    idx = torch.empty((b, m, s), dtype=torch.int32, device=dev)
-    cnt = torch.empty((b, m), dtype=torch.int32, device=dev)
-    grouped = torch.empty((b, m, s, 3), dtype=torch.float32, device=dev)
+
+    def out_buffers():
+        return dict(fps_idx=torch.empty((b, m), dtype=torch.int32, device=dev), new_xyz=torch.empty((b, m, 3), dtype=torch.float32, device=dev),
+                    idx=torch.empty((b, m, s), dtype=torch.int32, device=dev), cnt=torch.empty((b, m), dtype=torch.int32, device=dev),
+                    grouped=torch.empty((b, m, s, 3), dtype=torch.float32, device=dev))
+
+    seq, fus = out_buffers(), out_buffers()
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
     bq_ws_bytes = int(lib.pn2_query_ball_point_workspace_bytes(b, n))  # caller-provided scratch for the grid path
     bq_ws = torch.empty(bq_ws_bytes, dtype=torch.uint8, device=dev) if bq_ws_bytes else None
+    dws_bytes = int(lib.pn2_sa_layer_device_workspace_bytes(b, n, m, s))
     st = torch.cuda.current_stream(dev)
     sp = st.cuda_stream
 
-    def step_device(ev=None):
+    def step_sequential(ev=None):
+        """The four reference ops as three separate launches (the per-kernel breakdown and the
+        bit-identity check of the overlapped layer)."""
+        o = seq
         if ev:
             ev[0].record(st)
-        rc = lib.pn2_fps_gather(b, n, m, xyz.data_ptr(), fps_idx.data_ptr(), new_xyz.data_ptr(), sp)
+        rc = lib.pn2_fps_gather(b, n, m, xyz.data_ptr(), None, o["fps_idx"].data_ptr(), o["new_xyz"].data_ptr(), sp)
         if ev:
             ev[1].record(st)
-        rc |= lib.pn2_query_ball_point_ws(b, n, m, r, s, xyz.data_ptr(), new_xyz.data_ptr(), idx.data_ptr(), cnt.data_ptr(),
+        rc |= lib.pn2_query_ball_point_ws(b, n, m, r, s, xyz.data_ptr(), o["new_xyz"].data_ptr(), o["idx"].data_ptr(), o["cnt"].data_ptr(),
                                           bq_ws.data_ptr() if bq_ws is not None else None, bq_ws_bytes, sp)
         if ev:
             ev[2].record(st)
-        rc |= lib.pn2_group_point(b, n, 3, m, s, xyz.data_ptr(), idx.data_ptr(), grouped.data_ptr(), sp)
+        rc |= lib.pn2_group_point(b, n, 3, m, s, xyz.data_ptr(), o["idx"].data_ptr(), o["grouped"].data_ptr(), sp)
         if ev:
             ev[3].record(st)
         if rc:
             raise RuntimeError(f"kernel launch failed rc={rc}")
+
+    def layer(o, ws, stream_ptr):
+        """The product's layer call: FPS+gather with the ball query + grouping overlapped on the idle SMs."""
+        rc = lib.pn2_sa_layer_device(b, n, m, r, s, xyz.data_ptr(), o["fps_idx"].data_ptr(), o["new_xyz"].data_ptr(), o["idx"].data_ptr(),
+                                     o["cnt"].data_ptr(), o["grouped"].data_ptr(), 0, ws.data_ptr() if ws is not None else None,
+                                     dws_bytes, stream_ptr)
+        if rc:
+            raise RuntimeError(f"pn2_sa_layer_device failed rc={rc}")
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -316,53 +404,37 @@ def run_b200_arm(args, cfg):
     # ---- per-kernel breakdown (sequential launches on one stream, events between the ops) -----
     for _ in range(args.warmup):
         flush.zero_()
-        step_device()
+        step_sequential()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     barrier()
     for k in range(args.steps):
         flush.zero_()
-        step_device(evs[k])
+        step_sequential(evs[k])
     barrier()
     t_fps = [e[0].elapsed_time(e[1]) for e in evs]
     t_bq = [e[1].elapsed_time(e[2]) for e in evs]
     t_grp = [e[2].elapsed_time(e[3]) for e in evs]
     t_seq = [e[0].elapsed_time(e[3]) for e in evs]
 
-    # ---- device-resident leg (the `value`): the same step as ONE CUDA graph — the ball-query grid
-    #      build only needs xyz, so it is forked onto a second stream and overlaps the FPS kernel ----
-    side = torch.cuda.Stream(dev)
-    fork_ev, join_ev = torch.cuda.Event(), torch.cuda.Event()
-
-    def step_overlapped(cur):
-        sc = cur.cuda_stream
-        rc = 0
-        if bq_ws is not None:
-            fork_ev.record(cur)
-            side.wait_event(fork_ev)
-            rc |= lib.pn2_ball_grid_build(b, n, r, s, xyz.data_ptr(), bq_ws.data_ptr(), bq_ws_bytes, side.cuda_stream)
-            join_ev.record(side)
-        rc |= lib.pn2_fps_gather(b, n, m, xyz.data_ptr(), fps_idx.data_ptr(), new_xyz.data_ptr(), sc)
-        if bq_ws is not None:
-            cur.wait_event(join_ev)
-            rc |= lib.pn2_query_ball_point_prebuilt(b, n, m, r, s, xyz.data_ptr(), new_xyz.data_ptr(), idx.data_ptr(), cnt.data_ptr(),
-                                                    bq_ws.data_ptr(), bq_ws_bytes, sc)
-        else:
-            rc |= lib.pn2_query_ball_point(b, n, m, r, s, xyz.data_ptr(), new_xyz.data_ptr(), idx.data_ptr(), cnt.data_ptr(), sc)
-        rc |= lib.pn2_group_point(b, n, 3, m, s, xyz.data_ptr(), idx.data_ptr(), grouped.data_ptr(), sc)
-        if rc:
-            raise RuntimeError(f"kernel launch failed rc={rc}")
-
-    graph, launch_mode, launches_per_step = None, "direct launches, grid build on a second stream", 0
+    # ---- device-resident leg (the `value`): ONE pn2_sa_layer_device call per step — two launches, the
+    #      second a programmatically dependent grid that consumes centroids while the sampling chain
+    #      runs — replayed as a CUDA graph when capture works ----
+    dws = torch.empty(dws_bytes, dtype=torch.uint8, device=dev) if dws_bytes else None
+    layer(fus, dws, sp)  # loads modules / sets function attributes outside any capture
+    torch.cuda.synchronize(dev)
+    l0 = _lib.launch_count()
+    layer(fus, dws, sp)
+    torch.cuda.synchronize(dev)
+    launches_per_step = _lib.launch_count() - l0
+    graph, launch_mode = None, "direct launches"
     try:
-        step_overlapped(st)  # loads modules / sets function attributes outside the capture
-        torch.cuda.synchronize(dev)
-        l0 = _lib.launch_count()
         g = torch.cuda.CUDAGraph()
         cap = torch.cuda.Stream(dev)
         with torch.cuda.graph(g, stream=cap):
-            step_overlapped(torch.cuda.current_stream(dev))
-        launches_per_step = _lib.launch_count() - l0
-        graph, launch_mode = g, "one CUDA graph per step, grid build forked onto a second stream"
+            layer(fus, dws, torch.cuda.current_stream(dev).cuda_stream)
+        g.replay()
+        torch.cuda.synchronize(dev)
+        graph, launch_mode = g, "one CUDA graph per step"
     except Exception as e:  # noqa: BLE001 — fall back to direct launches, say so in the JSON
         launch_mode += f" (graph capture failed: {type(e).__name__})"
         torch.cuda.synchronize(dev)
@@ -371,7 +443,7 @@ def run_b200_arm(args, cfg):
         if graph is not None:
             graph.replay()
         else:
-            step_overlapped(st)
+            layer(fus, dws, sp)
 
     for _ in range(args.warmup):
         flush.zero_()
@@ -380,7 +452,6 @@ def run_b200_arm(args, cfg):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches0 = _lib.launch_count()
     barrier()
     for k in range(args.steps):
         flush.zero_()
@@ -388,55 +459,27 @@ def run_b200_arm(args, cfg):
         run_step()
         sev[k][1].record(st)
     barrier()
-    launches = (launches_per_step * args.steps) if graph is not None else (_lib.launch_count() - launches0)
+    launches = launches_per_step * args.steps
     t_step = [a.elapsed_time(bb) for a, bb in sev]
     total_ms = max_over_ranks(sum(t_step))
     value = world * b * n * args.steps / (total_ms * 1e-3)
-    # the graph path must produce exactly what the sequential path produced
-    chk_idx, chk_new = idx.clone(), new_xyz.clone()
-    step_device()
-    torch.cuda.synchronize(dev)
-    same_dev = bool(torch.equal(chk_idx, idx)) and bool(torch.equal(chk_new, new_xyz))
+    # the overlapped layer must produce exactly what the three sequential launches produced
+    same_dev = all(bool(torch.equal(fus[k], seq[k])) for k in seq)
 
-    # ---- secondary: the same graph with several batches in flight.  One FPS launch keeps one SM
-    #      per cloud busy (b of 148), so independent batches on separate streams fill the GPU; this
-    #      is reported beside `value` (which stays one batch at a time), never instead of it.
+    # ---- secondary: several independent batches in flight (one layer occupies 2*b of the 148 SMs).
+    #      Reported beside `value` (which stays one batch at a time), never instead of it. ----
     inflight = None
-    # rank-uniform switch: the leg runs only if the graph was captured on EVERY rank
     graph_everywhere = max_over_ranks(0.0 if graph is not None else 1.0) == 0.0
     if graph_everywhere and args.in_flight > 1:
         try:
             lanes = []
             for _ in range(args.in_flight):
-                bufs = dict(fps_idx=torch.empty_like(fps_idx), new_xyz=torch.empty_like(new_xyz), idx=torch.empty_like(idx),
-                            cnt=torch.empty_like(cnt), grouped=torch.empty_like(grouped),
-                            ws=torch.empty(bq_ws_bytes, dtype=torch.uint8, device=dev) if bq_ws_bytes else None)
-                ls, sd = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-                fe, je = torch.cuda.Event(), torch.cuda.Event()
-
-                def lane_step(cur, bufs=bufs, sd=sd, fe=fe, je=je):
-                    sc, rc = cur.cuda_stream, 0
-                    if bufs["ws"] is not None:
-                        fe.record(cur)
-                        sd.wait_event(fe)
-                        rc |= lib.pn2_ball_grid_build(b, n, r, s, xyz.data_ptr(), bufs["ws"].data_ptr(), bq_ws_bytes, sd.cuda_stream)
-                        je.record(sd)
-                    rc |= lib.pn2_fps_gather(b, n, m, xyz.data_ptr(), bufs["fps_idx"].data_ptr(), bufs["new_xyz"].data_ptr(), sc)
-                    if bufs["ws"] is not None:
-                        cur.wait_event(je)
-                        rc |= lib.pn2_query_ball_point_prebuilt(b, n, m, r, s, xyz.data_ptr(), bufs["new_xyz"].data_ptr(),
-                                                                bufs["idx"].data_ptr(), bufs["cnt"].data_ptr(),
-                                                                bufs["ws"].data_ptr(), bq_ws_bytes, sc)
-                    else:
-                        rc |= lib.pn2_query_ball_point(b, n, m, r, s, xyz.data_ptr(), bufs["new_xyz"].data_ptr(),
-                                                       bufs["idx"].data_ptr(), bufs["cnt"].data_ptr(), sc)
-                    rc |= lib.pn2_group_point(b, n, 3, m, s, xyz.data_ptr(), bufs["idx"].data_ptr(), bufs["grouped"].data_ptr(), sc)
-                    if rc:
-                        raise RuntimeError(f"kernel launch failed rc={rc}")
-
+                bufs = out_buffers()
+                lws = torch.empty(dws_bytes, dtype=torch.uint8, device=dev) if dws_bytes else None
+                ls = torch.cuda.Stream(dev)
                 lg = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(lg, stream=ls):
-                    lane_step(torch.cuda.current_stream(dev))
+                    layer(bufs, lws, torch.cuda.current_stream(dev).cuda_stream)
                 lanes.append((lg, ls, bufs))
 
             def run_lanes(steps, t0=None):
@@ -460,21 +503,20 @@ def run_b200_arm(args, cfg):
             torch.cuda.synchronize(dev)
             launches += launches_per_step * args.steps
             fl_local = q0.elapsed_time(q1)
-            lanes_same = all(bool(torch.equal(bf["idx"], idx)) and bool(torch.equal(bf["grouped"], grouped)) for _, _, bf in lanes)
+            lanes_same = all(bool(torch.equal(bf["idx"], seq["idx"])) and bool(torch.equal(bf["grouped"], seq["grouped"])) for _, _, bf in lanes)
             inflight = {"batches_in_flight": len(lanes), "unit": UNIT, "outputs_match_sequential": lanes_same,
                         "timing": "one event pair around all steps, L2 flush inside"}
         except Exception as e:  # noqa: BLE001 — secondary number only
             fl_local = float("inf")
             inflight = {"error": f"{type(e).__name__}: {e}"}
             torch.cuda.synchronize(dev)
-        # every rank takes part in the reduction whether or not its own leg succeeded
-        fl_ms = max_over_ranks(fl_local)
+        fl_ms = max_over_ranks(fl_local)  # every rank takes part whether or not its own leg succeeded
         if fl_ms != float("inf") and "error" not in inflight:
             inflight.update(value=world * b * n * args.steps / (fl_ms * 1e-3), ms_per_step=fl_ms / args.steps)
         elif "error" not in inflight:
             inflight = {"error": "the leg failed on another rank"}
 
-    # ---- end-to-end leg: host buffers through the C-ABI host call --------------------------
+    # ---- end-to-end, one batch in flight: host buffers through the C-ABI host call --------------------------
     sess = SetAbstractionHost(b, n, m, r, s, device=dev)
     sess.h_xyz.numpy()[...] = xyz_np
     for _ in range(args.warmup):
@@ -492,95 +534,144 @@ def run_b200_arm(args, cfg):
     launches += _lib.launch_count() - launches1
     e2e_serial_ms = max_over_ranks(sum(a.elapsed_time(bb) for a, bb in e2e_ev))
     e2e_serial_value = world * b * n * args.steps / (e2e_serial_ms * 1e-3)
+    same = bool((sess.h_idx.to(dev) == seq["idx"]).all()) and bool((sess.h_new_xyz.to(dev) == seq["new_xyz"]).all())
 
-    # ---- end-to-end, the headline: the same host-buffer call for a STREAM of batches — a ring of
-    #      `depth` sessions on private streams (SetAbstractionPipeline), so batch k+1's copy-in and
-    #      sampling overlap batch k's copy-out.  Every step still copies its input from pinned host
-    #      memory and its four results back; the L2 flush runs inside the timed region.
-    pipe = SetAbstractionPipeline(b, n, m, r, s, depth=args.e2e_depth, device=dev)
-    for sl in pipe.slots:
-        sl.h_xyz.numpy()[...] = xyz_np
+    # ---- end-to-end, the headline: the same host-buffer call for a STREAM of batches — a ring of `depth`
+    #      sessions on private streams (SetAbstractionPipeline).  Every step copies its input from pinned
+    #      host memory and its results back; the L2 flush runs inside the timed region. ----
+    def e2e_pipeline(want_grouped):
+        nonlocal launches
+        pipe = SetAbstractionPipeline(b, n, m, r, s, depth=args.e2e_depth, device=dev, want_grouped=want_grouped)
+        for sl in pipe.slots:
+            sl.h_xyz.numpy()[...] = xyz_np
 
-    def run_pipe(steps, t0=None):
-        if t0 is not None:
-            for ps in pipe.streams:
-                ps.wait_event(t0)
-        for _ in range(steps):
-            if pipe.full():
+        def run_pipe(steps, t0=None):
+            if t0 is not None:
+                for ps in pipe.streams:
+                    ps.wait_event(t0)
+            for _ in range(steps):
+                if pipe.full():
+                    pipe.collect()
+                with torch.cuda.stream(pipe.streams[pipe._next]):
+                    flush.zero_()
+                pipe.submit()
+            while pipe.pending():
                 pipe.collect()
-            with torch.cuda.stream(pipe.streams[pipe._next]):
-                flush.zero_()
-            pipe.submit()
-        while pipe.pending():
-            pipe.collect()
 
-    run_pipe(max(args.warmup, pipe.depth))
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches2 = _lib.launch_count()
-    barrier()
-    p0.record(st)
-    run_pipe(args.steps, p0)
-    for ev in pipe.done:
-        st.wait_event(ev)
-    p1.record(st)
-    barrier()
-    launches += _lib.launch_count() - launches2
-    e2e_ms = max_over_ranks(p0.elapsed_time(p1))
+        run_pipe(max(args.warmup, pipe.depth))
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l2 = _lib.launch_count()
+        barrier()
+        p0.record(st)
+        run_pipe(args.steps, p0)
+        for ev in pipe.done:
+            st.wait_event(ev)
+        p1.record(st)
+        barrier()
+        launches += _lib.launch_count() - l2
+        ms = max_over_ranks(p0.elapsed_time(p1))
+        ok = all(bool((sl.h_idx.to(dev) == seq["idx"]).all()) and bool((sl.h_new_xyz.to(dev) == seq["new_xyz"]).all())
+                 and (not want_grouped or bool((sl.h_grouped_xyz.to(dev) == seq["grouped"]).all())) for sl in pipe.slots)
+        return ms, ok, pipe.h2d_bytes, pipe.d2h_bytes
+
+    e2e_ms, same_pipe, h2d_bytes, d2h_bytes = e2e_pipeline(True)
     e2e_value = world * b * n * args.steps / (e2e_ms * 1e-3)
-    same_pipe = all(bool((sl.h_idx.to(dev) == idx).all()) and bool((sl.h_grouped_xyz.to(dev) == grouped).all())
-                    for sl in pipe.slots)
+    lean_ms, same_lean, _, lean_d2h = e2e_pipeline(False)
     clocks = sampler.stop() if rank == 0 else None
-    # sanity: the e2e outputs must equal the device-resident outputs
-    same = bool((sess.h_idx.to(dev) == idx).all()) and bool((sess.h_new_xyz.to(dev) == new_xyz).all())
+
+    # ---- the other BASELINE configs (cfg3 MSG stack, cfg4 sem-seg SA+FP, cfg5 sweep) at this rank's shard,
+    #      per kernel, max over ranks — outside every timed region above ----
+    configs_block = None
+    if not args.no_configs:
+        import bench_report
+        peak_c, kind_c = measured_peaks()
+        try:
+            rows = bench_report.config_rows(torch, lib, dev, flush, peak_c, kind_c, world=world, rank=rank, reps=5, full=False, echo=False)
+            ms_vec = torch.tensor([rw["ms"] for rw in rows], dtype=torch.float64, device=dev)
+            ok_flag = 0.0
+        except Exception as e:  # noqa: BLE001
+            rows, ms_vec, ok_flag = [], torch.zeros(1, dtype=torch.float64, device=dev), 1.0
+            configs_block = {"error": f"{type(e).__name__}: {e}"}
+        if max_over_ranks(ok_flag) == 0.0:
+            if world > 1:
+                dist.all_reduce(ms_vec, op=dist.ReduceOp.MAX)
+            out_rows = []
+            for rw, ms_v in zip(rows, ms_vec.tolist()):
+                nbytes = rw["algorithmic_MB"] * 1e6
+                o = {"config": rw["config"], "kernel": rw["kernel"], "ms": ms_v, "GBps_per_gpu": nbytes / (ms_v * 1e-3) / 1e9,
+                     "frac_of_peak": nbytes / (ms_v * 1e-3) / 1e9 / peak_c}
+                for k2 in ("us_per_iter", "fp32_issue_frac_of_gpu", "mean_cnt"):
+                    if k2 in rw:
+                        o[k2] = rw[k2] * (rw["ms"] / ms_v if k2 == "fp32_issue_frac_of_gpu" else (ms_v / rw["ms"] if k2 == "us_per_iter" else 1.0))
+                if "points_per_s" in rw:
+                    o["points_per_s_all_gpus"] = world * rw["points_per_s"] * rw["ms"] / ms_v
+                out_rows.append(o)
+            configs_block = {"what": "per kernel: CUDA events, L2 flushed before each timed launch, median of 5 (2-3 for N >= 65536), max over ranks; "
+                                     f"cfg3 B=32/GPU, cfg4 B={max(1, 16 // world)}/GPU, cfg5 B={max(1, 8 // world)}/GPU",
+                             "peak": f"{peak_c} GB/s of {kind_c}", "rows": out_rows}
+        elif configs_block is None:
+            configs_block = {"error": "the configs block failed on another rank"}
 
     if rank == 0:
-        import ctypes
         pt, pp, pc = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         lib.pn2_fps_plan(b, n, ctypes.byref(pt), ctypes.byref(pp), ctypes.byref(pc))
-        kinds = {1: "fps_cta_kernel", -1: "fps_bucket_kernel", 0: "fps_global_kernel"}
+        kinds = {1: "fps_cta_kernel", 0: "fps_global_kernel"}
         fps_kernel = f"{kinds.get(pc.value, 'fps_cluster_kernel')}<{pp.value},{pt.value}>" + (f" cluster={pc.value}" if pc.value > 1 else "")
         peak, peak_kind = measured_peaks()
         fps_ms = statistics.mean(t_fps)
         fps_bytes = W.bytes_fps(b, n, m, with_new_xyz=True)
         achieved = fps_bytes / (fps_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("fps_dram_bytes_per_launch")
+                tj = json.load(open(tpath))
+                traffic = tj.get("fps_dram_bytes_per_launch")
+                traffic_src = "profiles/ncu_traffic.json: " + tj.get("source", "ncu --set full capture of this kernel") + " (not re-measured in this run)"
             except Exception:
                 traffic = None
         layer_bytes = W.bytes_sa_layer(b, n, m, s)
+        step_ms = statistics.mean(t_step)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": dict(workload_config(cfg, world), launch=launch_mode),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": sess.h2d_bytes, "d2h_bytes_per_step": sess.d2h_bytes,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(cfg, world),
+            "launch": f"pn2_sa_layer_device: sampling kernel + programmatically dependent ball-query/grouping grid ({launches_per_step} launches per step), {launch_mode}",
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                     "ms_per_step": e2e_ms / args.steps, "outputs_match_device_leg": same and same_pipe,
-                    "mode": f"stream of batches, {pipe.depth} in flight (SetAbstractionPipeline); one event pair around all steps, L2 flush inside",
+                    "mode": f"stream of batches, {args.e2e_depth} in flight (SetAbstractionPipeline -> pn2_sa_layer_host); one event pair around all steps, L2 flush inside",
                     "serial": {"value": e2e_serial_value, "ms_per_step": e2e_serial_ms / args.steps,
-                               "mode": "one batch in flight (SetAbstractionHost); per-step event pairs, L2 flush between"}},
-            "gpu_launches": int(launches),  # this library's kernels inside the two timed regions (3 per step each)
+                               "mode": "one batch in flight (SetAbstractionHost); per-step event pairs, L2 flush between"},
+                    "idx_only": {"value": world * b * n * args.steps / (lean_ms * 1e-3), "ms_per_step": lean_ms / args.steps,
+                                 "d2h_bytes_per_step": lean_d2h, "outputs_match_device_leg": same_lean,
+                                 "mode": "same pipeline with grouped_xyz = NULL (new_xyz, idx, pts_cnt come back; the caller regroups xyz[idx] itself)"},
+                    "numa": numa.status()},
+            "gpu_launches": int(launches),  # this library's kernels inside the timed regions
             "roofline": {"bound": "hbm", "kernel": fps_kernel + " (FPS + fused gather_point)", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_kind": f"of {peak_kind}",
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_kind": f"of {peak_kind}",
                          "algorithmic_bytes_per_launch": fps_bytes, "ms_per_launch": fps_ms,
-                         "note": "FPS is a serial chain of npoint argmax steps: latency/FP32-issue bound, not HBM bound",
+                         "note": "FPS is a serial chain of npoint argmax steps: latency/FP32-issue bound, not HBM bound; it is "
+                                 f"{100 * fps_ms / step_ms:.0f} % of the step now that the ball query + grouping overlap it",
                          "secondary": {"point_pairs_per_s": b * (m - 1) * n / (fps_ms * 1e-3),
                                        # 10 FP32/ALU instructions per point pair is the minimum for the exact
                                        # arithmetic contract (SASS: 3 FADD, FMUL, 2 FFMA, FMNMX, FSETP, FSEL, SEL)
                                        "fp32_issue_frac_of_gpu": b * (m - 1) * n * 10 / (fps_ms * 1e-3) / (148 * 128 * 1.965e9),
                                        "fp32_issue_frac_of_occupied_sms": b * (m - 1) * n * 10 / (fps_ms * 1e-3) / (min(b, 148) * 128 * 1.965e9),
-                                       "whole_layer_GBps": layer_bytes / (statistics.mean(t_step) * 1e-3) / 1e9,
-                                       "whole_layer_frac": layer_bytes / (statistics.mean(t_step) * 1e-3) / 1e9 / peak}},
+                                       "whole_layer_GBps": layer_bytes / (step_ms * 1e-3) / 1e9,
+                                       "whole_layer_frac": layer_bytes / (step_ms * 1e-3) / 1e9 / peak}},
             "kernels_ms": {"fps_gather": fps_ms, "query_ball_point": statistics.mean(t_bq), "group_point": statistics.mean(t_grp),
-                           "step_sequential": statistics.mean(t_seq), "step": statistics.mean(t_step), "launch_mode": launch_mode,
-                           "graph_outputs_match_sequential": same_dev,
+                           "step_sequential": statistics.mean(t_seq), "step": step_ms,
+                           "overlap_hides_ms": statistics.mean(t_seq) - step_ms,
+                           "overlapped_outputs_match_sequential": same_dev,
                            "GBps": {"query_ball_point": W.bytes_ball_query(b, n, m, s) / (statistics.mean(t_bq) * 1e-3) / 1e9,
                                     "group_point": W.bytes_group(b, n, m, s, 3) / (statistics.mean(t_grp) * 1e-3) / 1e9}},
             "device_batches_in_flight": inflight,
+            "configs": configs_block,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
+            line["reference_cuda"] = child_json(["--impl", "reference_cuda", "--steps", "10", "--warmup", "3"], "reference_cuda", timeout=300.0)
             line["cpu_baseline"] = cpu_baseline(cfg, budget_s=args.cpu_budget)
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -593,8 +684,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--impl", choices=["b200", "reference", "reference_cuda"], default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline and reference_cuda children")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg3/cfg4/cfg5 per-kernel block")
     ap.add_argument("--cpu-budget", type=float, default=12.0)
     ap.add_argument("--in-flight", type=int, default=4, help="batches in flight in the secondary device-resident leg")
     ap.add_argument("--e2e-depth", type=int, default=3, help="batches in flight in the end-to-end leg")
@@ -612,6 +704,8 @@ def main():
         return
     if args.impl == "reference":
         run_reference_arm(args, cfg)
+    elif args.impl == "reference_cuda":
+        run_reference_cuda_arm(args, cfg)
     else:
         run_b200_arm(args, cfg)
 

@@ -117,7 +117,7 @@ def fps_sweep(out_path=None):
             rc = [0]
 
             def fn():
-                rc[0] |= lib.pn2_fps_gather(b, n, m, xyz.data_ptr(), idx.data_ptr(), nx.data_ptr(), None)
+                rc[0] |= lib.pn2_fps_gather(b, n, m, xyz.data_ptr(), None, idx.data_ptr(), nx.data_ptr(), None)
             try:
                 ms = timeit_batch(torch, fn)
             except Exception as e:  # noqa: BLE001
@@ -138,7 +138,7 @@ def fps_sweep(out_path=None):
                 idx2 = torch.empty((b, m2), dtype=torch.int32, device=dev)
                 nx2 = torch.empty((b, m2, 3), dtype=torch.float32, device=dev)
                 lib.pn2_set_fps_config(t, p, c)
-                ms2 = timeit_batch(torch, lambda: lib.pn2_fps_gather(b, n, m2, xyz.data_ptr(), idx2.data_ptr(), nx2.data_ptr(), None))
+                ms2 = timeit_batch(torch, lambda: lib.pn2_fps_gather(b, n, m2, xyz.data_ptr(), None, idx2.data_ptr(), nx2.data_ptr(), None))
                 lib.pn2_set_fps_config(0, 0, 0)
                 row["us_per_iter_marginal"] = 1e3 * (ms2 - ms) / m
                 row["setup_ms"] = ms - (ms2 - ms) * (m - 1) / m
@@ -160,7 +160,7 @@ def bq_sweep(out_path=None):
         xyz = torch.from_numpy(W.DISTRIBUTIONS[gen](b, n, 100)).to(dev)
         fi = torch.empty((b, m), dtype=torch.int32, device=dev)
         nx = torch.empty((b, m, 3), dtype=torch.float32, device=dev)
-        lib.pn2_fps_gather(b, n, m, xyz.data_ptr(), fi.data_ptr(), nx.data_ptr(), None)
+        lib.pn2_fps_gather(b, n, m, xyz.data_ptr(), None, fi.data_ptr(), nx.data_ptr(), None)
         idx = torch.empty((b, m, s), dtype=torch.int32, device=dev)
         cnt = torch.empty((b, m), dtype=torch.int32, device=dev)
         wsb = int(lib.pn2_query_ball_point_workspace_bytes(b, n))
@@ -186,26 +186,31 @@ def bq_sweep(out_path=None):
     return rows
 
 
-def report(out_path):
-    """Per-kernel time, algorithmic GB/s and fraction of the measured HBM peak for every BASELINE config."""
-    torch, lib, dev, flush = _setup()
-    from bench import measured_peaks
-    from pointnet2_b200 import workloads as W
-    peak, kind = measured_peaks()
-    rows = []
+def config_rows(torch, lib, dev, flush, peak, kind, world=1, rank=0, reps=10, full=True, echo=True):
+    """Per-kernel time, algorithmic GB/s and fraction of the measured HBM peak for BASELINE.json's
+    configs, as a list of dict rows (deterministic order: the same on every rank).
 
+    full=True (bench.py --report): cfg2 in three input distributions, cfg3, cfg4 at B=16 and at the
+    2-clouds-per-GPU shard, cfg5 at B=8 and B=1, with gradients and the brute-force-only ball query.
+    full=False (the `configs` block of bench.py's driver line): cfg3, cfg4 and cfg5 at THIS rank's
+    shard of the batch (B/world clouds: cfg4 16/world, cfg5 8/world), forward kernels only.
+    """
+    from pointnet2_b200 import workloads as W
+    rows = []
     lane_rate = 148 * 128 * 1.965e9  # FP32 lanes x max SM clock: the secondary bound for the pair-evaluation kernels
 
     def add(cfg, kernel, ms, nbytes, extra=None):
         gbps = nbytes / (ms * 1e-3) / 1e9
-        row = dict(config=cfg, kernel=kernel, ms=ms, algorithmic_MB=nbytes / 1e6, GBps=gbps, frac_of_peak=gbps / peak,
-                   peak=f"{peak} GB/s of {kind}")
+        row = dict(config=cfg, kernel=kernel, ms=ms, algorithmic_MB=nbytes / 1e6, GBps=gbps, frac_of_peak=gbps / peak)
+        if full:
+            row["peak"] = f"{peak} GB/s of {kind}"
         if extra:
             row.update(extra)
             if "pairs_per_s" in extra:  # point-pair evaluations per FP32-lane-cycle (1 = one pair per lane per clock)
                 row["pairs_per_lane_cycle"] = extra["pairs_per_s"] / lane_rate
         rows.append(row)
-        print(json.dumps(row), flush=True)
+        if echo:
+            print(json.dumps(row), flush=True)
 
     def T(a):
         return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
@@ -214,52 +219,65 @@ def report(out_path):
         b, n, _ = xyz.shape
         fi = torch.empty((b, m), dtype=torch.int32, device=dev)
         nx = torch.empty((b, m, 3), dtype=torch.float32, device=dev)
-        ms = timeit(torch, flush, lambda: lib.pn2_fps_gather(b, n, m, xyz.data_ptr(), fi.data_ptr(), nx.data_ptr(), None))
+        ms = timeit(torch, flush, lambda: lib.pn2_fps_gather(b, n, m, xyz.data_ptr(), None, fi.data_ptr(), nx.data_ptr(), None), reps=reps)
         add(tag, "fps+gather", ms, W.bytes_fps(b, n, m, True), dict(pairs_per_s=b * (m - 1) * n / (ms * 1e-3), us_per_iter=1e3 * ms / max(m - 1, 1)))
         idx = torch.empty((b, m, s), dtype=torch.int32, device=dev)
         cnt = torch.empty((b, m), dtype=torch.int32, device=dev)
         wsb = int(lib.pn2_query_ball_point_workspace_bytes(b, n))
         ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
         ms = timeit(torch, flush, lambda: lib.pn2_query_ball_point_ws(b, n, m, r, s, xyz.data_ptr(), nx.data_ptr(), idx.data_ptr(), cnt.data_ptr(),
-                                                                      ws.data_ptr() if wsb else None, wsb, None))
+                                                                      ws.data_ptr() if wsb else None, wsb, None), reps=reps)
         add(tag, f"query_ball_point r={r} S={s}", ms, W.bytes_ball_query(b, n, m, s), dict(mean_cnt=float(cnt.float().mean())))
-        lib.pn2_set_bq_mode(1)
-        ms = timeit(torch, flush, lambda: lib.pn2_query_ball_point_ws(b, n, m, r, s, xyz.data_ptr(), nx.data_ptr(), idx.data_ptr(), cnt.data_ptr(),
-                                                                      ws.data_ptr() if wsb else None, wsb, None))
-        lib.pn2_set_bq_mode(0)
-        add(tag, f"query_ball_point (brute force only) r={r} S={s}", ms, W.bytes_ball_query(b, n, m, s))
+        if full:
+            lib.pn2_set_bq_mode(1)
+            ms = timeit(torch, flush, lambda: lib.pn2_query_ball_point_ws(b, n, m, r, s, xyz.data_ptr(), nx.data_ptr(), idx.data_ptr(), cnt.data_ptr(),
+                                                                          ws.data_ptr() if wsb else None, wsb, None), reps=reps)
+            lib.pn2_set_bq_mode(0)
+            add(tag, f"query_ball_point (brute force only) r={r} S={s}", ms, W.bytes_ball_query(b, n, m, s))
         g = torch.empty((b, m, s, 3), dtype=torch.float32, device=dev)
-        ms = timeit(torch, flush, lambda: lib.pn2_group_point(b, n, 3, m, s, xyz.data_ptr(), idx.data_ptr(), g.data_ptr(), None))
+        ms = timeit(torch, flush, lambda: lib.pn2_group_point(b, n, 3, m, s, xyz.data_ptr(), idx.data_ptr(), g.data_ptr(), None), reps=reps)
         add(tag, f"group_point C=3 S={s}", ms, W.bytes_group(b, n, m, s, 3))
+        if lib.pn2_ball_group_fits(n):
+            ms = timeit(torch, flush, lambda: lib.pn2_ball_group(b, n, m, r, s, xyz.data_ptr(), nx.data_ptr(), idx.data_ptr(), cnt.data_ptr(), g.data_ptr(), 1, None), reps=reps)
+            add(tag, f"ball_group (query_ball_point + group_point(xyz) - centre, one launch) r={r} S={s}", ms,
+                W.bytes_ball_query(b, n, m, s) + 12 * b * m * s)
+        dwsb = int(lib.pn2_sa_layer_device_workspace_bytes(b, n, m, s))
+        dws = torch.empty(max(dwsb, 1), dtype=torch.uint8, device=dev)
+        ms = timeit(torch, flush, lambda: lib.pn2_sa_layer_device(b, n, m, r, s, xyz.data_ptr(), fi.data_ptr(), nx.data_ptr(), idx.data_ptr(), cnt.data_ptr(),
+                                                                  g.data_ptr(), 1, dws.data_ptr() if dwsb else None, dwsb, None), reps=reps)
+        add(tag, f"sa_layer_device (fps+gather+ball query+group xyz, overlapped when it applies) r={r} S={s}", ms, W.bytes_sa_layer(b, n, m, s),
+            dict(points_per_s=b * n / (ms * 1e-3)))
         c = 0 if feats is None else feats.shape[2]
         if c:
             gf = torch.empty((b, m, s, c), dtype=torch.float32, device=dev)
-            ms = timeit(torch, flush, lambda: lib.pn2_group_point(b, n, c, m, s, feats.data_ptr(), idx.data_ptr(), gf.data_ptr(), None))
+            ms = timeit(torch, flush, lambda: lib.pn2_group_point(b, n, c, m, s, feats.data_ptr(), idx.data_ptr(), gf.data_ptr(), None), reps=reps)
             add(tag, f"group_point C={c} S={s}", ms, W.bytes_group(b, n, m, s, c))
             del gf
-        if c:  # backward of the gather: atomic scatter-add (the caller's zero-fill is part of the op)
+        if c and full:  # backward of the gather: atomic scatter-add (the caller's zero-fill is part of the op)
             go = torch.randn((b, m, s, c), dtype=torch.float32, device=dev)
             gp = torch.empty((b, n, c), dtype=torch.float32, device=dev)
 
             def grad():
                 gp.zero_()
                 lib.pn2_group_point_grad(b, n, c, m, s, go.data_ptr(), idx.data_ptr(), gp.data_ptr(), None)
-            ms = timeit(torch, flush, grad)
+            ms = timeit(torch, flush, grad, reps=reps)
             add(tag, f"group_point_grad C={c} S={s} (incl. zero-fill)", ms, 4 * b * m * s + 4 * b * m * s * c + 2 * 4 * b * n * c)
             del go, gp
-        out = torch.empty((b, m, s, 3 + c), dtype=torch.float32, device=dev)
-        ms = timeit(torch, flush, lambda: lib.pn2_group_concat(b, n, c, m, s, xyz.data_ptr(), nx.data_ptr(), feats.data_ptr() if c else None,
-                                                               idx.data_ptr(), 1 if xyz_first else 0, out.data_ptr(), None, None))
-        add(tag, f"group_concat (fused tail) C={c}+3 S={s}", ms, 4 * b * m * s + 4 * b * min(n, m * s) * (c + 3) + 4 * b * m * s * (c + 3))
+        if c:
+            out = torch.empty((b, m, s, 3 + c), dtype=torch.float32, device=dev)
+            ms = timeit(torch, flush, lambda: lib.pn2_group_concat(b, n, c, m, s, xyz.data_ptr(), nx.data_ptr(), feats.data_ptr(),
+                                                                   idx.data_ptr(), 1 if xyz_first else 0, out.data_ptr(), None, None), reps=reps)
+            add(tag, f"group_concat (fused tail) C={c}+3 S={s}", ms, 4 * b * m * s + 4 * b * min(n, m * s) * (c + 3) + 4 * b * m * s * (c + 3))
         return nx
 
-    # cfg2 in the three input distributions
+    # cfg2 in the three input distributions (the driver line's own workload: --report only)
     c2 = W.CFG2_SSG_SA
-    for gen in ("U", "S", "D"):
-        sa_layer(f"cfg2[{gen}]", T(W.DISTRIBUTIONS[gen](c2["b"], c2["n"], 100)), None, c2["npoint"], c2["radius"], c2["nsample"])
-    # cfg3 MSG stack
+    if full:
+        for gen in ("U", "S", "D"):
+            sa_layer(f"cfg2[{gen}]", T(W.DISTRIBUTIONS[gen](c2["b"], c2["n"], 100)), None, c2["npoint"], c2["radius"], c2["nsample"])
+    # cfg3 MSG stack (B=32 per GPU: replicas under torchrun, like the driver line's cfg2)
     c3 = W.CFG3_MSG
-    xyz = T(W.cloud_surface(c3["b"], c3["n"], 100))
+    xyz = T(W.cloud_surface(c3["b"], c3["n"], 100 + rank))
     L1, L2 = c3["layers"]
     nx1 = None
     for r, s in zip(L1["radii"], L1["nsamples"]):
@@ -267,10 +285,12 @@ def report(out_path):
     feats = T(W.features(c3["b"], L1["npoint"], L2["c"], 103))
     for r, s in zip(L2["radii"], L2["nsamples"]):
         sa_layer("cfg3.L2", nx1, feats, L2["npoint"], r, s, xyz_first=False)
-    # cfg4 sem-seg: SA chain + FP chain, B=16 on one GPU and the 2-clouds-per-GPU shard
+    del feats
+    # cfg4 sem-seg: SA chain + FP chain.  --report: B=16 on one GPU and the 2-clouds-per-GPU shard;
+    # driver line: this rank's shard of the 16 clouds
     c4 = W.CFG4_SEMSEG
-    for b in (16, 2):
-        cur = T(W.cloud_duplicates(b, c4["n"], 100))
+    for b in ((16, 2) if full else (max(1, c4["b"] // world),)):
+        cur = T(W.cloud_duplicates(b, c4["n"], 100 + rank))
         levels = [cur]
         for L in c4["sa"]:
             f = T(W.features(b, cur.shape[1], L["c"], 104)) if L["c"] else None
@@ -283,39 +303,64 @@ def report(out_path):
             n_, m_, c_ = F["n"], F["m"], F["c"]
             d = torch.empty((b, n_, 3), dtype=torch.float32, device=dev)
             i = torch.empty((b, n_, 3), dtype=torch.int32, device=dev)
-            ms = timeit(torch, flush, lambda: lib.pn2_three_nn(b, n_, m_, x1.data_ptr(), x2.data_ptr(), d.data_ptr(), i.data_ptr(), None))
+            ms = timeit(torch, flush, lambda: lib.pn2_three_nn(b, n_, m_, x1.data_ptr(), x2.data_ptr(), d.data_ptr(), i.data_ptr(), None), reps=reps)
             add(f"cfg4[B={b}].FP{n_}<-{m_}", "three_nn", ms, W.bytes_three_nn(b, n_, m_), dict(pairs_per_s=b * n_ * m_ / (ms * 1e-3)))
             w = torch.full((b, n_, 3), 1 / 3, dtype=torch.float32, device=dev)
             o = torch.empty((b, n_, c_), dtype=torch.float32, device=dev)
-            ms = timeit(torch, flush, lambda: lib.pn2_three_interpolate(b, m_, c_, n_, p2.data_ptr(), i.data_ptr(), w.data_ptr(), o.data_ptr(), None))
+            ms = timeit(torch, flush, lambda: lib.pn2_three_interpolate(b, m_, c_, n_, p2.data_ptr(), i.data_ptr(), w.data_ptr(), o.data_ptr(), None), reps=reps)
             add(f"cfg4[B={b}].FP{n_}<-{m_}", f"three_interpolate C={c_}", ms, W.bytes_three_interpolate(b, n_, m_, c_))
-            go = torch.randn((b, n_, c_), dtype=torch.float32, device=dev)
-            gp = torch.empty((b, m_, c_), dtype=torch.float32, device=dev)
+            if full:
+                go = torch.randn((b, n_, c_), dtype=torch.float32, device=dev)
+                gp = torch.empty((b, m_, c_), dtype=torch.float32, device=dev)
 
-            def igrad():
-                gp.zero_()
-                lib.pn2_three_interpolate_grad(b, n_, c_, m_, go.data_ptr(), i.data_ptr(), w.data_ptr(), gp.data_ptr(), None)
-            ms = timeit(torch, flush, igrad)
-            add(f"cfg4[B={b}].FP{n_}<-{m_}", f"three_interpolate_grad C={c_} (incl. zero-fill)", ms, 2 * 4 * b * m_ * c_ + 24 * b * n_ + 4 * b * n_ * c_)
-            ms = timeit(torch, flush, lambda: lib.pn2_three_nn_interpolate(b, n_, m_, c_, x1.data_ptr(), x2.data_ptr(), p2.data_ptr(), o.data_ptr(), None, None, None, None))
+                def igrad():
+                    gp.zero_()
+                    lib.pn2_three_interpolate_grad(b, n_, c_, m_, go.data_ptr(), i.data_ptr(), w.data_ptr(), gp.data_ptr(), None)
+                ms = timeit(torch, flush, igrad, reps=reps)
+                add(f"cfg4[B={b}].FP{n_}<-{m_}", f"three_interpolate_grad C={c_} (atomics, incl. zero-fill)", ms, 2 * 4 * b * m_ * c_ + 24 * b * n_ + 4 * b * n_ * c_)
+                if hasattr(lib, "pn2_three_interpolate_grad_det"):
+                    dwb = int(lib.pn2_three_interpolate_grad_det_workspace_bytes(b, n_, m_))
+                    dw = torch.empty(max(dwb, 1), dtype=torch.uint8, device=dev)
+                    ms = timeit(torch, flush, lambda: lib.pn2_three_interpolate_grad_det(b, n_, c_, m_, go.data_ptr(), i.data_ptr(), w.data_ptr(), gp.data_ptr(),
+                                                                                         dw.data_ptr(), dwb, None), reps=reps)
+                    add(f"cfg4[B={b}].FP{n_}<-{m_}", f"three_interpolate_grad C={c_} (deterministic, inverse index)", ms,
+                        2 * 4 * b * m_ * c_ + 24 * b * n_ + 4 * b * n_ * c_)
+            ms = timeit(torch, flush, lambda: lib.pn2_three_nn_interpolate(b, n_, m_, c_, x1.data_ptr(), x2.data_ptr(), p2.data_ptr(), o.data_ptr(), None, None, None, None), reps=reps)
             add(f"cfg4[B={b}].FP{n_}<-{m_}", f"three_nn_interpolate (fused) C={c_}", ms, 12 * b * n_ + 12 * b * m_ + 4 * b * m_ * c_ + 4 * b * n_ * c_)
-    # cfg5 sweep: FPS + gather + ball query, B=8 and the per-GPU shards
+    # cfg5 sweep: FPS + gather + ball query.  --report: B=8 and B=1; driver line: this rank's 8/world clouds
     c5 = W.CFG5_SWEEP
     for n in c5["ns"]:
-        for b in (8, 1):
+        for b in ((8, 1) if full else (max(1, c5["b"] // world),)):
             if n >= 262144 and b == 8 and os.environ.get("PN2_REPORT_BIG", "1") != "1":
                 continue
-            xyz = T(W.cloud_uniform(b, n, 100 + int(np.log2(n))))
+            xyz = T(W.cloud_uniform(b, n, 100 + int(np.log2(n)) + 16 * rank))
             m = n // 4
             fi = torch.empty((b, m), dtype=torch.int32, device=dev)
             nx = torch.empty((b, m, 3), dtype=torch.float32, device=dev)
-            ms = timeit(torch, flush, lambda: lib.pn2_fps_gather(b, n, m, xyz.data_ptr(), fi.data_ptr(), nx.data_ptr(), None), reps=3, warm=1)
+            big = n >= 65536
+            ms = timeit(torch, flush, lambda: lib.pn2_fps_gather(b, n, m, xyz.data_ptr(), None, fi.data_ptr(), nx.data_ptr(), None),
+                        reps=(2 if big else 3), warm=1)
             add(f"cfg5[B={b},N={n}]", "fps+gather", ms, W.bytes_fps(b, n, m, True), dict(pairs_per_s=b * (m - 1) * n / (ms * 1e-3), us_per_iter=1e3 * ms / (m - 1),
-                                                                                         points_per_s=b * n / (ms * 1e-3)))
+                                                                                         points_per_s=b * n / (ms * 1e-3),
+                                                                                         fp32_issue_frac_of_gpu=b * (m - 1) * n * 10 / (ms * 1e-3) / lane_rate))
             idx = torch.empty((b, m, 32), dtype=torch.int32, device=dev)
             cnt = torch.empty((b, m), dtype=torch.int32, device=dev)
-            ms = timeit(torch, flush, lambda: lib.pn2_query_ball_point(b, n, m, 0.1, 32, xyz.data_ptr(), nx.data_ptr(), idx.data_ptr(), cnt.data_ptr(), None), reps=3, warm=1)
-            add(f"cfg5[B={b},N={n}]", "query_ball_point", ms, W.bytes_ball_query(b, n, m, 32), dict(mean_cnt=float(cnt.float().mean())))
+            wsb = int(lib.pn2_query_ball_point_workspace_bytes(b, n))
+            ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device=dev)
+            ms2 = timeit(torch, flush, lambda: lib.pn2_query_ball_point_ws(b, n, m, 0.1, 32, xyz.data_ptr(), nx.data_ptr(), idx.data_ptr(), cnt.data_ptr(),
+                                                                           ws.data_ptr() if wsb else None, wsb, None), reps=3, warm=1)
+            add(f"cfg5[B={b},N={n}]", "query_ball_point", ms2, W.bytes_ball_query(b, n, m, 32), dict(mean_cnt=float(cnt.float().mean()),
+                                                                                                   points_per_s_fps_plus_query=b * n / ((ms + ms2) * 1e-3)))
+            del xyz, fi, nx, idx, cnt
+    return rows
+
+
+def report(out_path):
+    """Per-kernel tables for every BASELINE config (bench.py --report FILE)."""
+    torch, lib, dev, flush = _setup()
+    from bench import measured_peaks
+    peak, kind = measured_peaks()
+    rows = config_rows(torch, lib, dev, flush, peak, kind, full=True)
     json.dump(rows, open(out_path, "w"), indent=1)
 
 

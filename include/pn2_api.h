@@ -20,8 +20,8 @@
  *   - limits: every tensor must have fewer than 2^31 elements per batch entry; n, m < 2^31
  *     (totals are indexed with 64 bits: gather / concat / interpolate are tested beyond 2^32 elements);
  *     ops that put the batch on gridDim.y (ball query, three_nn, the row kernels) take b <= 65535.
- *   - the pn2_set_* tuning hooks write process-wide state without locking: call them before use,
- *     not concurrently with launches.
+ *   - the pn2_set_* tuning hooks store one atomic word each: they may be called from any thread at any
+ *     time; a launch sees either the old or the new setting, never a mixture.
  */
 #ifndef PN2_API_H_
 #define PN2_API_H_
@@ -32,20 +32,26 @@
 extern "C" {
 #endif
 
-#define PN2_API_VERSION 1
+#define PN2_API_VERSION 2
 
 /* ---- sampling (replaces tf_ops/sampling/tf_sampling_g.cu launchers) ---------------------- */
 
 /* farthestpointsamplingLauncher(b,n,m,inp,temp,out), tf_sampling_g.cu:203-205.
  * inp (b,n,3) f32; out (b,m) i32.  out[:,0] = 0; selection order and tie-break identical to the
  * reference kernel (:105-170): argmax of the running min squared distance under
- * (value desc, k mod 512 asc, k asc).  `temp` is the reference's (32,n) scratch: unused here
- * (the running minimum lives in registers), may be NULL. */
+ * (value desc, k mod 512 asc, k asc).  `temp` is the reference's (32,n) float scratch
+ * (tf_sampling_g.cu:202).  Clouds of up to 262144 points keep the running minimum in registers and
+ * never touch it (temp may be NULL); larger clouds take the reference's global-scratch layout and
+ * need pn2_fps_scratch_bytes(b, n) bytes there (cudaErrorInvalidValue if temp is NULL then). */
 int pn2_fps(int b, int n, int m, const float* inp, float* temp, int* out, void* stream);
 
-/* Same, also emitting new_xyz (b,m,3) = inp gathered at out (FPS + gather_point in one launch;
- * the pair sample_and_group always issues, utils/pointnet_util.py:40). new_xyz may be NULL. */
-int pn2_fps_gather(int b, int n, int m, const float* inp, int* out, float* new_xyz, void* stream);
+/* Bytes of `temp` pn2_fps / pn2_fps_gather need for (b, n): 0 up to n = 262144, else
+ * min(b,32)*n*sizeof(float). */
+size_t pn2_fps_scratch_bytes(int b, int n);
+
+/* Same as pn2_fps, also emitting new_xyz (b,m,3) = inp gathered at out (FPS + gather_point in one
+ * launch; the pair sample_and_group always issues, utils/pointnet_util.py:40). new_xyz may be NULL. */
+int pn2_fps_gather(int b, int n, int m, const float* inp, float* temp, int* out, float* new_xyz, void* stream);
 
 /* probsampleLauncher(b,n,m,inp_p,inp_r,temp,out), tf_sampling_g.cu:198-201 (ProbSample op,
  * tf_sampling.cpp:66-92).  inp_p (b,n) f32 unnormalised probabilities; inp_r (b,m) f32 uniform
@@ -109,6 +115,15 @@ int pn2_group_point_grad(int b, int n, int c, int m, int nsample, const float* g
  * columns >= k hold the permuted remainder exactly as the reference leaves it. */
 int pn2_selection_sort(int b, int n, int m, int k, const float* dist, int* outi, float* out, void* stream);
 
+/* knn_point(k, xyz1, xyz2), tf_grouping.py:48-73, without the (b,m,n) distance matrix the reference's
+ * graph materialises: xyz1 (b,n,3) data, xyz2 (b,m,3) queries -> val (b,m,k) f32 squared distances
+ * ascending, idx (b,m,k) i32.  Bit-identical to the first k columns of selectionSortLauncher
+ * (tf_grouping_g.cu:83-123, :129-132) applied to dist[b,j,i] = ((dx*dx + dy*dy) + dz*dz), every product
+ * and sum rounded on its own — including the order the selection sort's SWAPS give to equal distances.
+ * 1 <= k <= min(n, 128); otherwise cudaErrorInvalidValue (use pn2_selection_sort on a matrix). */
+int pn2_knn_point(int b, int n, int m, int k, const float* xyz1, const float* xyz2, float* val, int* idx,
+                  void* stream);
+
 /* ---- 3d_interpolation (replaces the CPU functions of tf_interpolate.cpp; now on the GPU) -- */
 
 /* threenn_cpu(b,n,m,xyz1,xyz2,dist,idx), tf_interpolate.cpp:60-103.
@@ -146,13 +161,45 @@ int pn2_three_nn_interpolate(int b, int n, int m, int c, const float* xyz1, cons
                              const float* points2, float* out, float* dist, int* idx, float* weight,
                              void* stream);
 
+/* ---- the sampling+grouping half of a set-abstraction layer, device-resident ------------------ */
+
+/* query_ball_point + group_point(xyz) in ONE launch (tf_grouping_g.cu:3-57 back to back, as
+ * sample_and_group issues them, utils/pointnet_util.py:44-46): idx (b,m,nsample), pts_cnt (b,m) exactly as
+ * pn2_query_ball_point writes them, and grouped_xyz (b,m,nsample,3) = xyz1 gathered at idx (NULL to
+ * skip), minus the query when center != 0 (the tile+sub of :46, one rounding per coordinate).
+ * Each cloud is binned into a uniform grid held in shared memory (or kept in index order when its
+ * balls are dense), so it applies when pn2_ball_group_fits(n) != 0 (n <= 10750); otherwise
+ * cudaErrorInvalidValue — use pn2_query_ball_point_ws + pn2_group_point. */
+int pn2_ball_group_fits(int n);
+int pn2_ball_group(int b, int n, int m, float radius, int nsample, const float* xyz1, const float* xyz2,
+                   int* idx, int* pts_cnt, float* grouped_xyz, int center, void* stream);
+
+/* farthest_point_sample + gather_point + query_ball_point + group_point(xyz)
+ * (utils/pointnet_util.py:40-46) on DEVICE buffers, results bit-identical to the four separate
+ * calls: fps_idx (b,m) i32 (the sampling indices; required, it is also the channel between the two
+ * kernels), new_xyz (b,m,3), idx (b,m,nsample), pts_cnt (b,m), grouped_xyz (b,m,nsample,3) or NULL,
+ * centred on new_xyz when center != 0.
+ * When sampling runs one CTA per cloud (n <= 8192) and the cloud fits the shared-memory grid, the
+ * ball query + grouping run as a programmatically dependent grid on the SMs the sampling chain
+ * leaves idle and consume centroids while they are being produced; the layer then costs the sampling
+ * time plus about a microsecond.  Otherwise the four kernels run back to back, using `workspace`
+ * (pn2_sa_layer_device_workspace_bytes bytes, may be NULL when that is 0) for the sampling scratch
+ * and the ball-query grid.  Independent batches may be issued on different streams: one layer
+ * occupies 2*b SMs. */
+size_t pn2_sa_layer_device_workspace_bytes(int b, int n, int m, int nsample);
+int pn2_sa_layer_device(int b, int n, int m, float radius, int nsample, const float* xyz, int* fps_idx,
+                        float* new_xyz, int* idx, int* pts_cnt, float* grouped_xyz, int center,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- host-buffer entry point (the reference feeds numpy through feed_dict) ----------------- */
 
 /* One SSG set-abstraction sampling+grouping layer (farthest_point_sample + gather_point +
  * query_ball_point + group_point(xyz), utils/pointnet_util.py:40-45) on HOST buffers:
  * copies h_xyz (b,n,3) to the device, runs the four ops, copies new_xyz (b,m,3), idx (b,m,nsample),
- * pts_cnt (b,m) and grouped_xyz (b,m,nsample,3; NOT centred) back.  Host buffers should be
- * pinned for the copies to be asynchronous.  `workspace` is a device buffer of at least
+ * pts_cnt (b,m) and grouped_xyz (b,m,nsample,3; NOT centred) back — through pn2_sa_layer_device.
+ * Any of the four output pointers may be NULL: that result is neither copied back nor, for
+ * grouped_xyz, computed (a caller that regroups on the host saves 3/4 of the device-to-host bytes).
+ * Host buffers should be pinned for the copies to be asynchronous.  `workspace` is a device buffer of at least
  * pn2_sa_layer_workspace_bytes(b,n,m,nsample) bytes supplied by the caller.  Asynchronous on
  * `stream`: synchronise the stream before reading the outputs. */
 size_t pn2_sa_layer_workspace_bytes(int b, int n, int m, int nsample);
@@ -172,8 +219,8 @@ float pn2_ball_threshold(float radius);
  * (cluster 0 = global-scratch fallback); threads = 0 restores the built-in plan */
 void pn2_set_fps_config(int threads, int points_per_thread, int cluster);
 /* the kernel variant pn2_fps would launch for (b, n): threads per CTA, points per thread and
- * cluster size (1 = one CTA per cloud, >= 2 = thread-block cluster per cloud, -1 = bucketed single
- * CTA, 0 = global-scratch fallback) */
+ * cluster size (1 = one CTA per cloud, >= 2 = thread-block cluster per cloud, 0 = global-scratch
+ * fallback) */
 int pn2_fps_plan(int b, int n, int* threads, int* points_per_thread, int* cluster);
 /* tuning override: lanes cooperating on one ball query (1,2,4,..,32); 0 restores the heuristic */
 void pn2_set_bq_group(int lanes_per_query);

@@ -16,7 +16,8 @@ _P = c_void_p
 _SIGNATURES = {
     # name: (restype, argtypes)   — mirrors include/pn2_api.h
     "pn2_fps": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P]),
-    "pn2_fps_gather": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P]),
+    "pn2_fps_scratch_bytes": (c_size_t, [c_int, c_int]),
+    "pn2_fps_gather": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "pn2_prob_sample": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "pn2_gather_point": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P]),
     "pn2_gather_point_grad": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P]),
@@ -28,11 +29,16 @@ _SIGNATURES = {
     "pn2_group_point": (c_int, [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
     "pn2_group_point_grad": (c_int, [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
     "pn2_selection_sort": (c_int, [c_int, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "pn2_knn_point": (c_int, [c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "pn2_three_nn": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "pn2_three_interpolate": (c_int, [c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "pn2_three_interpolate_grad": (c_int, [c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "pn2_group_concat": (c_int, [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P, _P, _P]),
     "pn2_three_nn_interpolate": (c_int, [c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "pn2_ball_group_fits": (c_int, [c_int]),
+    "pn2_ball_group": (c_int, [c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P, c_int, _P]),
+    "pn2_sa_layer_device_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "pn2_sa_layer_device": (c_int, [c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P, _P, c_int, _P, c_size_t, _P]),
     "pn2_sa_layer_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "pn2_sa_layer_host": (c_int, [c_int, c_int, c_int, c_float, c_int, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "pn2_api_version": (c_int, []),

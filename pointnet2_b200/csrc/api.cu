@@ -7,7 +7,7 @@ unsigned long long g_launch_count = 0;
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct SaLayout {
-    size_t xyz, new_xyz, idx, cnt, grouped, bq_ws, bq_ws_bytes, total;
+    size_t xyz, new_xyz, fps_idx, idx, cnt, grouped, dev_ws, dev_ws_bytes, total;
 };
 
 static SaLayout sa_layout(int b, int n, int m, int nsample) {
@@ -15,11 +15,12 @@ static SaLayout sa_layout(int b, int n, int m, int nsample) {
     size_t off = 0;
     L.xyz = off;     off = align_up(off + sizeof(float) * (size_t)b * n * 3, 256);
     L.new_xyz = off; off = align_up(off + sizeof(float) * (size_t)b * m * 3, 256);
+    L.fps_idx = off; off = align_up(off + sizeof(int) * (size_t)b * m, 256);  // also the channel between the two overlapped kernels
     L.idx = off;     off = align_up(off + sizeof(int) * (size_t)b * m * nsample, 256);
     L.cnt = off;     off = align_up(off + sizeof(int) * (size_t)b * m, 256);
     L.grouped = off; off = align_up(off + sizeof(float) * (size_t)b * m * nsample * 3, 256);
-    L.bq_ws_bytes = pn2_query_ball_point_workspace_bytes(b, n);  // 0 when the grid path does not apply
-    L.bq_ws = off;   off = align_up(off + L.bq_ws_bytes, 256);
+    L.dev_ws_bytes = pn2_sa_layer_device_workspace_bytes(b, n, m, nsample);  // 0 on the overlapped path
+    L.dev_ws = off;  off = align_up(off + L.dev_ws_bytes, 256);
     L.total = off;
     return L;
 }
@@ -51,19 +52,15 @@ int pn2_sa_layer_host(int b, int n, int m, float radius, int nsample, const floa
     char* ws = static_cast<char*>(workspace);
     float* d_xyz = reinterpret_cast<float*>(ws + L.xyz);
     float* d_new = reinterpret_cast<float*>(ws + L.new_xyz);
+    int* d_fps = reinterpret_cast<int*>(ws + L.fps_idx);
     int* d_idx = reinterpret_cast<int*>(ws + L.idx);
     int* d_cnt = reinterpret_cast<int*>(ws + L.cnt);
-    float* d_grp = reinterpret_cast<float*>(ws + L.grouped);
+    float* d_grp = h_grouped_xyz ? reinterpret_cast<float*>(ws + L.grouped) : nullptr;  // not wanted: not computed
 
     cudaError_t e = cudaMemcpyAsync(d_xyz, h_xyz, sizeof(float) * (size_t)b * n * 3, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return (int)e;
-    int rc = pn2_fps_gather(b, n, m, d_xyz, d_idx /*scratch for the fps indices*/, d_new, stream);
-    if (rc) return rc;
-    // the fps indices themselves are not an output of sample_and_group; d_idx is overwritten next
-    rc = pn2_query_ball_point_ws(b, n, m, radius, nsample, d_xyz, d_new, d_idx, d_cnt,
-                                 L.bq_ws_bytes ? ws + L.bq_ws : nullptr, L.bq_ws_bytes, stream);
-    if (rc) return rc;
-    rc = pn2_group_point(b, n, 3, m, nsample, d_xyz, d_idx, d_grp, stream);
+    int rc = pn2_sa_layer_device(b, n, m, radius, nsample, d_xyz, d_fps, d_new, d_idx, d_cnt, d_grp, /*center=*/0,
+                                 L.dev_ws_bytes ? ws + L.dev_ws : nullptr, L.dev_ws_bytes, stream);
     if (rc) return rc;
     if (h_new_xyz) {
         e = cudaMemcpyAsync(h_new_xyz, d_new, sizeof(float) * (size_t)b * m * 3, cudaMemcpyDeviceToHost, st);

@@ -237,6 +237,13 @@ bq_grid_query_kernel(int n, int m, float thr, int nsample, const float* __restri
         }
     }
     int hcount = 0;
+    // a non-finite query (NaN: a hit against EVERY point in the reference, fmaxf(NaN,1e-20f) < radius) cannot be
+    // served from its cell neighbourhood: warp-uniformly take the ordered scan below
+    const bool qfinite = (fabsf(qx) <= 3.0e38f) && (fabsf(qy) <= 3.0e38f) && (fabsf(qz) <= 3.0e38f);
+    if (!qfinite) {
+        p = p1 = 0;
+        hcount = kHitCap + 1;
+    }
     while (__any_sync(kFullMask, p < p1)) {
         bool hit = false;
         int k = 0;

@@ -23,6 +23,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "pn2_common.cuh"
 
 namespace pn2 {
@@ -75,10 +78,17 @@ __device__ __forceinline__ void mbar_wait_parity_cluster(unsigned addr, unsigned
         "r"(parity)
         : "memory");
 }
-// 8-byte store into a peer CTA's shared memory that also completes 8 tx-bytes on the peer's mbarrier.
-__device__ __forceinline__ void st_async_u64(unsigned remote_addr, unsigned long long v, unsigned remote_mbar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr),
-                 "l"(v), "r"(remote_mbar)
+// Stores into a peer CTA's shared memory that also complete their byte count on the peer's mbarrier
+// (SASS: STAS.128 / STAS).
+__device__ __forceinline__ void st_async_v4(unsigned remote_addr, unsigned a, unsigned b, unsigned c, unsigned d,
+                                            unsigned remote_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(remote_addr),
+                 "r"(a), "r"(b), "r"(c), "r"(d), "r"(remote_mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void st_async_u32(unsigned remote_addr, unsigned v, unsigned remote_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr), "r"(v),
+                 "r"(remote_mbar)
                  : "memory");
 }
 
@@ -87,9 +97,9 @@ __device__ __forceinline__ void st_async_u64(unsigned remote_addr, unsigned long
 // T-thread CTA owns k = t + j*T, so for T < 512 its slots cycle with period D = 512/T.  The scan
 // visits the points in tie-break order (slot ascending, then k ascending): for each slot residue
 // r = j mod D in turn, j ascending — so the strict '>' keeps the reference's winner.
-template <int P, int D = 1>
+template <int P, int D = 1, int PT = P>
 __device__ __forceinline__ void fps_step(const float (&px)[P], const float (&py)[P], const float (&pz)[P],
-                                         float (&td)[P], float x1, float y1, float z1, float& best, int& bj) {
+                                         float (&td)[PT], float x1, float y1, float z1, float& best, int& bj) {
     best = -1.0f;
     bj = 0;
     constexpr int DD = (D < P) ? D : P;
@@ -108,6 +118,10 @@ __device__ __forceinline__ void fps_step(const float (&px)[P], const float (&py)
     }
 }
 
+// PDL hook used by the fused set-abstraction layer (sa_fused.cu): lets the dependent grid launch
+// as soon as every CTA of this grid has got here (SASS: PREEXIT).  A no-op for ordinary launches.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // =================================================================================================
 // One CTA per cloud.  Thread t owns points k = t + j*T (j < P).  When T is a multiple of 512 all of
 // a thread's points share the reference slot k mod 512 and the in-thread strict '>' scan in
@@ -115,11 +129,14 @@ __device__ __forceinline__ void fps_step(const float (&px)[P], const float (&py)
 // (fps_step) so it is still the reference's (slot, k) order.
 // Dynamic shared memory: 3*n floats — a copy of the cloud, so the picked point's coordinates are a
 // 3-word broadcast LDS instead of a global/L2 round trip on the critical path.
+// `sentinel` != 0 (fused SA layer only): the CTA first fills its row of idx_out with -1 and signals
+// programmatic launch completion, so a dependent grid that polls idx_out for non-negative entries
+// (sa_fused.cu) can consume the picks while this chain is still running — no fence in the loop.
 // =================================================================================================
 template <int P, int T>
 __global__ void __launch_bounds__(T, 1)
 fps_cta_kernel(int n, int m, const float* __restrict__ xyz, int* __restrict__ idx_out,
-               float* __restrict__ new_xyz) {
+               float* __restrict__ new_xyz, int sentinel) {
     static_assert(T % 512 == 0 || 512 % T == 0, "T must divide or be a multiple of the reference's 512 slots");
     constexpr int NW = T / 32;
     constexpr int D = (T >= 512) ? 1 : 512 / T;
@@ -132,8 +149,13 @@ fps_cta_kernel(int n, int m, const float* __restrict__ xyz, int* __restrict__ id
     int* __restrict__ out = idx_out + (size_t)cloud * m;
     float* __restrict__ oxyz = new_xyz ? new_xyz + (size_t)cloud * m * 3 : nullptr;
 
+    if (sentinel) {  // CTA-uniform
+        for (int e = tid; e < m; e += T) out[e] = -1;
+        __threadfence();  // the fill is performed device-wide before the dependent grid may start
+    }
     for (int e = tid; e < 3 * n; e += T) s_xyz[e] = pts[e];
     __syncthreads();
+    if (sentinel) pdl_launch_dependents();
     const float* __restrict__ src = s_xyz;
 
     float px[P], py[P], pz[P], td[P];
@@ -153,12 +175,12 @@ fps_cta_kernel(int n, int m, const float* __restrict__ xyz, int* __restrict__ id
 
     float x1 = src[0], y1 = src[1], z1 = src[2];
     if (tid == 0) {
-        out[0] = 0;
         if (oxyz) {
             oxyz[0] = x1;
             oxyz[1] = y1;
             oxyz[2] = z1;
         }
+        out[0] = 0;
     }
 
     for (int it = 1; it < m; ++it) {
@@ -182,705 +204,12 @@ fps_cta_kernel(int n, int m, const float* __restrict__ xyz, int* __restrict__ id
         y1 = src[3 * old + 1];
         z1 = src[3 * old + 2];
         if (tid == 0) {
+            if (oxyz) {
+                oxyz[3 * it + 0] = x1;
+                oxyz[3 * it + 1] = y1;
+                oxyz[3 * it + 2] = z1;
+            }
             out[it] = old;
-            if (oxyz) {
-                oxyz[3 * it + 0] = x1;
-                oxyz[3 * it + 1] = y1;
-                oxyz[3 * it + 2] = z1;
-            }
-        }
-    }
-}
-
-// =================================================================================================
-// fps_cta2_kernel — the same one-CTA-per-cloud scheme as fps_cta_kernel with the per-step update
-// restructured around what the profile showed binds it (profiles/r1_microbench_latency.txt):
-//   * packed FP32x2 arithmetic (PTX sub/mul/fma .f32x2 -> SASS FADD2/FMUL2/FFMA2): two points per
-//     instruction for the 6 distance ops, IEEE round-to-nearest per lane, so bit-identical to the
-//     scalar pattern while halving the issue slots the FMA side takes;
-//   * registers hold the points in SCAN order (the reference's tie-break order for this thread), in
-//     NACC contiguous blocks with one running (best, index) accumulator each — the serial
-//     FSETP->FSEL dependency chain of a fat thread becomes NACC independent chains; blocks are merged
-//     in order with a strict '>', which keeps the first maximum in scan order.
-// =================================================================================================
-__device__ __forceinline__ unsigned long long f2_pack(float a, float b) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-    return r;
-}
-__device__ __forceinline__ void f2_unpack(unsigned long long v, float& a, float& b) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b) {
-    unsigned long long r;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
-    unsigned long long r;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
-    unsigned long long r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-
-template <int P, int T>
-__global__ void __launch_bounds__(T, 1)
-fps_cta2_kernel(int n, int m, const float* __restrict__ xyz, int* __restrict__ idx_out,
-                float* __restrict__ new_xyz) {
-    static_assert(P % 2 == 0, "packed pairs");
-    static_assert(T % 512 == 0 || 512 % T == 0, "T must divide or be a multiple of the reference's 512 slots");
-    constexpr int NW = T / 32;
-    constexpr int D = (T >= 512) ? 1 : 512 / T;  // slot residues per thread
-    constexpr int DD = (D < P) ? D : P;
-    constexpr int Q = P / DD;                    // points per slot residue
-    constexpr int H = P / 2;                     // packed pairs
-    constexpr int NACC = (P >= 16) ? 4 : (P >= 8 ? 2 : 1);
-    constexpr int HB = H / NACC;                 // pairs per accumulator block
-    __shared__ uint2 s_keys[2][32];
-    extern __shared__ float s_xyz[];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cloud = blockIdx.x;
-    const float* __restrict__ pts = xyz + (size_t)cloud * n * 3;
-    int* __restrict__ out = idx_out + (size_t)cloud * m;
-    float* __restrict__ oxyz = new_xyz ? new_xyz + (size_t)cloud * m * 3 : nullptr;
-
-    for (int e = tid; e < 3 * n; e += T) s_xyz[e] = pts[e];
-    __syncthreads();
-    const float* __restrict__ src = s_xyz;
-
-    // scan-order element e <-> strided point j = (e % Q) * DD + e / Q, k = tid + j*T
-    unsigned long long X[H], Y[H], Z[H];
-    float td[P];
-#pragma unroll
-    for (int h = 0; h < H; ++h) {
-        float c[2][3];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int e = 2 * h + u;
-            const int j = (e % Q) * DD + e / Q;
-            const int k = tid + j * T;
-            c[u][0] = c[u][1] = c[u][2] = 0.0f;
-            td[e] = -1.0f;  // padding: can never win
-            if (k < n) {
-                c[u][0] = src[3 * k + 0];
-                c[u][1] = src[3 * k + 1];
-                c[u][2] = src[3 * k + 2];
-                td[e] = 1e38f;
-            }
-        }
-        X[h] = f2_pack(c[0][0], c[1][0]);
-        Y[h] = f2_pack(c[0][1], c[1][1]);
-        Z[h] = f2_pack(c[0][2], c[1][2]);
-    }
-
-    float x1 = src[0], y1 = src[1], z1 = src[2];
-    if (tid == 0) {
-        out[0] = 0;
-        if (oxyz) {
-            oxyz[0] = x1;
-            oxyz[1] = y1;
-            oxyz[2] = z1;
-        }
-    }
-
-    for (int it = 1; it < m; ++it) {
-        const unsigned long long X1 = f2_pack(x1, x1), Y1 = f2_pack(y1, y1), Z1 = f2_pack(z1, z1);
-        float best[NACC];
-        int be[NACC];
-#pragma unroll
-        for (int a = 0; a < NACC; ++a) {
-            best[a] = -1.0f;
-            be[a] = 0;
-#pragma unroll
-            for (int hh = 0; hh < HB; ++hh) {
-                const int h = a * HB + hh;
-                const unsigned long long dx = f2_sub(X[h], X1), dy = f2_sub(Y[h], Y1), dz = f2_sub(Z[h], Z1);
-                const unsigned long long d = f2_fma(dz, dz, f2_fma(dx, dx, f2_mul(dy, dy)));
-                float d0, d1;
-                f2_unpack(d, d0, d1);
-                const float a0 = fminf(d0, td[2 * h]);
-                td[2 * h] = a0;
-                if (a0 > best[a]) {
-                    best[a] = a0;
-                    be[a] = 2 * h;
-                }
-                const float a1 = fminf(d1, td[2 * h + 1]);
-                td[2 * h + 1] = a1;
-                if (a1 > best[a]) {
-                    best[a] = a1;
-                    be[a] = 2 * h + 1;
-                }
-            }
-        }
-#pragma unroll
-        for (int a = 1; a < NACC; ++a) {  // in block order, strict '>': the first maximum in scan order survives
-            if (best[a] > best[0]) {
-                best[0] = best[a];
-                be[0] = be[a];
-            }
-        }
-        unsigned hi = 0u, lo = 0u;
-        if (best[0] >= 0.0f) {
-            const int e = be[0];
-            const int j = (e % Q) * DD + e / Q;  // Q, DD are powers of two
-            hi = __float_as_uint(best[0]);
-            lo = ~tb_encode((unsigned)(tid + j * T));
-        }
-        warp_max_pair(hi, lo);
-        const int buf = it & 1;
-        if (lane == 0) s_keys[buf][warp] = make_uint2(lo, hi);
-        __syncthreads();
-        uint2 ent = (lane < NW) ? s_keys[buf][lane] : make_uint2(0u, 0u);
-        unsigned gh = ent.y, gl = ent.x;
-        warp_max_pair(gh, gl);
-        const int old = (int)tb_decode(~gl);
-        x1 = src[3 * old + 0];
-        y1 = src[3 * old + 1];
-        z1 = src[3 * old + 2];
-        if (tid == 0) {
-            out[it] = old;
-            if (oxyz) {
-                oxyz[3 * it + 0] = x1;
-                oxyz[3 * it + 1] = y1;
-                oxyz[3 * it + 2] = z1;
-            }
-        }
-    }
-}
-
-// =================================================================================================
-// Bucketed FPS, one CTA per cloud (the default for n <= 8192): EXACT, but most of the work of a
-// step is pruned.
-//
-// At start the CTA sorts its cloud along a Morton curve in shared memory; warp w then owns the
-// w-th run of 32*P consecutive sorted points (P per lane, coordinates and running minimum in
-// registers) — a spatially compact BUCKET with a bounding box.  For a new pick s, every computed
-// distance d(k,s) of a point in the bucket is >= LB(s) = the reference's distance formula applied
-// to the per-axis gaps between s and the box: rounding is monotone, so |fl(x_k - s_x)| is at
-// least the rounded gap, and the FMUL/FFMA/FFMA chain is monotone in |dx|,|dy|,|dz|.  Hence if
-// LB(s) >= max_k td[k] the step changes nothing in this bucket (min(d,td)=td for every k) and the
-// warp skips it, re-publishing its cached best.  Late in the sampling most buckets are skipped.
-//
-// Measured on B200 (profiles/r1_microbench_latency.txt) the step is bound by the ALU pipe (2
-// cycles per warp instruction), the XU pipe (ffs/popc) and barrier latency (78 cycles at 32
-// warps, 29 at 8), so the kernel uses FEW warps with many points each, keeps ffs/popc off the
-// common path (predicated publishing instead of leader election; redux instead of ballot+ffs),
-// publishes only (value, sorted position) per warp and looks the winner's coordinates up once
-// from a float4 table in shared memory.
-//
-// Tie-break exactness: within a bucket the points are re-sorted by the reference tie-break key
-// tb(k) and dealt to lanes in runs of P, so the in-thread strict '>' scan in register order picks
-// the smallest tb among equal values; across lanes / warps equal values are rare and take a slow
-// path that compares tb explicitly.
-// =================================================================================================
-__device__ __forceinline__ unsigned morton_part(unsigned v) {  // spread the low 10 bits to every 3rd bit
-    v = (v | (v << 16)) & 0x030000FFu;
-    v = (v | (v << 8)) & 0x0300F00Fu;
-    v = (v | (v << 4)) & 0x030C30C3u;
-    v = (v | (v << 2)) & 0x09249249u;
-    return v;
-}
-
-__device__ __forceinline__ float warp_min_f(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(kFullMask, v, o));
-    return v;
-}
-__device__ __forceinline__ float warp_max_f(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFullMask, v, o));
-    return v;
-}
-
-// ascending bitonic sort of s_key[0..len) in segments of `seg` (seg a power of two dividing len).
-// One thread owns a compare-exchange PAIR (i, i|j) per step and handles 4 independent pairs per
-// batch (loads first, then stores) so the shared-memory latency of the few setup warps overlaps.
-template <int T>
-__device__ __forceinline__ void bitonic_sort_smem(unsigned* s_key, int len, int seg, int tid) {
-    const int half = len >> 1;
-    for (int kk = 2; kk <= seg; kk <<= 1) {
-        for (int j = kk >> 1; j > 0; j >>= 1) {
-            for (int p0 = tid; p0 < half; p0 += 4 * T) {
-                unsigned a[4], b[4];
-                int ia[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int p = p0 + u * T;
-                    ia[u] = -1;
-                    if (p < half) {
-                        const int i = 2 * p - (p & (j - 1));  // bit j of i is clear; partner is i + j
-                        ia[u] = i;
-                        a[u] = s_key[i];
-                        b[u] = s_key[i + j];
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (ia[u] >= 0) {
-                        // the last level of a segmented sort must be ascending in EVERY segment
-                        const bool up = ((ia[u] & kk) == 0) || (kk == seg);
-                        if ((a[u] > b[u]) == up) {
-                            s_key[ia[u]] = b[u];
-                            s_key[ia[u] + j] = a[u];
-                        }
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
-
-template <int P, int T>
-__global__ void __launch_bounds__(T, 1)
-fps_bucket_kernel(int n, int m, int npad, const float* __restrict__ xyz, int* __restrict__ idx_out,
-                  float* __restrict__ new_xyz) {
-    constexpr int NW = T / 32;
-    constexpr int BUCKET = 32 * P;
-    static_assert(NW <= 32, "one table entry per lane");
-    __shared__ uint2 s_tab[2][32];  // per warp: (max running minimum as float bits, sorted position of its argmax)
-    __shared__ float s_red[6][32];
-    extern __shared__ float4 s_dyn4[];  // [n] sorted points (x, y, z, tb bits), then [npad] u32 sort keys
-    float4* s_sorted = s_dyn4;
-    unsigned* s_key = reinterpret_cast<unsigned*>(s_dyn4 + n);
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cloud = blockIdx.x;
-    const float* __restrict__ pts = xyz + (size_t)cloud * n * 3;
-    int* __restrict__ out = idx_out + (size_t)cloud * m;
-    float* __restrict__ oxyz = new_xyz ? new_xyz + (size_t)cloud * m * 3 : nullptr;
-
-    // ---- bounding box of the cloud --------------------------------------------------------------
-    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int k = tid; k < n; k += T) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float v = __ldg(pts + 3 * (size_t)k + c);
-            mn[c] = fminf(mn[c], v);
-            mx[c] = fmaxf(mx[c], v);
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const float a = warp_min_f(mn[c]), b = warp_max_f(mx[c]);
-        if (lane == 0) {
-            s_red[c][warp] = a;
-            s_red[3 + c][warp] = b;
-        }
-    }
-    __syncthreads();
-    float scale[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        mn[c] = warp_min_f(lane < NW ? s_red[c][lane] : INFINITY);
-        mx[c] = warp_max_f(lane < NW ? s_red[3 + c][lane] : -INFINITY);
-        const float ext = mx[c] - mn[c];
-        scale[c] = (ext > 0.f && ext < 3.0e38f) ? 64.0f / ext : 0.0f;
-    }
-    // ---- Morton keys (6 bits per axis) | original index; bitonic sort; then, inside every
-    //      bucket, re-sort by the tie-break key so lanes hold their points in tie-break order ----
-    for (int k = tid; k < npad; k += T) {
-        unsigned key = 0xffffffffu;
-        if (k < n) {
-            unsigned q[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float f = (__ldg(pts + 3 * (size_t)k + c) - mn[c]) * scale[c];
-                f = fminf(fmaxf(f, 0.f), 63.f);  // also maps NaN to 0
-                q[c] = (unsigned)f;
-            }
-            const unsigned mort = morton_part(q[0]) | (morton_part(q[1]) << 1) | (morton_part(q[2]) << 2);
-            key = (mort << 14) | (unsigned)k;  // k < 16384
-        }
-        s_key[k] = key;
-    }
-    __syncthreads();
-    bitonic_sort_smem<T>(s_key, npad, npad, tid);
-    for (int p = tid; p < npad; p += T) {
-        const unsigned key = s_key[p];
-        s_key[p] = (key == 0xffffffffu) ? 0xffffffffu : tb_encode(key & 0x3fffu);
-    }
-    __syncthreads();
-    if (npad >= BUCKET) bitonic_sort_smem<T>(s_key, npad, BUCKET, tid);
-    else bitonic_sort_smem<T>(s_key, npad, npad, tid);
-    for (int p = tid; p < n; p += T) {  // valid entries occupy [0, n): padding sorted to the global end in pass 1
-        const unsigned tbk = s_key[p];
-        const unsigned k = tb_decode(tbk);
-        s_sorted[p] = make_float4(__ldg(pts + 3 * (size_t)k), __ldg(pts + 3 * (size_t)k + 1), __ldg(pts + 3 * (size_t)k + 2),
-                                  __uint_as_float(tbk));
-    }
-    __syncthreads();
-
-    // ---- this thread's P points: sorted positions warp*BUCKET + lane*P + j ----------------------
-    const int pos0 = warp * BUCKET + lane * P;
-    float px[P], py[P], pz[P], td[P];
-    float blo[3] = {INFINITY, INFINITY, INFINITY}, bhi[3] = {-INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-    for (int j = 0; j < P; ++j) {
-        px[j] = py[j] = pz[j] = 0.f;
-        td[j] = -1.0f;  // padding: can never win, never lowers
-        if (pos0 + j < n) {
-            const float4 v = s_sorted[pos0 + j];
-            px[j] = v.x; py[j] = v.y; pz[j] = v.z;
-            td[j] = 1e38f;
-            blo[0] = fminf(blo[0], v.x); bhi[0] = fmaxf(bhi[0], v.x);
-            blo[1] = fminf(blo[1], v.y); bhi[1] = fmaxf(bhi[1], v.y);
-            blo[2] = fminf(blo[2], v.z); bhi[2] = fmaxf(bhi[2], v.z);
-        }
-    }
-    // bucket bounding box (empty buckets: +inf/-inf, their gap is +inf and they are always skipped)
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        blo[c] = warp_min_f(blo[c]);
-        bhi[c] = warp_max_f(bhi[c]);
-    }
-    // initial table entry: running minimum 1e38 everywhere -> the bucket's first point in
-    // tie-break order, which is sorted position warp*BUCKET (lane 0, j 0) if the bucket is non-empty
-    float wmax = -1.0f;
-    if (warp * BUCKET < n) wmax = 1e38f;
-    if (lane == 0) s_tab[0][warp] = make_uint2(wmax > 0.f ? __float_as_uint(1e38f) : 0u, (unsigned)min(warp * BUCKET, n - 1));
-
-    // the first pick is original index 0
-    float x1 = __ldg(pts + 0), y1 = __ldg(pts + 1), z1 = __ldg(pts + 2);
-    if (tid == 0) {
-        out[0] = 0;
-        if (oxyz) {
-            oxyz[0] = x1;
-            oxyz[1] = y1;
-            oxyz[2] = z1;
-        }
-    }
-    __syncthreads();
-
-    for (int it = 1; it < m; ++it) {
-        const int buf = it & 1;
-        // lower bound of every computed distance from the pick to a point of this bucket
-        const float gx = fmaxf(fmaxf(__fsub_rn(blo[0], x1), __fsub_rn(x1, bhi[0])), 0.f);
-        const float gy = fmaxf(fmaxf(__fsub_rn(blo[1], y1), __fsub_rn(y1, bhi[1])), 0.f);
-        const float gz = fmaxf(fmaxf(__fsub_rn(blo[2], z1), __fsub_rn(z1, bhi[2])), 0.f);
-        const float lb = __fmaf_rn(gz, gz, __fmaf_rn(gx, gx, __fmul_rn(gy, gy)));
-        if (lb < wmax) {  // warp-uniform: the pick can lower some running minimum in this bucket
-            float best = -1.0f;
-            int bj = 0;
-#pragma unroll
-            for (int j = 0; j < P; ++j) {
-                const float d = d2_fma_pattern(px[j], py[j], pz[j], x1, y1, z1);
-                const float d2 = fminf(d, td[j]);
-                td[j] = d2;
-                if (d2 > best) {  // register order == tie-break order: the first maximum wins
-                    best = d2;
-                    bj = j;
-                }
-            }
-            const bool has = best >= 0.0f;  // false only for lanes holding nothing but padding
-            const unsigned hi = has ? __float_as_uint(best) : 0u;
-            const unsigned mh = warp_max_u32(hi);
-            bool mine = (hi == mh);
-            const unsigned bal = __ballot_sync(kFullMask, mine);
-            if (bal & (bal - 1u)) {  // several lanes share the maximum: explicit tie-break (rare)
-                const unsigned lo = (mine && has) ? ~__float_as_uint(s_sorted[min(pos0 + bj, n - 1)].w) : 0u;
-                const unsigned ml = warp_max_u32(lo);
-                mine = mine && (lo == ml);
-                const unsigned bal2 = __ballot_sync(kFullMask, mine);
-                mine = mine && (lane == __ffs(bal2) - 1);  // all-padding buckets: any single lane
-            }
-            if (mine) s_tab[buf][warp] = make_uint2(mh, (unsigned)min(pos0 + bj, n - 1));
-            wmax = __uint_as_float(mh);  // an active bucket has valid points: mh is a real distance
-        } else {
-            // carry the cached entry forward; every lane stores the same value (no divergent branch)
-            s_tab[buf][warp] = s_tab[buf ^ 1][warp];
-        }
-        __syncthreads();
-        const bool in = lane < NW;
-        const uint2 e = in ? s_tab[buf][lane] : make_uint2(0u, 0u);
-        const unsigned gh = warp_max_u32(e.x);
-        bool top = in && (e.x == gh);
-        const unsigned gbal = __ballot_sync(kFullMask, top);
-        if (gbal & (gbal - 1u)) {  // several buckets share the maximum: explicit tie-break (rare)
-            const unsigned lo = top ? ~__float_as_uint(s_sorted[e.y].w) : 0u;
-            const unsigned gl = warp_max_u32(lo);
-            top = top && (lo == gl);
-        }
-        const unsigned wpos = warp_max_u32(top ? e.y : 0u);
-        const float4 c = s_sorted[wpos];
-        x1 = c.x;
-        y1 = c.y;
-        z1 = c.z;
-        if (tid == 0) {
-            out[it] = (int)tb_decode(__float_as_uint(c.w));
-            if (oxyz) {
-                oxyz[3 * it + 0] = x1;
-                oxyz[3 * it + 1] = y1;
-                oxyz[3 * it + 2] = z1;
-            }
-        }
-    }
-}
-
-// =================================================================================================
-// fps_prune_kernel — bucketed FPS with SUB-BUCKETS: few fat warps (the configuration that wins on
-// the ALU pipe / barrier side) AND fine pruning granularity.
-//
-// Warp w owns the w-th run of 32*P Morton-sorted points, split into SB = P/4 sub-buckets of 128
-// points (4 per lane, registers 4s..4s+3).  Lane s < SB keeps sub-bucket s's bounding box and
-// current maximum; one lane-parallel box test + one ballot per step tells the warp which
-// sub-buckets the new pick can touch, and only those are updated (each costs 4 fused
-// distance/min updates per lane and one redux for its new maximum).  Every thread caches its best
-// (value, register index) per sub-bucket, so the warp argmax after an update is a short tree over
-// SB cached values instead of a rescan of P points.  Exactness argument as in fps_bucket_kernel.
-// =================================================================================================
-template <int P, int T>
-__global__ void __launch_bounds__(T, 1)
-fps_prune_kernel(int n, int m, int npad, const float* __restrict__ xyz, int* __restrict__ idx_out,
-                 float* __restrict__ new_xyz) {
-    static_assert(P % 4 == 0 && P >= 4, "sub-buckets hold 4 points per lane");
-    constexpr int NW = T / 32;
-    constexpr int BUCKET = 32 * P;
-    constexpr int SB = P / 4;   // sub-buckets per warp
-    constexpr int SUB = 128;    // points per sub-bucket
-    static_assert(SB <= 32 && NW <= 32, "one lane per sub-bucket, one table entry per lane");
-    __shared__ uint2 s_tab[2][32];  // per warp: (max running minimum as float bits, sorted position of its argmax)
-    __shared__ float s_red[6][32];
-    extern __shared__ float4 s_dyn4[];  // [n] sorted points (x, y, z, tb bits), then [npad] u32 sort keys
-    float4* s_sorted = s_dyn4;
-    unsigned* s_key = reinterpret_cast<unsigned*>(s_dyn4 + n);
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int cloud = blockIdx.x;
-    const float* __restrict__ pts = xyz + (size_t)cloud * n * 3;
-    int* __restrict__ out = idx_out + (size_t)cloud * m;
-    float* __restrict__ oxyz = new_xyz ? new_xyz + (size_t)cloud * m * 3 : nullptr;
-
-    // ---- bounding box of the cloud, Morton sort, per-sub-bucket tie-break sort (as fps_bucket_kernel)
-    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int k = tid; k < n; k += T) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float v = __ldg(pts + 3 * (size_t)k + c);
-            mn[c] = fminf(mn[c], v);
-            mx[c] = fmaxf(mx[c], v);
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const float a = warp_min_f(mn[c]), b = warp_max_f(mx[c]);
-        if (lane == 0) {
-            s_red[c][warp] = a;
-            s_red[3 + c][warp] = b;
-        }
-    }
-    __syncthreads();
-    float scale[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        mn[c] = warp_min_f(lane < NW ? s_red[c][lane] : INFINITY);
-        mx[c] = warp_max_f(lane < NW ? s_red[3 + c][lane] : -INFINITY);
-        const float ext = mx[c] - mn[c];
-        scale[c] = (ext > 0.f && ext < 3.0e38f) ? 64.0f / ext : 0.0f;
-    }
-    for (int k = tid; k < npad; k += T) {
-        unsigned key = 0xffffffffu;
-        if (k < n) {
-            unsigned q[3];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                float f = (__ldg(pts + 3 * (size_t)k + c) - mn[c]) * scale[c];
-                f = fminf(fmaxf(f, 0.f), 63.f);
-                q[c] = (unsigned)f;
-            }
-            const unsigned mort = morton_part(q[0]) | (morton_part(q[1]) << 1) | (morton_part(q[2]) << 2);
-            key = (mort << 14) | (unsigned)k;  // k < 16384
-        }
-        s_key[k] = key;
-    }
-    __syncthreads();
-    bitonic_sort_smem<T>(s_key, npad, npad, tid);
-    for (int p = tid; p < npad; p += T) {
-        const unsigned key = s_key[p];
-        s_key[p] = (key == 0xffffffffu) ? 0xffffffffu : tb_encode(key & 0x3fffu);
-    }
-    __syncthreads();
-    bitonic_sort_smem<T>(s_key, npad, npad >= SUB ? SUB : npad, tid);
-    for (int p = tid; p < n; p += T) {
-        const unsigned tbk = s_key[p];
-        const unsigned k = tb_decode(tbk);
-        s_sorted[p] = make_float4(__ldg(pts + 3 * (size_t)k), __ldg(pts + 3 * (size_t)k + 1), __ldg(pts + 3 * (size_t)k + 2),
-                                  __uint_as_float(tbk));
-    }
-    __syncthreads();
-
-    // ---- registers: point r = 4*s + j of this lane is sorted position warp*BUCKET + s*SUB + lane*4 + j
-    const int wbase = warp * BUCKET;
-    float px[P], py[P], pz[P], td[P];
-    float tbv[SB];        // this thread's best running minimum inside sub-bucket s
-    unsigned tbj = 0u;    // its register offset j (2 bits per sub-bucket)
-    float blo[3] = {INFINITY, INFINITY, INFINITY}, bhi[3] = {-INFINITY, -INFINITY, -INFINITY};  // lane s: box of sub-bucket s
-    float smax = -1.0f;   // lane s: current maximum of sub-bucket s (-1: empty)
-#pragma unroll
-    for (int s = 0; s < SB; ++s) {
-        float lo3[3] = {INFINITY, INFINITY, INFINITY}, hi3[3] = {-INFINITY, -INFINITY, -INFINITY};
-        tbv[s] = -1.0f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int r = 4 * s + j;
-            const int pos = wbase + s * SUB + lane * 4 + j;
-            px[r] = py[r] = pz[r] = 0.f;
-            td[r] = -1.0f;
-            if (pos < n) {
-                const float4 v = s_sorted[pos];
-                px[r] = v.x; py[r] = v.y; pz[r] = v.z;
-                td[r] = 1e38f;
-                if (tbv[s] < 0.f) tbv[s] = 1e38f;  // first valid point of the thread in tie-break order: j stays 0
-                lo3[0] = fminf(lo3[0], v.x); hi3[0] = fmaxf(hi3[0], v.x);
-                lo3[1] = fminf(lo3[1], v.y); hi3[1] = fmaxf(hi3[1], v.y);
-                lo3[2] = fminf(lo3[2], v.z); hi3[2] = fmaxf(hi3[2], v.z);
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float a = warp_min_f(lo3[c]), b = warp_max_f(hi3[c]);
-            if (lane == s) {
-                blo[c] = a;
-                bhi[c] = b;
-            }
-        }
-        if (lane == s && wbase + s * SUB < n) smax = 1e38f;
-    }
-    // initial table entry: the warp's first valid point in tie-break order among maximal (1e38) values.
-    // Sub-buckets are Morton runs, not tie-break runs, so the earliest key must be searched: every
-    // sub-bucket's first position holds its smallest key.
-    {
-        unsigned best_lo = 0u, best_pos = (unsigned)min(wbase, n - 1);
-#pragma unroll
-        for (int s = 0; s < SB; ++s) {
-            const int pos = wbase + s * SUB;
-            if (pos < n) {
-                const unsigned lo = ~__float_as_uint(s_sorted[pos].w);
-                if (lo > best_lo) {
-                    best_lo = lo;
-                    best_pos = (unsigned)pos;
-                }
-            }
-        }
-        if (lane == 0) s_tab[0][warp] = make_uint2(wbase < n ? __float_as_uint(1e38f) : 0u, best_pos);
-    }
-    float x1 = __ldg(pts + 0), y1 = __ldg(pts + 1), z1 = __ldg(pts + 2);
-    if (tid == 0) {
-        out[0] = 0;
-        if (oxyz) {
-            oxyz[0] = x1;
-            oxyz[1] = y1;
-            oxyz[2] = z1;
-        }
-    }
-    __syncthreads();
-
-    for (int it = 1; it < m; ++it) {
-        const int buf = it & 1;
-        // lane s: can the pick lower any running minimum of sub-bucket s?
-        const float gx = fmaxf(fmaxf(__fsub_rn(blo[0], x1), __fsub_rn(x1, bhi[0])), 0.f);
-        const float gy = fmaxf(fmaxf(__fsub_rn(blo[1], y1), __fsub_rn(y1, bhi[1])), 0.f);
-        const float gz = fmaxf(fmaxf(__fsub_rn(blo[2], z1), __fsub_rn(z1, bhi[2])), 0.f);
-        const float lb = __fmaf_rn(gz, gz, __fmaf_rn(gx, gx, __fmul_rn(gy, gy)));
-        const unsigned amask = __ballot_sync(kFullMask, lb < smax);  // lanes >= SB: smax = -1, never set
-        if (amask != 0u) {
-#pragma unroll
-            for (int s = 0; s < SB; ++s) {
-                if (amask & (1u << s)) {  // warp-uniform
-                    float bv = -1.0f;
-                    unsigned bj = 0u;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int r = 4 * s + j;
-                        const float d = d2_fma_pattern(px[r], py[r], pz[r], x1, y1, z1);
-                        const float d2 = fminf(d, td[r]);
-                        td[r] = d2;
-                        if (d2 > bv) {  // register order == tie-break order inside the sub-bucket
-                            bv = d2;
-                            bj = (unsigned)j;
-                        }
-                    }
-                    tbv[s] = bv;
-                    tbj = (tbj & ~(3u << (2 * s))) | (bj << (2 * s));
-                    const unsigned mhs = warp_max_u32(bv >= 0.f ? __float_as_uint(bv) : 0u);
-                    if (lane == s) smax = __uint_as_float(mhs);  // an active sub-bucket is non-empty
-                }
-            }
-            // this thread's best over its sub-buckets: ties between sub-buckets are NOT in tie-break
-            // order (sub-buckets are spatial), so carry the candidate's key only when needed below
-            float best = tbv[0];
-            int bs = 0;
-#pragma unroll
-            for (int s = 1; s < SB; ++s) {
-                if (tbv[s] > best) {
-                    best = tbv[s];
-                    bs = s;
-                }
-            }
-            const bool has = best >= 0.0f;
-            const unsigned hi = has ? __float_as_uint(best) : 0u;
-            const unsigned mh = warp_max_u32(hi);
-            bool mine = (hi == mh);
-            // exact tie-break needs the key whenever the maximum may be shared: between lanes, or
-            // between sub-buckets of one thread
-            bool thread_tie = false;
-#pragma unroll
-            for (int s = 0; s < SB; ++s) thread_tie |= (s != bs) && (tbv[s] == best);
-            const unsigned bal = __ballot_sync(kFullMask, mine);
-            const bool any_tt = __any_sync(kFullMask, mine && thread_tie);
-            unsigned pos = (unsigned)min(wbase + bs * SUB + lane * 4 + (int)((tbj >> (2 * bs)) & 3u), n - 1);
-            if ((bal & (bal - 1u)) || any_tt) {  // rare: resolve by the reference key explicitly
-                unsigned lo = 0u;
-                if (mine && has) {
-#pragma unroll
-                    for (int s = 0; s < SB; ++s) {
-                        if (tbv[s] == best) {
-                            const unsigned ps = (unsigned)min(wbase + s * SUB + lane * 4 + (int)((tbj >> (2 * s)) & 3u), n - 1);
-                            const unsigned ls = ~__float_as_uint(s_sorted[ps].w);
-                            if (ls > lo) {
-                                lo = ls;
-                                pos = ps;
-                            }
-                        }
-                    }
-                }
-                const unsigned ml = warp_max_u32(lo);
-                mine = mine && (lo == ml);
-                const unsigned bal2 = __ballot_sync(kFullMask, mine);
-                mine = mine && (lane == __ffs(bal2) - 1);
-            }
-            if (mine) s_tab[buf][warp] = make_uint2(mh, pos);
-        } else {
-            s_tab[buf][warp] = s_tab[buf ^ 1][warp];
-        }
-        __syncthreads();
-        const bool in = lane < NW;
-        const uint2 e = in ? s_tab[buf][lane] : make_uint2(0u, 0u);
-        const unsigned gh = warp_max_u32(e.x);
-        bool top = in && (e.x == gh);
-        const unsigned gbal = __ballot_sync(kFullMask, top);
-        if (gbal & (gbal - 1u)) {
-            const unsigned lo = top ? ~__float_as_uint(s_sorted[e.y].w) : 0u;
-            const unsigned gl = warp_max_u32(lo);
-            top = top && (lo == gl);
-        }
-        const unsigned wpos = warp_max_u32(top ? e.y : 0u);
-        const float4 c = s_sorted[wpos];
-        x1 = c.x;
-        y1 = c.y;
-        z1 = c.z;
-        if (tid == 0) {
-            out[it] = (int)tb_decode(__float_as_uint(c.w));
-            if (oxyz) {
-                oxyz[3 * it + 0] = x1;
-                oxyz[3 * it + 1] = y1;
-                oxyz[3 * it + 2] = z1;
-            }
         }
     }
 }
@@ -888,29 +217,37 @@ fps_prune_kernel(int n, int m, int npad, const float* __restrict__ xyz, int* __r
 // =================================================================================================
 // One thread-block CLUSTER per cloud (C = 2..16 CTAs).  Thread t of CTA r owns points
 // k = t + T*(r + C*j): all in one reference slot (k mod 512) whenever C*T % 512 == 0.
-// Per step: CTA-local argmax as above, then warp 0 pushes the CTA's 8-byte key into slot r of
-// EVERY CTA's exchange buffer with st.async (which also completes 8 tx-bytes on that CTA's
-// mbarrier); all threads wait on their own CTA's mbarrier (expecting 8*C bytes), read the C keys
-// from local shared memory and reduce them.  Two buffers/mbarriers alternate by step parity.
-// XYZ_SMEM: coordinates are kept in shared memory instead of registers (only the running minimum
-// is register-resident) — for N/C too large for the register file.
+// Per step: CTA-local argmax as above; warp 0 then looks the CTA's candidate up in the CTA's
+// shared-memory copy of its own points and pushes a 20-byte message — the 8-byte key AND the
+// candidate's coordinates — into slot r of EVERY CTA's exchange buffer with st.async (one 16-byte
+// and one 4-byte store per peer, each completing tx-bytes on that peer's mbarrier); all threads wait
+// on their own CTA's mbarrier (expecting 20*C bytes), reduce the C keys and take the winner's
+// coordinates from the same local buffer.  Nothing on the per-step critical path leaves the cluster
+// (round 1 re-read the winner's coordinates from global memory/L2 every step: ~300 cycles).
+// Two buffers/mbarriers alternate by step parity; there is no cluster-wide barrier per step.
+// PR = points per thread whose coordinates are REGISTER-resident (the first PR of P).  PR == P: all
+// of them.  PR < P (clouds too large for the register file): the remaining P-PR points are streamed
+// from the shared-memory copy as 128-bit loads of 4 points per coordinate; the running minimum of
+// every point stays in registers.
 // =================================================================================================
-template <int P, int T, bool XYZ_SMEM>
+template <int P, int T, int PR>
 __global__ void __launch_bounds__(T, 1)
-fps_cluster_kernel(int n, int m, const float* __restrict__ xyz, int* __restrict__ idx_out,
+fps_cluster_kernel(int n, int m, int log2c, const float* __restrict__ xyz, int* __restrict__ idx_out,
                    float* __restrict__ new_xyz) {
-    // slot order: thread t of CTA r owns k = t + T*(r + C*j); all of them share the reference slot
-    // k mod 512 as long as C*T is a multiple of 512 (checked by the host dispatch)
     static_assert(T % 512 == 0 || 512 % T == 0, "T must divide or be a multiple of 512");
+    static_assert(PR == P || (PR % 4 == 0 && P % 4 == 0 && PR < P), "streamed points come in groups of four");
     constexpr int NW = T / 32;
+    constexpr bool STREAM = PR < P;
     __shared__ uint2 s_keys[2][32];
-    __shared__ __align__(8) unsigned long long s_xkeys[2][16];
+    __shared__ __align__(16) uint4 s_xa[2][16];   // per peer: (key lo, key hi, x bits, y bits)
+    __shared__ __align__(4) unsigned s_xz[2][16];  // per peer: z bits
     __shared__ __align__(8) unsigned long long s_mbar[2];
-    extern __shared__ float s_pts[];  // XYZ_SMEM: [3][P*T] SoA copy of this CTA's points
+    // this CTA's points.  !STREAM: SoA [c][j*T + t].  STREAM: float4 groups [(j/4)*3 + c][t] (.x..w = j%4)
+    extern __shared__ __align__(16) float s_pts[];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned C = cluster_nctarank(), rank = cluster_ctarank();
-    const int cloud = blockIdx.x / C;
+    const unsigned C = 1u << log2c, rank = cluster_ctarank();
+    const int cloud = blockIdx.x >> log2c;
     const float* __restrict__ pts = xyz + (size_t)cloud * n * 3;
     int* __restrict__ out = idx_out + (size_t)cloud * m;
     float* __restrict__ oxyz = new_xyz ? new_xyz + (size_t)cloud * m * 3 : nullptr;
@@ -921,7 +258,12 @@ fps_cluster_kernel(int n, int m, const float* __restrict__ xyz, int* __restrict_
         fence_mbar_init_cluster();
     }
 
-    float px[XYZ_SMEM ? 1 : P], py[XYZ_SMEM ? 1 : P], pz[XYZ_SMEM ? 1 : P], td[P];
+    auto slot_addr = [&](int j, int t, int c) -> int {  // float index of coordinate c of local point (j, t)
+        if constexpr (STREAM) return ((((j >> 2) * 3 + c) * T + t) << 2) + (j & 3);
+        else return c * P * T + j * T + t;
+    };
+
+    float px[PR], py[PR], pz[PR], td[P];
 #pragma unroll
     for (int j = 0; j < P; ++j) {
         const long long k = (long long)tid + (long long)T * (rank + (long long)C * j);
@@ -933,11 +275,10 @@ fps_cluster_kernel(int n, int m, const float* __restrict__ xyz, int* __restrict_
             t = 1e38f;
         }
         td[j] = t;
-        if constexpr (XYZ_SMEM) {
-            s_pts[0 * P * T + j * T + tid] = x;
-            s_pts[1 * P * T + j * T + tid] = y;
-            s_pts[2 * P * T + j * T + tid] = z;
-        } else {
+        s_pts[slot_addr(j, tid, 0)] = x;
+        s_pts[slot_addr(j, tid, 1)] = y;
+        s_pts[slot_addr(j, tid, 2)] = z;
+        if (j < PR) {
             px[j] = x;
             py[j] = y;
             pz[j] = z;
@@ -953,35 +294,38 @@ fps_cluster_kernel(int n, int m, const float* __restrict__ xyz, int* __restrict_
             oxyz[2] = z1;
         }
     }
-    // every CTA's mbarriers must be initialised before any peer targets them
+    // every CTA's mbarriers must be initialised (and its point copy complete) before any peer targets them
     cluster_sync_all();
 
     const unsigned mbar0 = smem_addr(&s_mbar[0]), mbar1 = smem_addr(&s_mbar[1]);
+    const float4* __restrict__ s4 = reinterpret_cast<const float4*>(s_pts);
 
     for (int it = 1; it < m; ++it) {
         const int q = it - 1, buf = q & 1;
         const unsigned parity = (unsigned)(q >> 1) & 1u;
         const unsigned mbar = buf ? mbar1 : mbar0;
-        if (tid == 0) mbar_arrive_expect_tx(mbar, 8u * C);
+        if (tid == 0) mbar_arrive_expect_tx(mbar, 20u * C);
 
-        float best = -1.0f;
-        int bj = 0;
-        if constexpr (XYZ_SMEM) {
+        float best;
+        int bj;
+        fps_step<PR, 1, P>(px, py, pz, td, x1, y1, z1, best, bj);  // the PR register-resident points
+        if constexpr (STREAM) {
 #pragma unroll
-            for (int j = 0; j < P; ++j) {
-                const float x = s_pts[0 * P * T + j * T + tid];
-                const float y = s_pts[1 * P * T + j * T + tid];
-                const float z = s_pts[2 * P * T + j * T + tid];
-                const float d = d2_fma_pattern(x, y, z, x1, y1, z1);
-                const float d2 = fminf(d, td[j]);
-                td[j] = d2;
-                if (d2 > best) {
-                    best = d2;
-                    bj = j;
+            for (int g = PR / 4; g < P / 4; ++g) {
+                const float4 X = s4[(g * 3 + 0) * T + tid], Y = s4[(g * 3 + 1) * T + tid], Z = s4[(g * 3 + 2) * T + tid];
+                const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = 4 * g + u;
+                    const float d = d2_fma_pattern(xs[u], ys[u], zs[u], x1, y1, z1);
+                    const float d2 = fminf(d, td[j]);
+                    td[j] = d2;
+                    if (d2 > best) {
+                        best = d2;
+                        bj = j;
+                    }
                 }
             }
-        } else {
-            fps_step<P>(px, py, pz, td, x1, y1, z1, best, bj);
         }
         unsigned hi = 0u, lo = 0u;
         if (best >= 0.0f) {
@@ -995,19 +339,39 @@ fps_cluster_kernel(int n, int m, const float* __restrict__ xyz, int* __restrict_
             uint2 e = (lane < NW) ? s_keys[buf][lane] : make_uint2(0u, 0u);
             unsigned ch = e.y, cl = e.x;
             warp_max_pair(ch, cl);
+            // the CTA's candidate: local point (j, t) of k = t + T*(rank + C*j)
+            float cx = 0.f, cy = 0.f, cz = 0.f;
+            if (cl != 0u) {
+                const unsigned k = tb_decode(~cl);
+                const int t = (int)(k % (unsigned)T), j = (int)((k / (unsigned)T) >> log2c);
+                if (j < P) {
+                    cx = s_pts[slot_addr(j, t, 0)];
+                    cy = s_pts[slot_addr(j, t, 1)];
+                    cz = s_pts[slot_addr(j, t, 2)];
+                }
+            }
+            const unsigned peer = lane & (C - 1u);
             if (lane < C) {
-                const unsigned long long key = ((unsigned long long)ch << 32) | cl;
-                st_async_u64(mapa_shared(smem_addr(&s_xkeys[buf][rank]), lane), key, mapa_shared(mbar, lane));
+                st_async_v4(mapa_shared(smem_addr(&s_xa[buf][rank]), peer), cl, ch, __float_as_uint(cx), __float_as_uint(cy),
+                            mapa_shared(mbar, peer));
+            } else if (lane < 2u * C) {
+                st_async_u32(mapa_shared(smem_addr(&s_xz[buf][rank]), peer), __float_as_uint(cz), mapa_shared(mbar, peer));
             }
         }
         mbar_wait_parity_cluster(mbar, parity);
-        const unsigned long long xe = (lane < C) ? s_xkeys[buf][lane] : 0ull;
-        unsigned gh = (unsigned)(xe >> 32), gl = (unsigned)xe;
+        unsigned gh = 0u, gl = 0u;
+        if (lane < C) {
+            const uint2 kk = *reinterpret_cast<const uint2*>(&s_xa[buf][lane]);
+            gl = kk.x;
+            gh = kk.y;
+        }
         warp_max_pair(gh, gl);
         const int old = (int)tb_decode(~gl);
-        x1 = __ldg(pts + 3 * (size_t)old + 0);
-        y1 = __ldg(pts + 3 * (size_t)old + 1);
-        z1 = __ldg(pts + 3 * (size_t)old + 2);
+        const unsigned wr = ((unsigned)old / (unsigned)T) & (C - 1u);  // the CTA that owns the winner
+        const uint4 wa = s_xa[buf][wr];
+        x1 = __uint_as_float(wa.z);
+        y1 = __uint_as_float(wa.w);
+        z1 = __uint_as_float(s_xz[buf][wr]);
         if (rank == 0 && tid == 0) {
             out[it] = old;
             if (oxyz) {
@@ -1090,77 +454,62 @@ fps_global_kernel(int b, int n, int m, const float* __restrict__ xyz, float* __r
 }
 
 // ---- host-side dispatch ------------------------------------------------------------------------
-static int g_cfg_threads = 0, g_cfg_ppt = 0, g_cfg_cluster = 0;  // pn2_set_fps_config override
+// Tuning override (pn2_set_fps_config / PN2_FPS_CFG): one atomic word, so concurrent launches from
+// several host threads always see a consistent (threads, points/thread, cluster) triple.
+static std::atomic<unsigned long long> g_fps_cfg{0ull};  // threads << 40 | ppt << 20 | (cluster + 64); 0 = built-in plan
+static std::once_flag g_fps_env_once;
 
-template <int P, int T>
-static int launch_cta(int b, int n, int m, const float* inp, int* out, float* new_xyz, cudaStream_t st) {
-    auto kern = fps_cta_kernel<P, T>;
-    size_t dyn = (size_t)n * 3 * sizeof(float);
-    if (dyn > 200 * 1024) return (int)cudaErrorInvalidValue;
+static unsigned long long pack_cfg(int threads, int ppt, int cluster) {
+    if (threads <= 0) return 0ull;
+    return ((unsigned long long)threads << 40) | ((unsigned long long)(ppt & 0xfffff) << 20) | (unsigned long long)(cluster + 64);
+}
+
+// cudaFuncSetAttribute once per (kernel instantiation, device), not on every launch
+struct AttrOnce {
+    std::atomic<unsigned long long> done{0ull};  // bit d: attributes set on device d (< 64)
+};
+template <typename K>
+static cudaError_t ensure_attrs(AttrOnce& once, K kern, size_t dyn, bool nonportable_cluster) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (dev < 64 && (once.done.load(std::memory_order_acquire) & bit)) return cudaSuccess;
     if (dyn > 40 * 1024) {  // static + dynamic beyond the 48 KB default needs the opt-in
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        if (e != cudaSuccess) return (int)e;
-    }
-    kern<<<b, T, dyn, st>>>(n, m, inp, out, new_xyz);
-    return finish_launch();
-}
-
-template <int P, int T>
-static int launch_cta2(int b, int n, int m, const float* inp, int* out, float* new_xyz, cudaStream_t st) {
-    auto kern = fps_cta2_kernel<P, T>;
-    size_t dyn = (size_t)n * 3 * sizeof(float);
-    if (dyn > 200 * 1024) return (int)cudaErrorInvalidValue;
-    if (dyn > 40 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        if (e != cudaSuccess) return (int)e;
-    }
-    kern<<<b, T, dyn, st>>>(n, m, inp, out, new_xyz);
-    return finish_launch();
-}
-
-template <int P, int T>
-static int launch_bucket(int b, int n, int m, const float* inp, int* out, float* new_xyz, cudaStream_t st) {
-    auto kern = fps_bucket_kernel<P, T>;
-    int npad = 1;
-    while (npad < n) npad <<= 1;
-    size_t dyn = (size_t)n * sizeof(float4) + (size_t)npad * sizeof(unsigned);
-    if (dyn > 220 * 1024 || n > 16384) return (int)cudaErrorInvalidValue;
-    if (dyn > 40 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        if (e != cudaSuccess) return (int)e;
-    }
-    kern<<<b, T, dyn, st>>>(n, m, npad, inp, out, new_xyz);
-    return finish_launch();
-}
-
-template <int P, int T>
-static int launch_prune(int b, int n, int m, const float* inp, int* out, float* new_xyz, cudaStream_t st) {
-    auto kern = fps_prune_kernel<P, T>;
-    int npad = 1;
-    while (npad < n) npad <<= 1;
-    size_t dyn = (size_t)n * sizeof(float4) + (size_t)npad * sizeof(unsigned);
-    if (dyn > 220 * 1024 || n > 16384) return (int)cudaErrorInvalidValue;
-    if (dyn > 40 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        if (e != cudaSuccess) return (int)e;
-    }
-    kern<<<b, T, dyn, st>>>(n, m, npad, inp, out, new_xyz);
-    return finish_launch();
-}
-
-template <int P, int T, bool XYZ_SMEM>
-static int launch_cluster(int C, int b, int n, int m, const float* inp, int* out, float* new_xyz, cudaStream_t st) {
-    auto kern = fps_cluster_kernel<P, T, XYZ_SMEM>;
-    size_t dyn = XYZ_SMEM ? (size_t)3 * P * T * sizeof(float) : 0;
-    cudaError_t e;
-    if (dyn > 40 * 1024) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-        if (e != cudaSuccess) return (int)e;
+        if (e != cudaSuccess) return e;
     }
-    if (C > 8) {
+    if (nonportable_cluster) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        if (e != cudaSuccess) return (int)e;
+        if (e != cudaSuccess) return e;
     }
+    if (dev < 64) once.done.fetch_or(bit, std::memory_order_release);
+    return cudaSuccess;
+}
+
+template <int P, int T>
+static int launch_cta(int b, int n, int m, const float* inp, int* out, float* new_xyz, int sentinel, cudaStream_t st) {
+    static AttrOnce once;
+    auto kern = fps_cta_kernel<P, T>;
+    // the opt-in is set for the largest cloud this instantiation can serve, so one call per device is enough
+    const size_t dyn = (size_t)n * 3 * sizeof(float), dyn_max = (size_t)P * T * 3 * sizeof(float);
+    if (dyn > 200 * 1024) return (int)cudaErrorInvalidValue;
+    cudaError_t e = ensure_attrs(once, kern, dyn_max > 200 * 1024 ? 200 * 1024 : dyn_max, false);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<b, T, dyn, st>>>(n, m, inp, out, new_xyz, sentinel);
+    return finish_launch();
+}
+
+template <int P, int T, int PR>
+static int launch_cluster(int C, int b, int n, int m, const float* inp, int* out, float* new_xyz, cudaStream_t st) {
+    static AttrOnce once;
+    auto kern = fps_cluster_kernel<P, T, PR>;
+    const size_t dyn = (size_t)3 * P * T * sizeof(float);
+    if (dyn > 200 * 1024) return (int)cudaErrorInvalidValue;
+    cudaError_t e = ensure_attrs(once, kern, dyn, true);
+    if (e != cudaSuccess) return (int)e;
+    int log2c = 0;
+    while ((1 << log2c) < C) ++log2c;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)b * C, 1, 1);
     cfg.blockDim = dim3(T, 1, 1);
@@ -1173,15 +522,15 @@ static int launch_cluster(int C, int b, int n, int m, const float* inp, int* out
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, n, m, inp, out, new_xyz);
+    e = cudaLaunchKernelEx(&cfg, kern, n, m, log2c, inp, out, new_xyz);
     count_launch();
     if (e != cudaSuccess) return (int)e;
     return (int)cudaGetLastError();
 }
 
 struct FpsPlan {
-    int threads, ppt, cluster;  // cluster == 0: global-scratch fallback; 1: single CTA; -1: bucketed single CTA; -2: single CTA, packed-math variant; -3: bucketed with sub-buckets (fps_prune_kernel)
-    bool xyz_smem;
+    int threads, ppt, cluster;  // cluster == 0: global-scratch fallback; 1: single CTA; >= 2: thread-block cluster
+    int pr;                     // cluster kernels: points per thread with register-resident coordinates (== ppt: all)
 };
 
 static int pow2_floor(int v) {
@@ -1191,42 +540,33 @@ static int pow2_floor(int v) {
 }
 
 static FpsPlan plan_fps(int b, int n) {
-    FpsPlan p{0, 0, 0, false};
-    static bool env_read = false;
-    if (!env_read) {  // PN2_FPS_CFG="threads,points_per_thread,cluster": profiling/tuning override
-        env_read = true;
+    std::call_once(g_fps_env_once, [] {  // PN2_FPS_CFG="threads,points_per_thread,cluster": profiling/tuning override
         const char* e = getenv("PN2_FPS_CFG");
-        if (e) {
-            int t = 0, pp = 0, c = 0;
-            if (sscanf(e, "%d,%d,%d", &t, &pp, &c) == 3) {
-                g_cfg_threads = t;
-                g_cfg_ppt = pp;
-                g_cfg_cluster = c;
-            }
-        }
-    }
-    if (g_cfg_threads > 0) {
-        p.threads = g_cfg_threads;
-        p.ppt = g_cfg_ppt;
-        p.cluster = g_cfg_cluster;
-        p.xyz_smem = (g_cfg_ppt >= 32 && g_cfg_threads >= 512);
+        int t = 0, pp = 0, c = 0;
+        if (e && sscanf(e, "%d,%d,%d", &t, &pp, &c) == 3) g_fps_cfg.store(pack_cfg(t, pp, c), std::memory_order_relaxed);
+    });
+    const unsigned long long ov = g_fps_cfg.load(std::memory_order_relaxed);
+    if (ov) {
+        FpsPlan p;
+        p.threads = (int)(ov >> 40);
+        p.ppt = (int)((ov >> 20) & 0xfffff);
+        p.cluster = (int)(ov & 0xfffff) - 64;
+        p.pr = (p.ppt >= 32 && p.threads >= 512) ? 16 : p.ppt;
         return p;
     }
     // single CTA, register-resident (cluster = 1).  Measured on B200 (profiles/r1_fps_sweep*.json):
     // few warps with many points each win at every size (4-8 warps; e.g. N=4096: 8 warps x 16 points
     // 0.313 us/step, 16 x 8: 0.410, 32 x 4: 0.501) — the step is bound by the ALU pipe, the per-warp
     // replicated reduction code and barrier latency, all of which shrink with fewer warps.
-    // The bucketed kernel (cluster = -1) prunes ~75 % of the distance updates but its longer
-    // dependent chain cancels the gain at these sizes; it stays selectable via pn2_set_fps_config.
-    if (n <= 128) return {128, 1, 1, false};
-    if (n <= 256) return {128, 2, 1, false};
-    if (n <= 512) return {256, 2, 1, false};
-    if (n <= 1024) return {128, 8, 1, false};
-    if (n <= 2048) return {128, 16, 1, false};
-    if (n <= 4096) return {256, 16, 1, false};
-    if (n <= 8192) return {256, 32, 1, false};
+    if (n <= 128) return {128, 1, 1, 1};
+    if (n <= 256) return {128, 2, 1, 2};
+    if (n <= 512) return {256, 2, 1, 2};
+    if (n <= 1024) return {128, 8, 1, 8};
+    if (n <= 2048) return {128, 16, 1, 16};
+    if (n <= 4096) return {256, 16, 1, 16};
+    if (n <= 8192) return {256, 32, 1, 32};
     // cluster: as many CTAs per cloud as keeps all clouds co-resident on the 148 SMs; inside each CTA
-    // again few fat warps (measured: N=16384 x8 clouds 0.72 -> 0.54 us/step, N=65536 1.05 -> 0.81)
+    // again few fat warps
     int cmax = pow2_floor(148 / (b > 148 ? 148 : b));
     if (cmax > 16) cmax = 16;
     if (cmax < 2) cmax = 2;
@@ -1235,106 +575,55 @@ static FpsPlan plan_fps(int b, int n) {
         const int pmin = (t == 128) ? 4 : 2;
         for (int pp = pmin; pp <= 32; pp *= 2) {
             if (per <= (long long)t * pp) {
-                out = {t, pp, C, false};
+                out = {t, pp, C, pp};
                 return true;
             }
         }
         if (per <= 256LL * 32) {
-            out = {256, 32, C, false};
+            out = {256, 32, C, 32};
             return true;
         }
         if (per <= 512LL * 32) {
-            out = {512, 32, C, true};  // coordinates in shared memory, running minimum in registers
+            out = {512, 32, C, 16};  // half of the coordinates in registers, half streamed from shared memory
             return true;
         }
         return false;
     };
     for (int C = cmax; C >= 2; C /= 2) {
         const long long per = ((long long)n + C - 1) / C;  // points per CTA
-        if (per <= 1024 && C > 2) continue;                // too thin: fewer, fatter CTAs (N=16384: 8 CTAs x 2048 pts 0.537 us/step, 16 x 1024 0.565)
+        if (per <= 1024 && C > 2) continue;                // too thin: fewer, fatter CTAs
+        FpsPlan p;
         if (pick(per, C, p)) return p;
         break;
     }
+    FpsPlan p;
     // widest cluster regardless of co-residency
     if (pick(((long long)n + 15) / 16, 16, p)) return p;
-    return {1024, 0, 0, false};
+    return {1024, 0, 0, 0};
 }
 
 #define PN2_TRY_CTA(PP, TT) \
-    if (plan.ppt == PP && plan.threads == TT) return launch_cta<PP, TT>(b, n, m, inp, out, new_xyz, st);
-#define PN2_TRY_CLU(PP, TT, XS) \
-    if (plan.ppt == PP && plan.threads == TT && plan.xyz_smem == XS) \
-        return launch_cluster<PP, TT, XS>(plan.cluster, b, n, m, inp, out, new_xyz, st);
+    if (plan.ppt == PP && plan.threads == TT) return launch_cta<PP, TT>(b, n, m, inp, out, new_xyz, sentinel, st);
+#define PN2_TRY_CLU(PP, TT, PRR) \
+    if (plan.ppt == PP && plan.threads == TT && plan.pr == PRR) \
+        return launch_cluster<PP, TT, PRR>(plan.cluster, b, n, m, inp, out, new_xyz, st);
 
-static int fps_dispatch(int b, int n, int m, const float* inp, float* temp, int* out, float* new_xyz, cudaStream_t st) {
+bool fps_single_cta(int b, int n) { return plan_fps(b, n).cluster == 1; }
+
+size_t fps_scratch_bytes(int b, int n) {
+    if (b <= 0 || n <= 0) return 0;
+    return plan_fps(b, n).cluster == 0 ? sizeof(float) * (size_t)(b < 32 ? b : 32) * (size_t)n : 0;
+}
+
+int fps_dispatch(int b, int n, int m, const float* inp, float* temp, int* out, float* new_xyz, int sentinel, cudaStream_t st) {
     if (b < 0 || n <= 0 || m < 0) return (int)cudaErrorInvalidValue;
     if (b == 0 || m == 0) return 0;
     if (!inp || !out) return (int)cudaErrorInvalidValue;
-    FpsPlan plan = plan_fps(b, n);
-    if (plan.cluster >= 1 || plan.cluster == -1 || plan.cluster == -2 || plan.cluster == -3) {
-        long long cap = (long long)plan.threads * plan.ppt * (plan.cluster < 0 ? 1 : plan.cluster);
+    const FpsPlan plan = plan_fps(b, n);
+    if (sentinel && plan.cluster != 1) return (int)cudaErrorInvalidValue;  // the fused layer asks fps_single_cta() first
+    if (plan.cluster >= 1) {
+        const long long cap = (long long)plan.threads * plan.ppt * plan.cluster;
         if (cap < n) return (int)cudaErrorInvalidValue;
-    }
-    if (plan.cluster == -3) {
-#define PN2_TRY_PRN(PP, TT) \
-    if (plan.ppt == PP && plan.threads == TT) return launch_prune<PP, TT>(b, n, m, inp, out, new_xyz, st);
-        PN2_TRY_PRN(4, 128)
-        PN2_TRY_PRN(8, 128)
-        PN2_TRY_PRN(16, 128)
-        PN2_TRY_PRN(32, 128)
-        PN2_TRY_PRN(4, 256)
-        PN2_TRY_PRN(8, 256)
-        PN2_TRY_PRN(16, 256)
-        PN2_TRY_PRN(32, 256)
-        PN2_TRY_PRN(4, 512)
-        PN2_TRY_PRN(8, 512)
-        PN2_TRY_PRN(16, 512)
-        return (int)cudaErrorInvalidValue;
-    }
-    if (plan.cluster == -2) {
-#define PN2_TRY_CTA2(PP, TT) \
-    if (plan.ppt == PP && plan.threads == TT) return launch_cta2<PP, TT>(b, n, m, inp, out, new_xyz, st);
-        PN2_TRY_CTA2(2, 128)
-        PN2_TRY_CTA2(4, 128)
-        PN2_TRY_CTA2(8, 128)
-        PN2_TRY_CTA2(16, 128)
-        PN2_TRY_CTA2(32, 128)
-        PN2_TRY_CTA2(2, 256)
-        PN2_TRY_CTA2(4, 256)
-        PN2_TRY_CTA2(8, 256)
-        PN2_TRY_CTA2(16, 256)
-        PN2_TRY_CTA2(32, 256)
-        PN2_TRY_CTA2(2, 512)
-        PN2_TRY_CTA2(4, 512)
-        PN2_TRY_CTA2(8, 512)
-        PN2_TRY_CTA2(16, 512)
-        return (int)cudaErrorInvalidValue;
-    }
-    if (plan.cluster == -1) {
-#define PN2_TRY_BKT(PP, TT) \
-    if (plan.ppt == PP && plan.threads == TT) return launch_bucket<PP, TT>(b, n, m, inp, out, new_xyz, st);
-        PN2_TRY_BKT(1, 128)
-        PN2_TRY_BKT(2, 128)
-        PN2_TRY_BKT(4, 128)
-        PN2_TRY_BKT(8, 128)
-        PN2_TRY_BKT(16, 128)
-        PN2_TRY_BKT(32, 128)
-        PN2_TRY_BKT(1, 256)
-        PN2_TRY_BKT(2, 256)
-        PN2_TRY_BKT(4, 256)
-        PN2_TRY_BKT(8, 256)
-        PN2_TRY_BKT(16, 256)
-        PN2_TRY_BKT(32, 256)
-        PN2_TRY_BKT(1, 512)
-        PN2_TRY_BKT(2, 512)
-        PN2_TRY_BKT(4, 512)
-        PN2_TRY_BKT(8, 512)
-        PN2_TRY_BKT(16, 512)
-        PN2_TRY_BKT(1, 1024)
-        PN2_TRY_BKT(2, 1024)
-        PN2_TRY_BKT(4, 1024)
-        PN2_TRY_BKT(8, 1024)
-        return (int)cudaErrorInvalidValue;
     }
     if (plan.cluster == 1) {
         PN2_TRY_CTA(1, 128)
@@ -1343,12 +632,12 @@ static int fps_dispatch(int b, int n, int m, const float* inp, float* temp, int*
         PN2_TRY_CTA(8, 128)
         PN2_TRY_CTA(16, 128)
         PN2_TRY_CTA(32, 128)
+        PN2_TRY_CTA(1, 256)
         PN2_TRY_CTA(2, 256)
         PN2_TRY_CTA(4, 256)
         PN2_TRY_CTA(8, 256)
         PN2_TRY_CTA(16, 256)
         PN2_TRY_CTA(32, 256)
-        PN2_TRY_CTA(1, 256)
         PN2_TRY_CTA(1, 512)
         PN2_TRY_CTA(2, 512)
         PN2_TRY_CTA(4, 512)
@@ -1363,27 +652,27 @@ static int fps_dispatch(int b, int n, int m, const float* inp, float* temp, int*
     if (plan.cluster >= 2) {
         if (plan.cluster > 16 || (plan.cluster & (plan.cluster - 1))) return (int)cudaErrorInvalidValue;
         if (((long long)plan.cluster * plan.threads) % 512 != 0) return (int)cudaErrorInvalidValue;
-        PN2_TRY_CLU(4, 128, false)
-        PN2_TRY_CLU(8, 128, false)
-        PN2_TRY_CLU(16, 128, false)
-        PN2_TRY_CLU(32, 128, false)
-        PN2_TRY_CLU(2, 256, false)
-        PN2_TRY_CLU(4, 256, false)
-        PN2_TRY_CLU(8, 256, false)
-        PN2_TRY_CLU(16, 256, false)
-        PN2_TRY_CLU(32, 256, false)
-        PN2_TRY_CLU(1, 512, false)
-        PN2_TRY_CLU(2, 512, false)
-        PN2_TRY_CLU(4, 512, false)
-        PN2_TRY_CLU(8, 512, false)
-        PN2_TRY_CLU(16, 512, false)
-        PN2_TRY_CLU(32, 512, true)
-        PN2_TRY_CLU(2, 1024, false)
-        PN2_TRY_CLU(4, 1024, false)
-        PN2_TRY_CLU(8, 1024, false)
+        PN2_TRY_CLU(4, 128, 4)
+        PN2_TRY_CLU(8, 128, 8)
+        PN2_TRY_CLU(16, 128, 16)
+        PN2_TRY_CLU(32, 128, 32)
+        PN2_TRY_CLU(2, 256, 2)
+        PN2_TRY_CLU(4, 256, 4)
+        PN2_TRY_CLU(8, 256, 8)
+        PN2_TRY_CLU(16, 256, 16)
+        PN2_TRY_CLU(32, 256, 32)
+        PN2_TRY_CLU(1, 512, 1)
+        PN2_TRY_CLU(2, 512, 2)
+        PN2_TRY_CLU(4, 512, 4)
+        PN2_TRY_CLU(8, 512, 8)
+        PN2_TRY_CLU(16, 512, 16)
+        PN2_TRY_CLU(32, 512, 16)
+        PN2_TRY_CLU(2, 1024, 2)
+        PN2_TRY_CLU(4, 1024, 4)
+        PN2_TRY_CLU(8, 1024, 8)
         return (int)cudaErrorInvalidValue;
     }
-    // global-scratch fallback
+    // global-scratch fallback: needs the reference's (32, n) float scratch (tf_sampling_g.cu:202)
     if (!temp) return (int)cudaErrorInvalidValue;
     int grid = b < 32 ? b : 32;
     fps_global_kernel<1024><<<grid, 1024, 0, st>>>(b, n, m, inp, temp, out, new_xyz);
@@ -1395,12 +684,14 @@ static int fps_dispatch(int b, int n, int m, const float* inp, float* temp, int*
 extern "C" {
 
 int pn2_fps(int b, int n, int m, const float* inp, float* temp, int* out, void* stream) {
-    return pn2::fps_dispatch(b, n, m, inp, temp, out, nullptr, pn2::as_stream(stream));
+    return pn2::fps_dispatch(b, n, m, inp, temp, out, nullptr, 0, pn2::as_stream(stream));
 }
 
-int pn2_fps_gather(int b, int n, int m, const float* inp, int* out, float* new_xyz, void* stream) {
-    return pn2::fps_dispatch(b, n, m, inp, nullptr, out, new_xyz, pn2::as_stream(stream));
+int pn2_fps_gather(int b, int n, int m, const float* inp, float* temp, int* out, float* new_xyz, void* stream) {
+    return pn2::fps_dispatch(b, n, m, inp, temp, out, new_xyz, 0, pn2::as_stream(stream));
 }
+
+size_t pn2_fps_scratch_bytes(int b, int n) { return pn2::fps_scratch_bytes(b, n); }
 
 int pn2_fps_plan(int b, int n, int* threads, int* points_per_thread, int* cluster) {
     if (b <= 0 || n <= 0) return (int)cudaErrorInvalidValue;
@@ -1412,9 +703,7 @@ int pn2_fps_plan(int b, int n, int* threads, int* points_per_thread, int* cluste
 }
 
 void pn2_set_fps_config(int threads, int points_per_thread, int cluster) {
-    pn2::g_cfg_threads = threads;
-    pn2::g_cfg_ppt = points_per_thread;
-    pn2::g_cfg_cluster = cluster;
+    pn2::g_fps_cfg.store(pn2::pack_cfg(threads, points_per_thread, cluster), std::memory_order_relaxed);
 }
 
 }  // extern "C"

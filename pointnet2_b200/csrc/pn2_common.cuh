@@ -69,6 +69,13 @@ __device__ __forceinline__ void warp_max_pair(unsigned& hi, unsigned& lo) {
 int launch_ball_query_brute(int b, int n, int m, float thr, int nsample, const float* xyz1, const float* xyz2,
                             int* idx, int* pts_cnt, const int* grid_params, int grid_stride, cudaStream_t st);
 
+// farthest point sampling dispatch (fps.cu), shared with the fused set-abstraction layer (sa_fused.cu).
+// sentinel != 0: single-CTA plans only (ask fps_single_cta first) — the kernel pre-fills `out` with -1 and
+// signals programmatic launch completion so that a dependent grid can consume the picks as they appear.
+int fps_dispatch(int b, int n, int m, const float* inp, float* temp, int* out, float* new_xyz, int sentinel, cudaStream_t st);
+bool fps_single_cta(int b, int n);
+size_t fps_scratch_bytes(int b, int n);
+
 // ---- streaming memory ops ---------------------------------------------------------------------
 __device__ __forceinline__ void st_stream_f4(float4* p, float4 v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream_i4(int4* p, int4 v) { __stcs(p, v); }

@@ -1,0 +1,476 @@
+// sa_fused.cu — the sampling+grouping half of a set-abstraction layer as ONE overlapped pair of
+// kernels, for sm_100a.
+//
+// Replaces the op sequence sample_and_group issues (reference utils/pointnet_util.py:40-46):
+//   farthest_point_sample -> gather_point -> query_ball_point -> group_point(xyz) [-> tile/sub]
+// i.e. tf_sampling_g.cu:105-181 + tf_grouping_g.cu:3-57, with results bit-identical to running
+// pn2_fps_gather, pn2_query_ball_point and pn2_group_point one after the other.
+//
+// Why: farthest point sampling is a serial chain that keeps ONE SM per cloud busy (32 of 148 at
+// B=32) for ~0.3 ms, and in round 1 the ball query + grouping (0.046 ms on the whole GPU) ran
+// strictly after it.  Here a second grid — `ball_group_kernel`, one 1024-thread CTA per cloud —
+// starts on the idle SMs as soon as every sampling CTA is resident (programmatic dependent launch:
+// the sampling kernel pre-fills its index output with -1 and executes
+// griddepcontrol.launch_dependents; SASS PREEXIT) and serves centroid j the moment index j turns
+// non-negative.  The consumer needs no flag and the producer no fence: the 4-byte index IS the
+// message (a centroid is a data point, so its coordinates are read from the immutable input cloud).
+// When the chain ends, all that is left is the last few queries: the layer costs the sampling time
+// plus ~1 us instead of plus 46 us.
+//
+// The consumer builds, in shared memory, the same uniform grid as ball_query_grid.cu (cell edge >=
+// 1.01 radius, points stored cell-sorted as float4 (x,y,z,index)) when the cloud's balls are sparse,
+// or keeps the cloud in index order when they are dense; a warp per query then either walks the 9
+// contiguous candidate ranges of the 3x3x3 cell neighbourhood and rank-sorts the hits by index, or
+// scans in index order with early exit.  The hit test is the very same expression on the very same
+// operands as ball_query.cu (pn2::d2_fma_pattern(query, point), !(d2 > thr)), so idx / pts_cnt are
+// bit-identical; grouped_xyz is emitted in the same pass (raw gather, or centred on the query with
+// one __fsub_rn per coordinate — utils/pointnet_util.py:46), so group_point(xyz) disappears.
+//
+// The same kernel also serves query_ball_point + group_point(xyz) on their own (all queries known up
+// front: several CTAs per cloud, no polling) — one launch instead of grid build + grid query +
+// brute-force + group.
+#include <math.h>
+
+#include <atomic>
+
+#include "pn2_common.cuh"
+
+namespace pn2 {
+
+constexpr int kBgThreads = 1024;
+constexpr int kBgWarps = kBgThreads / 32;
+constexpr int kBgMaxDim = 16;                                   // cells per axis
+constexpr int kBgMaxCells = kBgMaxDim * kBgMaxDim * kBgMaxDim;  // 4096
+constexpr int kBgHitCap = 128;                                  // hits buffered per query before the ordered scan takes over
+constexpr int kBgMinGridN = 512;                                // below this the in-smem ordered scan is already short
+constexpr float kBgDenseFrac = 0.9f;
+constexpr size_t kBgSmemMax = 200 * 1024;
+constexpr int kBgPosBits = 14;  // positions and indices < 2^14 (n <= 10750 by the shared-memory budget): one int holds both
+
+__host__ __device__ inline size_t bg_smem_bytes(int n) {
+    // float4 points + cell_start[kBgMaxCells + 1] (padded to 16 B) + cursors / hit buffers (aliased)
+    return (size_t)n * 16 + (size_t)(kBgMaxCells + 4) * 4 + (size_t)kBgWarps * kBgHitCap * 4;
+}
+
+__device__ __forceinline__ int bg_cell(float x, float origin, float inv_h, int dim) {
+    float f = floorf(__fmul_rn(__fsub_rn(x, origin), inv_h));
+    f = fminf(fmaxf(f, -1.0f), (float)dim);  // monotone; out-of-box (and NaN) queries map to the border cells +-1
+    return (int)f;
+}
+__device__ __forceinline__ float bg_wmin(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(kFullMask, v, o));
+    return v;
+}
+__device__ __forceinline__ float bg_wmax(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFullMask, v, o));
+    return v;
+}
+__device__ __forceinline__ int ld_volatile_s32(const int* p) {
+    int v;
+    asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// xyz1 (b,n,3) data.  Queries: xyz2 (b,m,3), or — when q_idx != NULL — the data points
+// xyz1[b, q_idx[b,j]], where q_idx (b,m) is being filled by a concurrently running sampling kernel
+// (-1 = not produced yet).  idx (b,m,nsample), pts_cnt (b,m), grouped (b,m,nsample,3) or NULL.
+__global__ void __launch_bounds__(kBgThreads, 1)
+ball_group_kernel(int n, int m, float radius, float thr, int nsample, const float* __restrict__ xyz1,
+                  const float* __restrict__ xyz2, const int* q_idx, int* __restrict__ idx,
+                  int* __restrict__ pts_cnt, float* __restrict__ grouped, int center, int ctas_per_cloud,
+                  int wait_primary) {
+    constexpr int T = kBgThreads, NW = kBgWarps;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    float4* __restrict__ s_pts = reinterpret_cast<float4*>(s_raw);                     // [n]
+    int* __restrict__ s_cell = reinterpret_cast<int*>(s_raw + (size_t)n * 16);          // [kBgMaxCells + 1]: cell_start
+    int* __restrict__ s_cur = s_cell + (kBgMaxCells + 4);                               // build: histogram / cursors
+    int(*s_hits)[kBgHitCap] = reinterpret_cast<int(*)[kBgHitCap]>(s_cur);               // query: per-warp hit positions
+    __shared__ float s_red[6][32];
+    __shared__ int s_wsum[32];
+    __shared__ int s_heavy;
+    __shared__ float4 s_first[NW];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cloud = blockIdx.x / ctas_per_cloud, part = blockIdx.x - cloud * ctas_per_cloud;
+    const float* __restrict__ pts = xyz1 + (size_t)cloud * n * 3;
+
+    // ---- bounding box (a NaN coordinate makes the box infinite: such clouds take the ordered scan,
+    //      the only path that reproduces "a NaN point is a hit in every ball", tf_grouping_g.cu:24-25)
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int k = tid; k < n; k += T) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = __ldg(pts + 3 * (size_t)k + c);
+            mn[c] = fminf(mn[c], v);
+            mx[c] = (v == v) ? fmaxf(mx[c], v) : INFINITY;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float a = bg_wmin(mn[c]), b = bg_wmax(mx[c]);
+        if (lane == 0) {
+            s_red[c][warp] = a;
+            s_red[3 + c][warp] = b;
+        }
+    }
+    for (int c = tid; c < kBgMaxCells; c += T) s_cur[c] = 0;
+    if (tid == 0) s_heavy = 0;
+    __syncthreads();
+    float ext[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        mn[c] = bg_wmin(s_red[c][lane]);
+        mx[c] = bg_wmax(s_red[3 + c][lane]);
+        ext[c] = mx[c] - mn[c];
+    }
+    const float emax = fmaxf(fmaxf(ext[0], ext[1]), ext[2]);
+    float h = fmaxf(1.01f * radius, emax / (float)(kBgMaxDim - 1));
+    const bool finite_box = (emax >= 0.f) && (emax < 1e30f) && (h > 0.f) && (h < 1e30f);
+    if (!finite_box) h = 1.0f;
+    const float inv_h = 1.0f / h;
+    int dims[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int d = finite_box ? (int)floorf(ext[c] * inv_h) + 1 : 1;
+        dims[c] = min(max(d, 1), kBgMaxDim);
+    }
+    const int ncell = dims[0] * dims[1] * dims[2];
+    const int nb = min(dims[0], 3) * min(dims[1], 3) * min(dims[2], 3);
+    const float vol = fmaxf(ext[0], h) * fmaxf(ext[1], h) * fmaxf(ext[2], h);
+    const float expect = (float)n * 4.18879f * radius * radius * radius / vol;
+    // same rules as ball_query_grid.cu: the neighbourhood must prune >= 70 % of the cloud, and the balls
+    // must be sparse (when they fill up, the ordered scan exits early and wins)
+    bool use_grid = finite_box && n >= kBgMinGridN && 10 * nb <= 3 * ncell && expect < 0.75f * (float)nsample;
+    __syncthreads();  // s_red is reused below
+    if (use_grid) {   // CTA-uniform
+        for (int k = tid; k < n; k += T) {
+            int cc[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+                cc[c] = min(max(bg_cell(__ldg(pts + 3 * (size_t)k + c), mn[c], inv_h, dims[c]), 0), dims[c] - 1);
+            atomicAdd(&s_cur[(cc[2] * dims[1] + cc[1]) * dims[0] + cc[0]], 1);
+        }
+        __syncthreads();
+        const int per = (ncell + T - 1) / T;
+        const int c0 = min(tid * per, ncell), c1 = min(c0 + per, ncell);
+        int local = 0, heavy = 0;
+        float sq = 0.f;
+        for (int c = c0; c < c1; ++c) {
+            const int cntc = s_cur[c];
+            local += cntc;
+            sq += (float)cntc * (float)cntc;
+            heavy |= (cntc > 256) ? 1 : 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(kFullMask, sq, o);
+        if (lane == 0) s_red[0][warp] = sq;
+        if (heavy) s_heavy = 1;
+        int incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        int wv = s_wsum[lane], winc = wv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(kFullMask, winc, o);
+            if (lane >= o) winc += v;
+        }
+        const int wprefix = __shfl_sync(kFullMask, winc - wv, warp);
+        int run = wprefix + incl - local;
+        for (int c = c0; c < c1; ++c) {
+            const int cntc = s_cur[c];
+            s_cell[c] = run;
+            s_cur[c] = run;
+            run += cntc;
+        }
+        if (tid == 0) s_cell[ncell] = n;
+        float sqsum = s_red[0][lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sqsum += __shfl_xor_sync(kFullMask, sqsum, o);
+        const float rh = radius * inv_h;
+        const float expect_local = 4.18879f * rh * rh * rh * sqsum / (float)n;
+        __syncthreads();
+        use_grid = (s_heavy == 0) && (expect_local < kBgDenseFrac * (float)nsample);
+        if (use_grid) {
+            for (int k = tid; k < n; k += T) {
+                const float x = __ldg(pts + 3 * (size_t)k), y = __ldg(pts + 3 * (size_t)k + 1), z = __ldg(pts + 3 * (size_t)k + 2);
+                const int cx = min(max(bg_cell(x, mn[0], inv_h, dims[0]), 0), dims[0] - 1);
+                const int cy = min(max(bg_cell(y, mn[1], inv_h, dims[1]), 0), dims[1] - 1);
+                const int cz = min(max(bg_cell(z, mn[2], inv_h, dims[2]), 0), dims[2] - 1);
+                const int pos = atomicAdd(&s_cur[(cz * dims[1] + cy) * dims[0] + cx], 1);
+                s_pts[pos] = make_float4(x, y, z, __int_as_float(k));
+            }
+        }
+    }
+    if (!use_grid) {  // index order: the ordered scan reads it straight from shared memory
+        for (int k = tid; k < n; k += T)
+            s_pts[k] = make_float4(__ldg(pts + 3 * (size_t)k), __ldg(pts + 3 * (size_t)k + 1), __ldg(pts + 3 * (size_t)k + 2),
+                                   __int_as_float(k));
+    }
+    __syncthreads();  // grid / cloud complete; s_cur is dead from here on (s_hits aliases it)
+
+    // ---- queries: warp `gw` of the cloud's ctas_per_cloud*32 warps serves queries gw, gw + stride, ... ----
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const int qstride = ctas_per_cloud * NW;
+    const int dxs = dims[0], dys = dims[1], dzs = dims[2];
+    const long long t_start = clock64();
+    for (int q = part * NW + warp; q < m; q += qstride) {
+        float qx, qy, qz;
+        if (q_idx) {
+            // wait for the sampling kernel to publish centroid q (its index turns non-negative)
+            int qi = 0;
+            if (lane == 0) {
+                const int* src = q_idx + (size_t)cloud * m + q;
+                qi = ld_volatile_s32(src);
+                unsigned backoff = 32;
+                while (qi < 0) {
+                    __nanosleep(backoff);
+                    if (backoff < 256) backoff <<= 1;
+                    qi = ld_volatile_s32(src);
+                    if (clock64() - t_start > 4000000000ll) break;  // ~2 s: never hang the device on a lost producer
+                }
+            }
+            qi = __shfl_sync(kFullMask, qi, 0);
+            if (qi < 0 || qi >= n) {  // producer lost / corrupt index: flag the row instead of faulting
+                if (lane == 0) pts_cnt[(size_t)cloud * m + q] = -1;
+                continue;
+            }
+            qx = __ldg(pts + 3 * (size_t)qi);
+            qy = __ldg(pts + 3 * (size_t)qi + 1);
+            qz = __ldg(pts + 3 * (size_t)qi + 2);
+        } else {
+            const float* qp = xyz2 + ((size_t)cloud * m + q) * 3;
+            qx = __ldg(qp);
+            qy = __ldg(qp + 1);
+            qz = __ldg(qp + 2);
+        }
+        const float ox = center ? qx : 0.f, oy = center ? qy : 0.f, oz = center ? qz : 0.f;
+        int* __restrict__ row = idx + ((size_t)cloud * m + q) * nsample;
+        float* __restrict__ grow = grouped ? grouped + ((size_t)cloud * m + q) * nsample * 3 : nullptr;
+        auto emit = [&](int r, int k, float x, float y, float z) {
+            row[r] = k;
+            if (grow) {
+                // centred: xyz[idx] - new_xyz, one rounding per coordinate (utils/pointnet_util.py:46); x - 0 == x otherwise
+                grow[3 * r + 0] = __fsub_rn(x, ox);
+                grow[3 * r + 1] = __fsub_rn(y, oy);
+                grow[3 * r + 2] = __fsub_rn(z, oz);
+            }
+        };
+
+        int cnt = 0;
+        bool scanned = false;
+        const bool qfinite = (fabsf(qx) <= 3.0e38f) && (fabsf(qy) <= 3.0e38f) && (fabsf(qz) <= 3.0e38f);  // false for NaN / inf
+        if (use_grid && qfinite) {
+            const int cx = bg_cell(qx, mn[0], inv_h, dxs), cy = bg_cell(qy, mn[1], inv_h, dys), cz = bg_cell(qz, mn[2], inv_h, dzs);
+            const int x0 = max(cx - 1, 0), x1 = min(cx + 1, dxs - 1);
+            // 9 rows (dy, dz in {-1,0,1}) of up to 3 x-adjacent cells = 9 contiguous candidate ranges;
+            // lanes 3r..3r+2 walk range r with stride 3
+            int p = 0, p1 = 0;
+            {
+                const int r = lane / 3, sub = lane - 3 * r;
+                const int y = cy + (r % 3) - 1, z = cz + (r / 3) - 1;
+                if (lane < 27 && x0 <= x1 && y >= 0 && y < dys && z >= 0 && z < dzs) {
+                    const int rowbase = (z * dys + y) * dxs;
+                    p = s_cell[rowbase + x0] + sub;
+                    p1 = s_cell[rowbase + x1 + 1];
+                }
+            }
+            int hcount = 0;
+            while (__any_sync(kFullMask, p < p1)) {
+                bool hit = false;
+                if (p < p1) {
+                    const float4 c = s_pts[p];
+                    hit = !(d2_fma_pattern(qx, qy, qz, c.x, c.y, c.z) > thr);
+                }
+                const unsigned bal = __ballot_sync(kFullMask, hit);
+                if (bal) {
+                    const int r = hcount + __popc(bal & lt_mask);
+                    // key = (data index << 14 | position): indices are distinct, so keys order by index
+                    if (hit && r < kBgHitCap) s_hits[warp][r] = (__float_as_int(s_pts[p].w) << kBgPosBits) | p;
+                    hcount += __popc(bal);
+                    if (hcount > kBgHitCap) break;  // warp-uniform: dense ball, take the ordered scan
+                }
+                p += 3;
+            }
+            if (hcount <= kBgHitCap) {
+                // order the (distinct) hits by data index: rank = number of hits with a smaller index
+                __syncwarp();
+                cnt = min(hcount, nsample);
+                for (int e = lane; e < hcount; e += 32) {
+                    const int key = s_hits[warp][e];
+                    int r = 0;
+                    for (int f = 0; f < hcount; ++f) r += (s_hits[warp][f] < key) ? 1 : 0;
+                    const float4 c = s_pts[key & ((1 << kBgPosBits) - 1)];
+                    if (r < nsample) emit(r, key >> kBgPosBits, c.x, c.y, c.z);
+                    if (r == 0) s_first[warp] = c;
+                }
+                scanned = true;
+            }
+        }
+        if (!scanned) {
+            // ordered scan with early exit: from shared memory when the cloud is stored in index order,
+            // from global memory (L1/L2) when it is stored cell-sorted
+            for (int base = 0; base < n && cnt < nsample; base += 32) {
+                const int k = base + lane;
+                bool hit = false;
+                float x = 0.f, y = 0.f, z = 0.f;
+                if (k < n) {
+                    if (use_grid) {
+                        x = __ldg(pts + 3 * (size_t)k);
+                        y = __ldg(pts + 3 * (size_t)k + 1);
+                        z = __ldg(pts + 3 * (size_t)k + 2);
+                    } else {
+                        const float4 c = s_pts[k];
+                        x = c.x;
+                        y = c.y;
+                        z = c.z;
+                    }
+                    hit = !(d2_fma_pattern(qx, qy, qz, x, y, z) > thr);
+                }
+                const unsigned bal = __ballot_sync(kFullMask, hit);
+                if (bal) {
+                    const int r = cnt + __popc(bal & lt_mask);
+                    if (hit && r < nsample) emit(r, k, x, y, z);
+                    if (hit && r == 0) s_first[warp] = make_float4(x, y, z, __int_as_float(k));
+                    cnt = min(cnt + __popc(bal), nsample);
+                }
+            }
+        }
+        __syncwarp();
+        // pad the row with the first hit (tf_grouping_g.cu:26-29); rows with no hit are zeros (undefined in the reference)
+        const float4 f = (cnt > 0) ? s_first[warp] : make_float4(ox, oy, oz, __int_as_float(0));
+        const int fk = (cnt > 0) ? __float_as_int(f.w) : 0;
+        for (int l = cnt + lane; l < nsample; l += 32) {
+            row[l] = fk;
+            if (grow) {
+                if (cnt > 0) {
+                    grow[3 * l + 0] = __fsub_rn(f.x, ox);
+                    grow[3 * l + 1] = __fsub_rn(f.y, oy);
+                    grow[3 * l + 2] = __fsub_rn(f.z, oz);
+                } else {  // index 0 is what an unfused group_point would gather for an all-zero row
+                    grow[3 * l + 0] = __fsub_rn(__ldg(pts + 0), ox);
+                    grow[3 * l + 1] = __fsub_rn(__ldg(pts + 1), oy);
+                    grow[3 * l + 2] = __fsub_rn(__ldg(pts + 2), oz);
+                }
+            }
+        }
+        if (lane == 0) pts_cnt[(size_t)cloud * m + q] = cnt;
+        __syncwarp();  // s_first / s_hits are reused by this warp's next query
+    }
+    // Completion of this grid must imply completion of the sampling grid it overlaps (stream order and
+    // graph edges only see this grid): wait for the primary to finish and flush (SASS ACQBULK).
+    if (wait_primary) asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+struct BgOnce {
+    std::atomic<unsigned long long> done{0ull};
+};
+
+static int launch_ball_group(int b, int n, int m, float radius, float thr, int nsample, const float* xyz1, const float* xyz2,
+                             const int* q_idx, int* idx, int* pts_cnt, float* grouped, int center, int ctas_per_cloud,
+                             bool dependent, cudaStream_t st) {
+    static BgOnce once;
+    const size_t dyn = bg_smem_bytes(n);
+    if (dyn > kBgSmemMax) return (int)cudaErrorInvalidValue;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return (int)e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (dev >= 64 || !(once.done.load(std::memory_order_acquire) & bit)) {
+        e = cudaFuncSetAttribute(ball_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBgSmemMax);
+        if (e != cudaSuccess) return (int)e;
+        if (dev < 64) once.done.fetch_or(bit, std::memory_order_release);
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)b * (unsigned)ctas_per_cloud, 1, 1);
+    cfg.blockDim = dim3(kBgThreads, 1, 1);
+    cfg.dynamicSmemBytes = dyn;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = dependent ? 1 : 0;
+    e = cudaLaunchKernelEx(&cfg, ball_group_kernel, n, m, radius, thr, nsample, xyz1, xyz2, q_idx, idx, pts_cnt, grouped, center,
+                           ctas_per_cloud, dependent ? 1 : 0);
+    count_launch();
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaGetLastError();
+}
+
+static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+}  // namespace pn2
+
+extern "C" {
+
+int pn2_ball_group_fits(int n) {
+    return (n > 0 && n < (1 << pn2::kBgPosBits) && pn2::bg_smem_bytes(n) <= pn2::kBgSmemMax) ? 1 : 0;
+}
+
+int pn2_ball_group(int b, int n, int m, float radius, int nsample, const float* xyz1, const float* xyz2, int* idx,
+                   int* pts_cnt, float* grouped_xyz, int center, void* stream) {
+    using namespace pn2;
+    if (b < 0 || n <= 0 || m < 0 || nsample <= 0 || !(radius > 0.0f)) return (int)cudaErrorInvalidValue;
+    if (b == 0 || m == 0) return 0;
+    if (!xyz1 || !xyz2 || !idx || !pts_cnt) return (int)cudaErrorInvalidValue;
+    const float thr = pn2_ball_threshold(radius);
+    if (!pn2_ball_group_fits(n) || thr < 0.0f || (long long)b * 148 > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
+    // several CTAs per cloud until the machine is full (each builds its own copy of the grid: the
+    // build is ~n/1024 shared-memory atomics per thread) — but never more than the queries can feed
+    int r = 148 / (b < 148 ? b : 148);
+    const int rmax = (m + kBgWarps - 1) / kBgWarps;
+    if (r > rmax) r = rmax;
+    if (r < 1) r = 1;
+    return launch_ball_group(b, n, m, radius, thr, nsample, xyz1, xyz2, nullptr, idx, pts_cnt, grouped_xyz, center, r, false,
+                             as_stream(stream));
+}
+
+size_t pn2_sa_layer_device_workspace_bytes(int b, int n, int m, int nsample) {
+    if (b <= 0 || n <= 0 || m <= 0 || nsample <= 0) return 0;
+    (void)m;
+    (void)nsample;
+    // sequential fallback only: FPS scratch for clouds beyond the cluster capacity + the uniform-grid scratch
+    return pn2::align256(pn2_fps_scratch_bytes(b, n)) + pn2::align256(pn2_query_ball_point_workspace_bytes(b, n));
+}
+
+int pn2_sa_layer_device(int b, int n, int m, float radius, int nsample, const float* xyz, int* fps_idx, float* new_xyz,
+                        int* idx, int* pts_cnt, float* grouped_xyz, int center, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+    using namespace pn2;
+    if (b < 0 || n <= 0 || m < 0 || nsample <= 0 || !(radius > 0.0f)) return (int)cudaErrorInvalidValue;
+    if (b == 0 || m == 0) return 0;
+    if (!xyz || !fps_idx || !new_xyz || !idx || !pts_cnt) return (int)cudaErrorInvalidValue;
+    cudaStream_t st = as_stream(stream);
+    const float thr = pn2_ball_threshold(radius);
+    if (fps_single_cta(b, n) && pn2_ball_group_fits(n) && thr >= 0.0f) {
+        // overlapped pair: sampling (one CTA per cloud) + dependent ball_group grid (one CTA per cloud)
+        int rc = fps_dispatch(b, n, m, xyz, nullptr, fps_idx, new_xyz, /*sentinel=*/1, st);
+        if (rc) return rc;
+        return launch_ball_group(b, n, m, radius, thr, nsample, xyz, nullptr, fps_idx, idx, pts_cnt, grouped_xyz, center, 1, true, st);
+    }
+    // sequential path (clustered / global-scratch sampling, or clouds too large for the in-smem grid)
+    const size_t fps_b = align256(pn2_fps_scratch_bytes(b, n)), bq_b = pn2_query_ball_point_workspace_bytes(b, n);
+    char* ws = static_cast<char*>(workspace);
+    float* temp = nullptr;
+    void* bq_ws = nullptr;
+    if (fps_b) {
+        if (!ws || workspace_bytes < fps_b) return (int)cudaErrorInvalidValue;
+        temp = reinterpret_cast<float*>(ws);
+    }
+    if (bq_b && ws && workspace_bytes >= fps_b + bq_b) bq_ws = ws + fps_b;
+    int rc = pn2_fps_gather(b, n, m, xyz, temp, fps_idx, new_xyz, stream);
+    if (rc) return rc;
+    rc = pn2_query_ball_point_ws(b, n, m, radius, nsample, xyz, new_xyz, idx, pts_cnt, bq_ws, bq_ws ? bq_b : 0, stream);
+    if (rc || !grouped_xyz) return rc;
+    if (center) return pn2_group_concat(b, n, 0, m, nsample, xyz, new_xyz, nullptr, idx, 1, grouped_xyz, nullptr, stream);
+    return pn2_group_point(b, n, 3, m, nsample, xyz, idx, grouped_xyz, stream);
+}
+
+}  // extern "C"

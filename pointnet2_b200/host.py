@@ -4,8 +4,8 @@ The reference is driven from numpy through ``sess.run(feed_dict=...)`` (train.py
 start in host memory and results come back to host memory.  ``SetAbstractionHost`` is that call
 for one SSG sampling+grouping layer (farthest_point_sample + gather_point + query_ball_point +
 group_point(xyz), utils/pointnet_util.py:40-45): it owns pinned host staging buffers and a device
-workspace, and each ``run`` issues H2D copy -> 4 kernels -> D2H copies on one stream through the
-C-ABI ``pn2_sa_layer_host``.
+workspace, and each ``run`` issues H2D copy -> the overlapped sampling + grouping kernels (sa_fused.cu) -> D2H copies on one
+stream through the C-ABI ``pn2_sa_layer_host``.
 
 ``SetAbstractionPipeline`` is the same call for a STREAM of batches (the reference's training loop
 feeds one batch per ``sess.run`` while its input queue prepares the next, train.py:207-231): a ring
@@ -21,11 +21,11 @@ import ctypes
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, numa
 
 
 class SetAbstractionHost:
-    def __init__(self, b: int, n: int, npoint: int, radius: float, nsample: int, device=None):
+    def __init__(self, b: int, n: int, npoint: int, radius: float, nsample: int, device=None, want_grouped: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("SetAbstractionHost needs a CUDA device: pointnet2_b200 has no CPU path")
         self.b, self.n, self.m, self.radius, self.s = int(b), int(n), int(npoint), float(radius), int(nsample)
@@ -36,14 +36,23 @@ class SetAbstractionHost:
             raise ValueError("SetAbstractionHost expects positive b, n, npoint, nsample")
         self.workspace = torch.empty(ws, dtype=torch.uint8, device=self.device)
         pin = dict(pin_memory=True)
-        self.h_xyz = torch.empty((self.b, self.n, 3), dtype=torch.float32, **pin)
-        self.h_new_xyz = torch.empty((self.b, self.m, 3), dtype=torch.float32, **pin)
-        self.h_idx = torch.empty((self.b, self.m, self.s), dtype=torch.int32, **pin)
-        self.h_pts_cnt = torch.empty((self.b, self.m), dtype=torch.int32, **pin)
-        self.h_grouped_xyz = torch.empty((self.b, self.m, self.s, 3), dtype=torch.float32, **pin)
+        # pinned staging buffers are placed on the NUMA node the GPU hangs off (the copies of a rank
+        # whose buffers sit on the other socket cross the inter-socket link and do not scale)
+        with numa.prefer_node_of(self.device):
+            self.h_xyz = torch.empty((self.b, self.n, 3), dtype=torch.float32, **pin)
+            self.h_new_xyz = torch.empty((self.b, self.m, 3), dtype=torch.float32, **pin)
+            self.h_idx = torch.empty((self.b, self.m, self.s), dtype=torch.int32, **pin)
+            self.h_pts_cnt = torch.empty((self.b, self.m), dtype=torch.int32, **pin)
+            # want_grouped=False: grouped_xyz is neither computed nor copied back (it is xyz[idx], which a
+            # host-side caller can regroup itself) — 3/4 of the device-to-host bytes of the layer
+            self.h_grouped_xyz = (torch.empty((self.b, self.m, self.s, 3), dtype=torch.float32, **pin)
+                                  if want_grouped else None)
+            for t in (self.h_xyz, self.h_new_xyz, self.h_idx, self.h_pts_cnt, self.h_grouped_xyz):
+                if t is not None:
+                    t.zero_()  # first touch under the NUMA preference
         self.h2d_bytes = self.h_xyz.numel() * 4
         self.d2h_bytes = 4 * (self.h_new_xyz.numel() + self.h_idx.numel() + self.h_pts_cnt.numel()
-                              + self.h_grouped_xyz.numel())
+                              + (self.h_grouped_xyz.numel() if want_grouped else 0))
 
     def launch(self, stream: torch.cuda.Stream | None = None) -> None:
         """Enqueue copy-in, the four kernels and copy-out for whatever is in ``self.h_xyz``."""
@@ -53,7 +62,8 @@ class SetAbstractionHost:
                 self.b, self.n, self.m, self.radius, self.s,
                 ctypes.c_void_p(self.h_xyz.data_ptr()), ctypes.c_void_p(self.h_new_xyz.data_ptr()),
                 ctypes.c_void_p(self.h_idx.data_ptr()), ctypes.c_void_p(self.h_pts_cnt.data_ptr()),
-                ctypes.c_void_p(self.h_grouped_xyz.data_ptr()), ctypes.c_void_p(self.workspace.data_ptr()),
+                ctypes.c_void_p(self.h_grouped_xyz.data_ptr() if self.h_grouped_xyz is not None else 0),
+                ctypes.c_void_p(self.workspace.data_ptr()),
                 ctypes.c_size_t(self.workspace.numel()), ctypes.c_void_p(st.cuda_stream))
         _lib.check(rc, "pn2_sa_layer_host")
 
@@ -66,7 +76,7 @@ class SetAbstractionHost:
         self.launch()
         torch.cuda.current_stream(self.device).synchronize()
         return (self.h_new_xyz.numpy().copy(), self.h_idx.numpy().copy(), self.h_pts_cnt.numpy().copy(),
-                self.h_grouped_xyz.numpy().copy())
+                self.h_grouped_xyz.numpy().copy() if self.h_grouped_xyz is not None else None)
 
 
 class SetAbstractionPipeline:
@@ -86,10 +96,12 @@ class SetAbstractionPipeline:
     next ``submit`` that reuses the slot (``depth`` submits later).
     """
 
-    def __init__(self, b: int, n: int, npoint: int, radius: float, nsample: int, depth: int = 2, device=None):
+    def __init__(self, b: int, n: int, npoint: int, radius: float, nsample: int, depth: int = 2, device=None,
+                 want_grouped: bool = True):
         if depth < 1:
             raise ValueError("SetAbstractionPipeline expects depth >= 1")
-        self.slots = [SetAbstractionHost(b, n, npoint, radius, nsample, device=device) for _ in range(int(depth))]
+        self.slots = [SetAbstractionHost(b, n, npoint, radius, nsample, device=device, want_grouped=want_grouped)
+                      for _ in range(int(depth))]
         self.device = self.slots[0].device
         self.streams = [torch.cuda.Stream(self.device) for _ in self.slots]
         self.done = [torch.cuda.Event() for _ in self.slots]
@@ -140,4 +152,5 @@ class SetAbstractionPipeline:
         i = self._inflight.popleft()
         self.done[i].synchronize()
         s = self.slots[i]
-        return s.h_new_xyz.numpy(), s.h_idx.numpy(), s.h_pts_cnt.numpy(), s.h_grouped_xyz.numpy()
+        return (s.h_new_xyz.numpy(), s.h_idx.numpy(), s.h_pts_cnt.numpy(),
+                s.h_grouped_xyz.numpy() if s.h_grouped_xyz is not None else None)

@@ -23,6 +23,7 @@ from . import _lib
 from ._tensor import on_device, ptr, require_cuda, same_device, stream_ptr
 from .tf_grouping import group_point, knn_point, query_ball_point
 from .tf_interpolate import three_interpolate, three_nn, three_nn_interpolate
+from .sa_layer import sample_group
 from .tf_sampling import farthest_point_sample, farthest_point_sample_and_gather, gather_point
 
 
@@ -89,31 +90,42 @@ def group_and_concat(xyz, new_xyz, points, idx, xyz_first: bool = True):
 
 
 def sample_and_group(npoint, radius, nsample, xyz, points, knn=False, use_xyz=True, fused=True):
-    '''
-    Input:
-        npoint: int32
-        radius: float32
-        nsample: int32
-        xyz: (batch_size, ndataset, 3) tensor
-        points: (batch_size, ndataset, channel) tensor, if None will just use xyz as points
-        knn: bool, if True use kNN instead of radius search
-        use_xyz: bool, if True concat XYZ with local point features, otherwise just use point features
-    Output:
-        new_xyz: (batch_size, npoint, 3) tensor
-        new_points: (batch_size, npoint, nsample, 3+channel) tensor
-        idx: (batch_size, npoint, nsample) tensor, indices of local points as in ndataset points
-        grouped_xyz: (batch_size, npoint, nsample, 3) tensor, normalized point XYZs
-            (subtracted by seed point XYZ) in local regions
-    Reference: utils/pointnet_util.py:22-56.
-    '''
-    if fused and not xyz.requires_grad:
+    """Sampling + grouping half of a set-abstraction layer (same positional arguments and return
+    tuple as the reference's sample_and_group, utils/pointnet_util.py:22-56).
+
+    Args:
+        npoint, radius, nsample: centroids to sample, ball radius, neighbours kept per centroid.
+        xyz (b, n, 3) float32; points (b, n, c) float32 or None (then the grouped xyz are the features).
+        knn: k-nearest-neighbour grouping instead of the ball query; use_xyz: keep the centred xyz
+        in front of the grouped features.
+    Returns:
+        new_xyz (b, npoint, 3), new_points (b, npoint, nsample, 3 + c) [c alone when use_xyz is False],
+        idx (b, npoint, nsample) int32 into the n input points, grouped_xyz (b, npoint, nsample, 3)
+        centred on new_xyz.
+
+    ``fused=True`` uses the overlapped sampling+grouping layer (sa_layer.sample_group) and the
+    single-pass concat kernel; ``fused=False`` issues the reference's op sequence one by one.  Both
+    return identical values.
+    """
+    no_grad_xyz = not xyz.requires_grad
+    if fused and no_grad_xyz and not knn:
+        # one call: FPS + gather + ball query (+ centred grouped xyz when they are the whole output)
+        need_g = points is None or not use_xyz
+        _, new_xyz, idx, _, grouped_xyz = sample_group(npoint, radius, nsample, xyz, center=True, want_grouped=need_g)
+        if points is None:
+            return new_xyz, grouped_xyz, idx, grouped_xyz
+        if not use_xyz:
+            return new_xyz, group_point(points, idx), idx, grouped_xyz
+        new_points, grouped_xyz = group_and_concat(xyz, new_xyz, points, idx, xyz_first=True)
+        return new_xyz, new_points, idx, grouped_xyz
+    if fused and no_grad_xyz:
         _, new_xyz = farthest_point_sample_and_gather(npoint, xyz)
     else:
-        new_xyz = gather_point(xyz, farthest_point_sample(npoint, xyz))  # (batch_size, npoint, 3)
+        new_xyz = gather_point(xyz, farthest_point_sample(npoint, xyz))
     if knn:
         _, idx = knn_point(nsample, xyz, new_xyz)
     else:
-        idx, pts_cnt = query_ball_point(radius, nsample, xyz, new_xyz)
+        idx, _ = query_ball_point(radius, nsample, xyz, new_xyz)
     if fused:
         feats = points if (points is not None and use_xyz) else None
         if points is not None and not use_xyz:
@@ -121,44 +133,30 @@ def sample_and_group(npoint, radius, nsample, xyz, points, knn=False, use_xyz=Tr
             return new_xyz, group_point(points, idx), idx, grouped_xyz
         new_points, grouped_xyz = group_and_concat(xyz, new_xyz, feats, idx, xyz_first=True)
         return new_xyz, new_points, idx, grouped_xyz
-    grouped_xyz = group_point(xyz, idx)  # (batch_size, npoint, nsample, 3)
-    grouped_xyz = grouped_xyz - new_xyz.unsqueeze(2)  # translation normalization (tile+sub, :46)
-    if points is not None:
-        grouped_points = group_point(points, idx)  # (batch_size, npoint, nsample, channel)
-        if use_xyz:
-            new_points = torch.cat([grouped_xyz, grouped_points], dim=-1)  # (:50) xyz first
-        else:
-            new_points = grouped_points
-    else:
+    # the reference's sequence, op by op (:44-54)
+    grouped_xyz = group_point(xyz, idx) - new_xyz.unsqueeze(2)
+    if points is None:
         new_points = grouped_xyz
+    else:
+        grouped_points = group_point(points, idx)
+        new_points = torch.cat([grouped_xyz, grouped_points], dim=-1) if use_xyz else grouped_points
     return new_xyz, new_points, idx, grouped_xyz
 
 
 def sample_and_group_all(xyz, points, use_xyz=True):
-    '''
-    Inputs:
-        xyz: (batch_size, ndataset, 3) tensor
-        points: (batch_size, ndataset, channel) tensor, if None will just use xyz as points
-        use_xyz: bool, if True concat XYZ with local point features, otherwise just use point features
-    Outputs:
-        new_xyz: (batch_size, 1, 3) as (0,0,0)
-        new_points: (batch_size, 1, ndataset, 3+channel) tensor
-    Note:
-        Equivalent to sample_and_group with npoint=1, radius=inf, use (0,0,0) as the centroid
-    Reference: utils/pointnet_util.py:59-84 (no kernels: zeros, arange, reshape, concat).
-    '''
-    batch_size, nsample = xyz.shape[0], xyz.shape[1]
-    new_xyz = torch.zeros((batch_size, 1, 3), dtype=torch.float32, device=xyz.device)
-    idx = torch.arange(nsample, dtype=torch.int32, device=xyz.device).reshape(1, 1, nsample).repeat(batch_size, 1, 1)
-    grouped_xyz = xyz.reshape(batch_size, 1, nsample, 3)
-    if points is not None:
-        if use_xyz:
-            new_points = torch.cat([xyz, points], dim=2)
-        else:
-            new_points = points
-        new_points = new_points.unsqueeze(1)
-    else:
-        new_points = grouped_xyz
+    """The group_all variant (reference utils/pointnet_util.py:59-84): one group holding every point,
+    centred on the origin — no sampling, no search, no kernel.
+
+    Returns new_xyz (b, 1, 3) zeros, new_points (b, 1, n, 3 + c) (xyz first; c alone when use_xyz is
+    False; the xyz themselves when points is None), idx (b, 1, n) = arange, grouped_xyz (b, 1, n, 3).
+    """
+    b, n = xyz.shape[0], xyz.shape[1]
+    new_xyz = xyz.new_zeros((b, 1, 3))
+    idx = torch.arange(n, dtype=torch.int32, device=xyz.device).view(1, 1, n).expand(b, 1, n).contiguous()
+    grouped_xyz = xyz.view(b, 1, n, 3)
+    if points is None:
+        return new_xyz, grouped_xyz, idx, grouped_xyz
+    new_points = (torch.cat([xyz, points], dim=2) if use_xyz else points).unsqueeze(1)
     return new_xyz, new_points, idx, grouped_xyz
 
 

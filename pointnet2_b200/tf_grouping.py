@@ -149,14 +149,32 @@ def knn_point(k: int, xyz1: torch.Tensor, xyz2: torch.Tensor):
     Output:
         val: (batch_size, npoint, k) float32 array, L2 distances
         idx: (batch_size, npoint, k) int32 array, indices to input points
-    Reference: tf_grouping.py:48-73 — the same composite: pairwise squared distances
-    sum((xyz1 - xyz2)**2, -1) as an (b,m,n) matrix, select_top_k, slice the first k columns.
+    Reference: tf_grouping.py:48-73.  The reference builds the (b,m,n) matrix of squared distances
+    sum((xyz1 - xyz2)**2, -1) and runs select_top_k on it; for 3-D points and k <= 128 this runs one
+    tiled top-k kernel instead (pn2_knn_point: no matrix), whose val / idx equal the first k columns
+    of that composite bit for bit, ties included.  Other shapes take the composite itself.
     """
+    k = int(k)
+    if k <= 0:
+        raise ValueError("knn_point expects positive k")
     xyz1 = require_cuda(xyz1, "xyz1", torch.float32)
     xyz2 = require_cuda(xyz2, "xyz2", torch.float32)
     same_device(xyz1, xyz2)
     if xyz1.dim() != 3 or xyz2.dim() != 3 or xyz1.shape[0] != xyz2.shape[0] or xyz1.shape[2] != xyz2.shape[2]:
         raise ValueError("knn_point expects (b,n,c) xyz1 and (b,m,c) xyz2")
+    b, n, c = xyz1.shape
+    m = xyz2.shape[1]
+    if k > n:
+        raise ValueError(f"knn_point expects k <= ndataset (the reference slices k columns of an n-column matrix), got k={k}, n={n}")
+    if c == 3 and k <= 128:
+        val = torch.empty((b, m, k), dtype=torch.float32, device=xyz1.device)
+        idx = torch.empty((b, m, k), dtype=torch.int32, device=xyz1.device)
+        if b * m:
+            with on_device(xyz1):
+                rc = _lib.load().pn2_knn_point(b, n, m, k, ptr(xyz1.detach()), ptr(xyz2.detach()), ptr(val), ptr(idx),
+                                               stream_ptr(xyz1.device))
+            _lib.check(rc, "pn2_knn_point")
+        return val, idx
     diff = xyz1.unsqueeze(1) - xyz2.unsqueeze(2)  # (b,m,n,c): tile(xyz1) - tile(xyz2), tf_grouping.py:64-66
     dist = (diff * diff).sum(-1)
     outi, out = select_top_k(k, dist)

@@ -76,8 +76,9 @@ def farthest_point_sample(npoint: int, inp: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     with on_device(inp):
         # clouds beyond the cluster kernels' capacity (n > 262144) need the reference's own
-        # (32, n) float scratch (tf_sampling.cpp:115)
-        temp = torch.empty((32, n), dtype=torch.float32, device=inp.device) if n > 262144 else None
+        # (32, n) float scratch (tf_sampling.cpp:115); the library says how much
+        tb = int(lib.pn2_fps_scratch_bytes(b, n))
+        temp = torch.empty(tb, dtype=torch.uint8, device=inp.device) if tb else None
         rc = lib.pn2_fps(b, n, npoint, ptr(inp), ptr(temp), ptr(out), stream_ptr(inp.device))
     _lib.check(rc, "pn2_fps")
     return out
@@ -93,15 +94,17 @@ def farthest_point_sample_and_gather(npoint: int, inp: torch.Tensor):
     inp = require_cuda(inp, "inp", torch.float32)
     _check_xyz(inp, "inp", "FarthestPointSample")
     b, n, _ = inp.shape
-    if n > 262144:
-        idx = farthest_point_sample(npoint, inp)
-        return idx, gather_point(inp.detach(), idx)
+    if n <= 0:
+        raise ValueError("FarthestPointSample expects at least one point per batch entry")
     idx = torch.empty((b, npoint), dtype=torch.int32, device=inp.device)
     new_xyz = torch.empty((b, npoint, 3), dtype=torch.float32, device=inp.device)
     if b == 0:
         return idx, new_xyz
+    lib = _lib.load()
     with on_device(inp):
-        rc = _lib.load().pn2_fps_gather(b, n, npoint, ptr(inp), ptr(idx), ptr(new_xyz), stream_ptr(inp.device))
+        tb = int(lib.pn2_fps_scratch_bytes(b, n))
+        temp = torch.empty(tb, dtype=torch.uint8, device=inp.device) if tb else None
+        rc = lib.pn2_fps_gather(b, n, npoint, ptr(inp), ptr(temp), ptr(idx), ptr(new_xyz), stream_ptr(inp.device))
     _lib.check(rc, "pn2_fps_gather")
     return idx, new_xyz
 

@@ -29,7 +29,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/pn2_api.h but not exported"
     assert set(syms) == set(_lib.EXPORTED_SYMBOLS), "ctypes signature table and header disagree"
-    assert lib.pn2_api_version() == 1
+    assert lib.pn2_api_version() == 2
     assert os.path.dirname(_lib.lib_path()) == os.path.join(ROOT, "pointnet2_b200")  # in-tree
 
 

@@ -44,25 +44,20 @@ def test_fps_matches_oracle(dev, gen, b, n, m):
     np.testing.assert_array_equal(got, O.oracle_fps(m, xyz))
 
 
-@pytest.mark.parametrize("cfg", [(512, 2, 2), (512, 1, 4), (512, 4, 2), (512, 8, 4), (1024, 2, 2), (512, 2, 8),
-                                 (512, 1, 16), (512, 16, 2), (512, 32, 2), (1024, 4, 1), (512, 8, 1), (512, 16, 1),
-                                 (256, 2, 2), (256, 8, 4), (256, 32, 2), (128, 4, 4), (128, 16, 8), (128, 32, 16), (256, 16, 16),
-                                 (128, 2, 1), (128, 8, 1), (128, 32, 1), (256, 2, 1), (256, 4, 1), (256, 16, 1), (256, 32, 1),
-                                 (128, 4, -3), (128, 8, -3), (128, 16, -3), (128, 32, -3), (256, 4, -3), (256, 8, -3), (256, 16, -3),
-                                 (256, 32, -3), (512, 4, -3), (512, 8, -3), (512, 16, -3),
-                                 (128, 2, -2), (128, 4, -2), (128, 8, -2), (128, 16, -2), (128, 32, -2), (256, 2, -2), (256, 4, -2),
-                                 (256, 8, -2), (256, 16, -2), (256, 32, -2), (512, 2, -2), (512, 4, -2), (512, 8, -2), (512, 16, -2),
-                                 (128, 1, -1), (128, 2, -1), (128, 4, -1), (128, 8, -1), (128, 16, -1), (128, 32, -1),
-                                 (256, 1, -1), (256, 2, -1), (256, 4, -1), (256, 8, -1), (256, 16, -1), (256, 32, -1),
-                                 (512, 1, -1), (512, 2, -1), (512, 4, -1), (512, 8, -1), (512, 16, -1),
-                                 (1024, 1, -1), (1024, 2, -1), (1024, 4, -1), (1024, 8, -1)])
+FPS_VARIANTS = [(512, 2, 2), (512, 1, 4), (512, 4, 2), (512, 8, 4), (1024, 2, 2), (512, 2, 8),
+                (512, 1, 16), (512, 16, 2), (512, 32, 2), (1024, 4, 1), (512, 8, 1), (512, 16, 1),
+                (256, 2, 2), (256, 8, 4), (256, 32, 2), (128, 4, 4), (128, 16, 8), (128, 32, 16), (256, 16, 16),
+                (128, 2, 1), (128, 8, 1), (128, 32, 1), (256, 2, 1), (256, 4, 1), (256, 16, 1), (256, 32, 1)]
+
+
+@pytest.mark.parametrize("cfg", FPS_VARIANTS)
 @pytest.mark.parametrize("gen", ["U", "D", "S"])
 def test_fps_every_kernel_variant_matches_oracle(dev, cfg, gen):
     """Force each (threads, points/thread, cluster) kernel variant — register-resident single CTA
-    (cluster 1), bucketed single CTA (cluster -1), the DSMEM cluster exchange (cluster >= 2) and
-    the shared-memory-coordinate variant — on a cloud that fits it."""
+    (cluster 1), the DSMEM cluster exchange carrying key + coordinates (cluster >= 2) and the variant
+    that streams half of the coordinates from shared memory (512 x 32) — on a cloud that fits it."""
     threads, ppt, cluster = cfg
-    cap = threads * ppt * (cluster if cluster > 0 else 1)
+    cap = threads * ppt * cluster
     n = min(cap, 6000) - 3
     xyz = W.DISTRIBUTIONS[gen](2, n, 32)
     lib = _lib.load()
@@ -72,6 +67,27 @@ def test_fps_every_kernel_variant_matches_oracle(dev, cfg, gen):
     finally:
         lib.pn2_set_fps_config(0, 0, 0)
     np.testing.assert_array_equal(got, O.oracle_fps(150, xyz))
+
+
+@pytest.mark.parametrize("cfg,n", [((512, 32, 16), 262144), ((512, 32, 16), 262143), ((512, 32, 2), 32768), ((256, 32, 16), 131072),
+                                   ((128, 32, 16), 65536), ((256, 16, 16), 65536), ((256, 32, 8), 65536)])
+def test_fps_cluster_variants_at_full_capacity(dev, cfg, n):
+    """The cluster kernels with EVERY per-thread slot occupied (the 512x32 variant had only
+    been forced on n <= 5997, i.e. 31 of its 32 points per thread were padding).  Duplicate-heavy
+    clouds so that the tie-break order crosses CTAs; checked against the oracle."""
+    threads, ppt, cluster = cfg
+    m = 96
+    lib = _lib.load()
+    for gen, b in (("U", 1), ("D", 2)):
+        xyz = W.DISTRIBUTIONS[gen](b, n, 33)
+        lib.pn2_set_fps_config(threads, ppt, cluster)
+        try:
+            fi, fx = farthest_point_sample_and_gather(m, T(xyz, dev))
+        finally:
+            lib.pn2_set_fps_config(0, 0, 0)
+        want = O.oracle_fps(m, xyz)
+        np.testing.assert_array_equal(N(fi), want)
+        np.testing.assert_array_equal(N(fx), O.oracle_gather_point(xyz, want))
 
 
 def test_fps_cfg1_plumbing_matches_cpu_restatement(dev):

@@ -1,0 +1,36 @@
+#!/bin/bash
+# One gpurun call = several stages; every stage writes under gpurun_out/ and never aborts the rest.
+#   gpurun --timeout 1500 -- 'bash tools/gpu_r2.sh newtests alltests bench sweep'
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.max.sm,clocks.sm --format=csv,noheader > gpurun_out/gpu.txt 2>&1
+for stage in "$@"; do
+  echo "=== stage $stage ($(date +%T))"
+  case "$stage" in
+    newtests)
+      timeout 600 python -m pytest tests/test_sa_fused_gpu.py tests/test_full_size_parity_gpu.py -x -q -m gpu 2>&1 | tail -40 | tee gpurun_out/newtests.log ;;
+    alltests)
+      timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -40 | tee gpurun_out/alltests.log ;;
+    smoke)
+      timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/smoke.log ;;
+    bench)
+      timeout 900 python bench.py --steps 50 --warmup 5 > gpurun_out/bench_r2.json 2> gpurun_out/bench_r2.err; tail -c 600 gpurun_out/bench_r2.err; head -c 1500 gpurun_out/bench_r2.json ;;
+    benchref)
+      timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_ref_r2.json 2> gpurun_out/bench_ref_r2.err; head -c 600 gpurun_out/bench_ref_r2.json ;;
+    report)
+      timeout 1200 python bench.py --report gpurun_out/report_r2.json > gpurun_out/report_r2.log 2>&1; tail -3 gpurun_out/report_r2.log ;;
+    sweep)
+      PN2_SWEEP_LARGE=1 timeout 900 python bench.py --fps-sweep > gpurun_out/fps_sweep_large.log 2>&1; cp gpurun_out/fps_sweep.json gpurun_out/fps_sweep_large_r2.json 2>/dev/null; tail -3 gpurun_out/fps_sweep_large.log ;;
+    sweep262)
+      timeout 600 python tools/fps_large_bench.py > gpurun_out/fps_262k.log 2>&1; tail -20 gpurun_out/fps_262k.log ;;
+    launches)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-configs > gpurun_out/ncu_bench.log 2>&1; tail -2 gpurun_out/ncu_bench.log | head -c 300 ;;
+    ncufull)
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:'fps_cta_kernel|ball_group_kernel' -s 4 -c 4 -o gpurun_out/r2_prof_layer python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-configs > gpurun_out/ncu_full.log 2>&1; tail -2 gpurun_out/ncu_full.log | head -c 300 ;;
+    sanitize)
+      timeout 900 compute-sanitizer --tool memcheck python tools/sanitize_smoke.py > gpurun_out/sanitize_mem.log 2>&1; tail -3 gpurun_out/sanitize_mem.log
+      timeout 900 compute-sanitizer --tool racecheck python tools/sanitize_smoke.py > gpurun_out/sanitize_race.log 2>&1; tail -3 gpurun_out/sanitize_race.log ;;
+    *) echo "unknown stage $stage" ;;
+  esac
+done
+echo "=== done ($(date +%T))"

@@ -14,7 +14,7 @@ nx, npts, idx, gx = sample_and_group(64, 0.3, 16, xyz, f)
 npts.sum().backward()
 up = pointnet_fp_module(xyz, nx, None, npts.max(dim=2).values.detach())
 _ = pointnet_sa_module_msg(xyz, f.detach(), 32, [0.2, 0.4], [8, 16])
-for cfg in [(128, 32, 1), (256, 16, -1), (128, 32, -3), (256, 16, -2), (128, 8, 4), (512, 32, 2)]:
+for cfg in [(128, 32, 1), (128, 8, 4), (256, 8, 2), (512, 32, 2)]:
     lib.pn2_set_fps_config(*cfg)
     farthest_point_sample(40, xyz)
 lib.pn2_set_fps_config(0, 0, 0)
@@ -23,5 +23,12 @@ q = u[:, :200].contiguous()
 query_ball_point(0.08, 16, u, q)          # grid path
 lib.pn2_set_bq_mode(1); query_ball_point(0.08, 16, u, q); lib.pn2_set_bq_mode(0)
 select_top_k(3, torch.rand(2, 5, 40, device=dev))
+from pointnet2_b200.sa_layer import ball_group, sample_group
+from pointnet2_b200.tf_grouping import knn_point
+sample_group(128, 0.08, 16, u)                      # overlapped layer, grid mode
+sample_group(64, 0.3, 16, xyz, center=False)        # overlapped layer, ordered-scan mode (duplicate-heavy cloud)
+ball_group(0.08, 16, u, q)
+knn_point(8, u, q)
+knn_point(40, xyz, nx)
 torch.cuda.synchronize()
 print("sanitize smoke done")
