@@ -89,16 +89,10 @@ def fps_sweep(out_path=None):
     if os.environ.get("PN2_SWEEP_SMALL"):
         cases = [c for c in cases if c[1] <= 8192]
     if os.environ.get("PN2_SWEEP_LARGE"):
-        cases = [(16, 8192, 1024), (2, 8192, 1024), (8, 16384, 4096), (1, 16384, 4096), (8, 65536, 2048), (1, 65536, 2048)]
+        cases = [(32, 4096, 1024), (8, 16384, 4096), (1, 16384, 4096), (8, 65536, 2048), (1, 65536, 2048), (8, 131072, 512), (8, 262144, 256), (1, 262144, 256)]
     variants = [(128, 1, 1), (256, 1, 1), (512, 1, 1), (512, 2, 1), (512, 4, 1), (512, 8, 1), (512, 16, 1), (1024, 1, 1),
                 (1024, 2, 1), (1024, 4, 1), (1024, 8, 1)]
     variants += [(128, p, 1) for p in (2, 4, 8, 16, 32)] + [(256, p, 1) for p in (2, 4, 8, 16, 32)]
-    for t, ps in ((128, (1, 2, 4, 8, 16, 32)), (256, (1, 2, 4, 8, 16, 32)), (512, (1, 2, 4, 8, 16)), (1024, (1, 2, 4, 8))):
-        variants += [(t, p, -1) for p in ps]
-    for t, ps in ((128, (2, 4, 8, 16, 32)), (256, (2, 4, 8, 16, 32)), (512, (2, 4, 8, 16))):
-        variants += [(t, p, -2) for p in ps]
-    for t, ps in ((128, (4, 8, 16, 32)), (256, (4, 8, 16, 32)), (512, (4, 8, 16))):
-        variants += [(t, p, -3) for p in ps]
     for C in (2, 4, 8, 16):
         for (t, p) in [(512, 1), (512, 2), (512, 4), (512, 8), (512, 16), (512, 32), (1024, 2), (1024, 4), (1024, 8),
                        (256, 2), (256, 4), (256, 8), (256, 16), (256, 32), (128, 4), (128, 8), (128, 16), (128, 32)]:
@@ -111,7 +105,7 @@ def fps_sweep(out_path=None):
         ref = None
         for (t, p, c) in [(0, 0, 0)] + variants:
             cc = c if c > 0 else 1
-            if t and (t * p * cc < n or t * p * cc > (4 if c < 0 else 16) * n or b * cc > 8 * 148):
+            if t and (t * p * cc < n or t * p * cc > 16 * n or b * cc > 8 * 148):
                 continue
             lib.pn2_set_fps_config(t, p, c)
             rc = [0]
@@ -133,15 +127,6 @@ def fps_sweep(out_path=None):
             ok = bool(torch.equal(ref, idx))
             row = dict(b=b, n=n, m=m, cfg=[t, p, c], ms=ms, us_per_iter=1e3 * ms / (m - 1), same_as_default=ok,
                        pairs_per_s=b * (m - 1) * n / (ms * 1e-3))
-            if c < 0 and m * 2 <= 8192:  # separate setup (sort) from the per-step cost: time 2m picks too
-                m2 = 2 * m
-                idx2 = torch.empty((b, m2), dtype=torch.int32, device=dev)
-                nx2 = torch.empty((b, m2, 3), dtype=torch.float32, device=dev)
-                lib.pn2_set_fps_config(t, p, c)
-                ms2 = timeit_batch(torch, lambda: lib.pn2_fps_gather(b, n, m2, xyz.data_ptr(), None, idx2.data_ptr(), nx2.data_ptr(), None))
-                lib.pn2_set_fps_config(0, 0, 0)
-                row["us_per_iter_marginal"] = 1e3 * (ms2 - ms) / m
-                row["setup_ms"] = ms - (ms2 - ms) * (m - 1) / m
             rows.append(row)
             print(json.dumps(row), flush=True)
     if out_path:

@@ -142,6 +142,16 @@ int pn2_three_interpolate(int b, int m, int c, int n, const float* points, const
 int pn2_three_interpolate_grad(int b, int n, int c, int m, const float* grad_out, const int* idx,
                                const float* weight, float* grad_points, void* stream);
 
+/* The same gradient WITHOUT atomics: an inverse index (which unknown points reference each known point) is
+ * built in `workspace` (pn2_three_interpolate_grad_det_workspace_bytes(b,n,m) bytes), then one warp per
+ * known point adds its contributions in ascending (j, t) order — the order threeinterpolate_grad_cpu adds
+ * them, every product and sum rounded on its own — so the result is run-to-run deterministic AND bit-identical
+ * to the reference's CPU function.  grad_points (b,m,c) is overwritten: no zero-fill needed. */
+size_t pn2_three_interpolate_grad_det_workspace_bytes(int b, int n, int m);
+int pn2_three_interpolate_grad_det(int b, int n, int c, int m, const float* grad_out, const int* idx,
+                                   const float* weight, float* grad_points, void* workspace,
+                                   size_t workspace_bytes, void* stream);
+
 /* ---- fused callers' glue (utils/pointnet_util.py) ------------------------------------------ */
 
 /* sample_and_group's grouping tail, utils/pointnet_util.py:45-54 (SSG) and :179-186 (MSG), in
@@ -160,6 +170,12 @@ int pn2_group_concat(int b, int n, int c, int m, int nsample, const float* xyz, 
 int pn2_three_nn_interpolate(int b, int n, int m, int c, const float* xyz1, const float* xyz2,
                              const float* points2, float* out, float* dist, int* idx, float* weight,
                              void* stream);
+
+/* The whole front end of pointnet_fp_module, utils/pointnet_util.py:211-219, in one pass: the above plus the
+ * concat with the dense level's own features: out (b,n,c2+c1) = [interpolated points2 (c2) | points1 (c1)].
+ * points1 (b,n,c1) may be NULL with c1 = 0.  Values equal three_nn -> weights -> three_interpolate -> concat. */
+int pn2_fp_interpolate_concat(int b, int n, int m, int c2, int c1, const float* xyz1, const float* xyz2,
+                              const float* points1, const float* points2, float* out, void* stream);
 
 /* ---- the sampling+grouping half of a set-abstraction layer, device-resident ------------------ */
 
@@ -222,6 +238,10 @@ void pn2_set_fps_config(int threads, int points_per_thread, int cluster);
  * cluster size (1 = one CTA per cloud, >= 2 = thread-block cluster per cloud, 0 = global-scratch
  * fallback) */
 int pn2_fps_plan(int b, int n, int* threads, int* points_per_thread, int* cluster);
+/* how many thread-block clusters of the FPS cluster kernel (threads, points/thread, cluster size) the
+ * current device can hold at once (cudaOccupancyMaxActiveClusters); 0 = no such kernel / cannot launch.
+ * The planner uses it to keep every cloud's cluster co-resident. */
+int pn2_fps_cluster_capacity(int threads, int points_per_thread, int cluster);
 /* tuning override: lanes cooperating on one ball query (1,2,4,..,32); 0 restores the heuristic */
 void pn2_set_bq_group(int lanes_per_query);
 /* tuning override for pn2_query_ball_point_ws: 0 = automatic, 1 = brute force only, 2 = same as 0 */

@@ -33,6 +33,9 @@ _SIGNATURES = {
     "pn2_three_nn": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "pn2_three_interpolate": (c_int, [c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
     "pn2_three_interpolate_grad": (c_int, [c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P]),
+    "pn2_three_interpolate_grad_det_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "pn2_three_interpolate_grad_det": (c_int, [c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "pn2_fp_interpolate_concat": (c_int, [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "pn2_group_concat": (c_int, [c_int, c_int, c_int, c_int, c_int, _P, _P, _P, _P, c_int, _P, _P, _P]),
     "pn2_three_nn_interpolate": (c_int, [c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     "pn2_ball_group_fits": (c_int, [c_int]),
@@ -46,6 +49,7 @@ _SIGNATURES = {
     "pn2_launch_count": (c_ulonglong, []),
     "pn2_ball_threshold": (c_float, [c_float]),
     "pn2_fps_plan": (c_int, [c_int, c_int, _P, _P, _P]),
+    "pn2_fps_cluster_capacity": (c_int, [c_int, c_int, c_int]),
     "pn2_set_fps_config": (None, [c_int, c_int, c_int]),
     "pn2_set_bq_group": (None, [c_int]),
     "pn2_set_bq_mode": (None, [c_int]),

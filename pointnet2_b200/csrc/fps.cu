@@ -528,6 +528,43 @@ static int launch_cluster(int C, int b, int n, int m, const float* inp, int* out
     return (int)cudaGetLastError();
 }
 
+// How many clusters of this kernel the device can hold at once (cudaOccupancyMaxActiveClusters): the
+// planner must keep every cloud's cluster co-resident — a cluster that has to wait for a second wave
+// doubles the time of the whole call (measured: 8 clouds x 16-CTA clusters with 196 KB of shared
+// memory per CTA run as two waves on B200, profiles/r2_fps_cluster_occupancy.txt).
+template <int P, int T, int PR>
+static int cluster_capacity(int C) {
+    static std::atomic<int> cache[5][64];  // [log2 C][device]; 0 = not asked yet
+    int log2c = 0;
+    while ((1 << log2c) < C) ++log2c;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || log2c > 4) return 0;
+    const int hit = cache[log2c][dev].load(std::memory_order_relaxed);
+    if (hit) return hit > 0 ? hit : 0;
+    static AttrOnce once;
+    auto kern = fps_cluster_kernel<P, T, PR>;
+    const size_t dyn = (size_t)3 * P * T * sizeof(float);
+    if (dyn > 200 * 1024 || ensure_attrs(once, kern, dyn, true) != cudaSuccess) return 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)C * 148u, 1, 1);
+    cfg.blockDim = dim3(T, 1, 1);
+    cfg.dynamicSmemBytes = dyn;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int num = 0;
+    if (cudaOccupancyMaxActiveClusters(&num, kern, &cfg) != cudaSuccess) {
+        (void)cudaGetLastError();
+        num = 0;
+    }
+    cache[log2c][dev].store(num > 0 ? num : -1, std::memory_order_relaxed);
+    return num;
+}
+
 struct FpsPlan {
     int threads, ppt, cluster;  // cluster == 0: global-scratch fallback; 1: single CTA; >= 2: thread-block cluster
     int pr;                     // cluster kernels: points per thread with register-resident coordinates (== ppt: all)
@@ -538,6 +575,8 @@ static int pow2_floor(int v) {
     while (p * 2 <= v) p *= 2;
     return p;
 }
+
+int fps_cluster_capacity(int threads, int ppt, int cluster);
 
 static FpsPlan plan_fps(int b, int n) {
     std::call_once(g_fps_env_once, [] {  // PN2_FPS_CFG="threads,points_per_thread,cluster": profiling/tuning override
@@ -589,13 +628,19 @@ static FpsPlan plan_fps(int b, int n) {
         }
         return false;
     };
+    FpsPlan first{0, 0, 0, 0};
     for (int C = cmax; C >= 2; C /= 2) {
         const long long per = ((long long)n + C - 1) / C;  // points per CTA
         if (per <= 1024 && C > 2) continue;                // too thin: fewer, fatter CTAs
         FpsPlan p;
-        if (pick(per, C, p)) return p;
-        break;
+        if (!pick(per, C, p)) break;                       // smaller clusters cannot hold the cloud either
+        if (first.cluster == 0) first = p;
+        // every cloud's cluster must be resident at once: a cluster left for a second wave doubles the call
+        // (0 = capacity unknown, e.g. no device yet: take the plan)
+        const int cap = fps_cluster_capacity(p.threads, p.ppt, p.cluster);
+        if (cap == 0 || cap >= b) return p;
     }
+    if (first.cluster) return first;  // nothing fits at once: widest cluster, several waves
     FpsPlan p;
     // widest cluster regardless of co-residency
     if (pick(((long long)n + 15) / 16, 16, p)) return p;
@@ -679,9 +724,38 @@ int fps_dispatch(int b, int n, int m, const float* inp, float* temp, int* out, f
     return finish_launch();
 }
 
+#define PN2_CAP_CLU(PP, TT, PRR) \
+    if (ppt == PP && threads == TT) return cluster_capacity<PP, TT, PRR>(cluster);
+int fps_cluster_capacity(int threads, int ppt, int cluster) {
+    if (cluster < 2 || cluster > 16 || (cluster & (cluster - 1))) return 0;
+    PN2_CAP_CLU(4, 128, 4)
+    PN2_CAP_CLU(8, 128, 8)
+    PN2_CAP_CLU(16, 128, 16)
+    PN2_CAP_CLU(32, 128, 32)
+    PN2_CAP_CLU(2, 256, 2)
+    PN2_CAP_CLU(4, 256, 4)
+    PN2_CAP_CLU(8, 256, 8)
+    PN2_CAP_CLU(16, 256, 16)
+    PN2_CAP_CLU(32, 256, 32)
+    PN2_CAP_CLU(1, 512, 1)
+    PN2_CAP_CLU(2, 512, 2)
+    PN2_CAP_CLU(4, 512, 4)
+    PN2_CAP_CLU(8, 512, 8)
+    PN2_CAP_CLU(16, 512, 16)
+    PN2_CAP_CLU(32, 512, 16)
+    PN2_CAP_CLU(2, 1024, 2)
+    PN2_CAP_CLU(4, 1024, 4)
+    PN2_CAP_CLU(8, 1024, 8)
+    return 0;
+}
+
 }  // namespace pn2
 
 extern "C" {
+
+int pn2_fps_cluster_capacity(int threads, int points_per_thread, int cluster) {
+    return pn2::fps_cluster_capacity(threads, points_per_thread, cluster);
+}
 
 int pn2_fps(int b, int n, int m, const float* inp, float* temp, int* out, void* stream) {
     return pn2::fps_dispatch(b, n, m, inp, temp, out, nullptr, 0, pn2::as_stream(stream));

@@ -163,6 +163,82 @@ group_rows_kernel(int n, int c, int nsample, unsigned rows_per_cloud, const floa
     }
 }
 
+// ---- the fused sample_and_group tail with features (c > 0): one warp per block of 32 output rows ----
+// Output rows are w = 3 + c floats wide — 67, 131, 259, 323 in the reference's networks — so they are
+// not 16-byte aligned, but CONSECUTIVE ROWS ARE CONTIGUOUS: a block of 32 rows is one run of 32*w
+// floats.  The warp reads its 32 row indices (and computes the 32 centred xyz triples, one row per
+// lane) up front, then walks the run flat: lane l handles floats l, l+32, ... of the run, finds its
+// (row, channel) with one multiply-high, fetches the row's index by shuffle and copies one word —
+// every store instruction covers 128 consecutive bytes whatever w is, there are no partial chunks at
+// row ends, and UNR independent gathers are in flight per lane (round 1's row-at-a-time kernel had one
+// index -> gather -> store chain per warp and reached 17 % of the HBM peak at w = 67).  The 3 xyz words of
+// each row are written by that row's lane (they are 3 of w words: 32 scattered words per store).
+template <int UNR>
+__global__ void __launch_bounds__(kCopyThreads)
+group_concat_flat_kernel(int n, int c, int nsample, unsigned rows_per_cloud, const float* __restrict__ xyz,
+                         const float* __restrict__ new_xyz, const float* __restrict__ points, const int* __restrict__ idx,
+                         int xyz_lo, int feat_lo, float* __restrict__ out, float* __restrict__ grouped_xyz, unsigned magic) {
+    const int lane = threadIdx.x & 31;
+    const unsigned cloud = blockIdx.y;
+    const unsigned w = (unsigned)c + 3u;
+    const unsigned warps = (gridDim.x * kCopyThreads) >> 5;
+    const unsigned warp = (blockIdx.x * kCopyThreads + threadIdx.x) >> 5;
+    const size_t cloud_row0 = (size_t)cloud * rows_per_cloud;
+    const unsigned m = rows_per_cloud / (unsigned)nsample;
+    const int* __restrict__ cidx = idx + cloud_row0;
+    const float* __restrict__ cpts = points + (size_t)cloud * n * c;
+    const float* __restrict__ cxyz = xyz + (size_t)cloud * n * 3;
+    const float* __restrict__ cctr = new_xyz + (size_t)cloud * m * 3;
+    for (unsigned r0 = warp * 32u; r0 < rows_per_cloud; r0 += warps * 32u) {
+        const unsigned nrows = min(32u, rows_per_cloud - r0);
+        const unsigned r = r0 + lane;
+        int a = 0;
+        float vx = 0.f, vy = 0.f, vz = 0.f;
+        if (lane < nrows) {
+            a = __ldg(cidx + r);
+            const float* __restrict__ s = cxyz + (size_t)a * 3;
+            const float* __restrict__ q = cctr + (size_t)(r / (unsigned)nsample) * 3;
+            vx = __fsub_rn(__ldg(s), __ldg(q));
+            vy = __fsub_rn(__ldg(s + 1), __ldg(q + 1));
+            vz = __fsub_rn(__ldg(s + 2), __ldg(q + 2));
+        }
+        float* __restrict__ obase = out + (cloud_row0 + r0) * w;
+        if (lane < nrows) {  // this row's centred xyz
+            float* __restrict__ d = obase + (size_t)lane * w + xyz_lo;
+            __stcs(d, vx);
+            __stcs(d + 1, vy);
+            __stcs(d + 2, vz);
+        }
+        if (grouped_xyz) {  // the 32 triples are one run of 96 floats: transpose through shuffles, 3 coalesced stores
+            float* __restrict__ g = grouped_xyz + (cloud_row0 + r0) * 3;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const unsigned t = (unsigned)lane + 32u * j, row = t / 3u, comp = t - 3u * row;
+                const float x = __shfl_sync(kFullMask, vx, row), y = __shfl_sync(kFullMask, vy, row), z = __shfl_sync(kFullMask, vz, row);
+                if (row < nrows) __stcs(g + t, comp == 0 ? x : (comp == 1 ? y : z));
+            }
+        }
+        // the feature words: flat walk over the nrows*w floats of this block
+        const unsigned total = nrows * w;
+        for (unsigned f0 = 0; f0 < total; f0 += 32u * UNR) {
+            float v[UNR];
+            bool ok[UNR];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const unsigned f = f0 + 32u * u + lane;
+                const unsigned row = __umulhi(f, magic);       // f / w, exact for f < 32 * w
+                const int e = (int)(f - row * w) - feat_lo;     // channel within the feature part
+                const int ar = __shfl_sync(kFullMask, a, row & 31u);
+                ok[u] = f < total && e >= 0 && e < c;
+                if (ok[u]) v[u] = __ldg(cpts + (size_t)ar * c + e);
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+                if (ok[u]) __stcs(obase + f0 + 32u * u + lane, v[u]);
+        }
+    }
+}
+
 // Narrow rows (w <= 4 floats, e.g. group_point(xyz) and the C=0 sample_and_group tail): one thread
 // per output row — the per-row index/centroid work is the cost, not the copy.
 template <bool HAS_XYZ>
@@ -207,6 +283,18 @@ static int launch_group_rows(int b, int n, int c, int m, int nsample, const floa
         if (gx > cap) gx = cap;
         group_narrow_kernel<HAS_XYZ><<<dim3(gx, b, 1), kCopyThreads, 0, st>>>(n, c, nsample, rpc, xyz, new_xyz, points, idx, out,
                                                                                 grouped_xyz);
+        return finish_launch();
+    }
+    if (HAS_XYZ && c > 0 && w <= 8192) {  // (the multiply-high row lookup is exact for 32*w*w < 2^32)
+        // fused tail with features: flat 32-row blocks (see group_concat_flat_kernel)
+        const unsigned blocks_needed = (rpc + 32u * (kCopyThreads / 32) - 1) / (32u * (kCopyThreads / 32));
+        unsigned gx = blocks_needed;
+        const unsigned cap = (148u * 16u + b - 1) / b;
+        if (gx > cap) gx = cap;
+        if (gx < 1) gx = 1;
+        const unsigned magic = (unsigned)((0x100000000ull + (unsigned)w - 1) / (unsigned)w);  // ceil(2^32 / w)
+        group_concat_flat_kernel<4><<<dim3(gx, b, 1), kCopyThreads, 0, st>>>(n, c, nsample, rpc, xyz, new_xyz, points, idx, xyz_lo, feat_lo,
+                                                                              out, grouped_xyz, magic);
         return finish_launch();
     }
     const int lpr = w <= 4 ? 4 : (w <= 8 ? 8 : (w <= 16 ? 16 : 32));

@@ -166,27 +166,55 @@ __device__ __forceinline__ float interp3(float p1, float p2, float p3, float w1,
 
 constexpr int kItThreads = 256;
 
-template <typename IndexT>
+// One thread per output float4, U outputs in flight per thread: the 6 small loads (3 indices, 3 weights) of
+// all U outputs are issued first, then the 3U 16-byte gathers, then the U streaming stores — round 1's
+// one-output-per-iteration loop had a single index -> gather -> store chain per thread (45 % of the HBM peak
+// at C = 128).
+template <typename IndexT, int U>
 __global__ void __launch_bounds__(kItThreads)
 three_interp_vec4_kernel(int m, int c4, IndexT rows_per_cloud, IndexT total_vec, const float4* __restrict__ points,
                          const int* __restrict__ idx, const float* __restrict__ weight, float4* __restrict__ out) {
     const IndexT stride = (IndexT)gridDim.x * kItThreads;
-    for (IndexT v = (IndexT)blockIdx.x * kItThreads + threadIdx.x; v < total_vec; v += stride) {
-        const IndexT row = v / (IndexT)c4;
-        const int l = (int)(v - row * (IndexT)c4);
-        const IndexT cloud = row / rows_per_cloud;
-        const int i1 = __ldg(idx + (size_t)row * 3 + 0), i2 = __ldg(idx + (size_t)row * 3 + 1),
-                  i3 = __ldg(idx + (size_t)row * 3 + 2);
-        const float w1 = __ldg(weight + (size_t)row * 3 + 0), w2 = __ldg(weight + (size_t)row * 3 + 1),
-                    w3 = __ldg(weight + (size_t)row * 3 + 2);
-        const float4* pb = points + (size_t)cloud * m * c4 + l;
-        const float4 a = __ldg(pb + (size_t)i1 * c4), b = __ldg(pb + (size_t)i2 * c4), c = __ldg(pb + (size_t)i3 * c4);
-        float4 o;
-        o.x = interp3(a.x, b.x, c.x, w1, w2, w3);
-        o.y = interp3(a.y, b.y, c.y, w1, w2, w3);
-        o.z = interp3(a.z, b.z, c.z, w1, w2, w3);
-        o.w = interp3(a.w, b.w, c.w, w1, w2, w3);
-        st_stream_f4(out + v, o);
+    for (IndexT v0 = (IndexT)blockIdx.x * kItThreads + threadIdx.x; v0 < total_vec; v0 += stride * U) {
+        int i1[U], i2[U], i3[U];
+        float w1[U], w2[U], w3[U];
+        const float4* pb[U];
+        bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const IndexT v = v0 + (IndexT)u * stride;
+            ok[u] = v < total_vec;
+            const IndexT row = ok[u] ? v / (IndexT)c4 : 0;
+            const int l = ok[u] ? (int)(v - row * (IndexT)c4) : 0;
+            const IndexT cloud = row / rows_per_cloud;
+            i1[u] = __ldg(idx + (size_t)row * 3 + 0);
+            i2[u] = __ldg(idx + (size_t)row * 3 + 1);
+            i3[u] = __ldg(idx + (size_t)row * 3 + 2);
+            w1[u] = __ldg(weight + (size_t)row * 3 + 0);
+            w2[u] = __ldg(weight + (size_t)row * 3 + 1);
+            w3[u] = __ldg(weight + (size_t)row * 3 + 2);
+            pb[u] = points + (size_t)cloud * m * c4 + l;
+        }
+        float4 a[U], b[U], c[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (ok[u]) {
+                a[u] = __ldg(pb[u] + (size_t)i1[u] * c4);
+                b[u] = __ldg(pb[u] + (size_t)i2[u] * c4);
+                c[u] = __ldg(pb[u] + (size_t)i3[u] * c4);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (ok[u]) {
+                float4 o;
+                o.x = interp3(a[u].x, b[u].x, c[u].x, w1[u], w2[u], w3[u]);
+                o.y = interp3(a[u].y, b[u].y, c[u].y, w1[u], w2[u], w3[u]);
+                o.z = interp3(a[u].z, b[u].z, c[u].z, w1[u], w2[u], w3[u]);
+                o.w = interp3(a[u].w, b[u].w, c[u].w, w1[u], w2[u], w3[u]);
+                st_stream_f4(out + v0 + (IndexT)u * stride, o);
+            }
+        }
     }
 }
 
@@ -248,30 +276,71 @@ three_interp_grad_scalar_kernel(int m, int c, IndexT rows_per_cloud, IndexT tota
     }
 }
 
-// ---- fused FP front end: three_nn -> inverse-distance weights -> three_interpolate ---------------
-// utils/pointnet_util.py:211-216.  Phase 1: one thread per unknown point finds its 3 neighbours
-// and weights (kept in shared memory).  Phase 2: the CTA writes its kNnThreads x c output block
-// with consecutive lanes on consecutive channels (coalesced), never materialising dist/idx/weight
-// in HBM unless the caller asks for them.
+// ---- fused FP front end: three_nn -> inverse-distance weights -> three_interpolate -> concat -----
+// utils/pointnet_util.py:211-219.  G lanes share one unknown point: lane g scans the known points of
+// pairs p = g, g+G, ... (ascending index inside the lane), the G partial top-3 lists are merged by a
+// shuffle butterfly under (distance, index) — exactly the order the reference's strict '<' scan over
+// ascending indices produces — so small layers (64 or 256 unknown points per cloud) still fill the
+// machine: a CTA covers 128/G points.  Phase 2 writes the CTA's rows of the output
+// [interpolated (c2) | points1 (c1)] with consecutive lanes on consecutive channels; dist / idx /
+// weight never touch HBM unless the caller asks for them, and the concat of :219 is not a separate pass.
+__device__ __forceinline__ void top3_insert_lex(Top3& t, float d, int k) {
+    // like top3_insert, with ties broken by the smaller index (candidates arrive out of index order)
+    const bool c3 = d < t.d3 || (d == t.d3 && k < t.i3), c2 = d < t.d2 || (d == t.d2 && k < t.i2),
+               c1 = d < t.d1 || (d == t.d1 && k < t.i1);
+    const float nd3 = c2 ? t.d2 : d;
+    const int ni3 = c2 ? t.i2 : k;
+    const float nd2 = c1 ? t.d1 : d;
+    const int ni2 = c1 ? t.i1 : k;
+    t.d3 = c3 ? nd3 : t.d3;
+    t.i3 = c3 ? ni3 : t.i3;
+    t.d2 = c2 ? nd2 : t.d2;
+    t.i2 = c2 ? ni2 : t.i2;
+    t.d1 = c1 ? d : t.d1;
+    t.i1 = c1 ? k : t.i1;
+}
+
+// lane g of G scans pairs g, g+G, ... of the tile (2 points per pair)
+template <int G>
+__device__ __forceinline__ void scan_tile_strided(Top3& t, const KnownTile& tile, int tp_pad, int base, int g, float ux, float uy,
+                                                  float uz) {
+    const unsigned long long UX = nn_pack(ux, ux), UY = nn_pack(uy, uy), UZ = nn_pack(uz, uz);
+    for (int p = g; p < tp_pad; p += G) {
+        const ulonglong2 xy = tile.xy[p];
+        const unsigned long long zz = tile.z[p];
+        const unsigned long long dx = nn_sub2(xy.x, UX), dy = nn_sub2(xy.y, UY), dz = nn_sub2(zz, UZ);
+        float xx0, xx1, yy0, yy1, zz0, zz1;
+        nn_unpack(nn_mul2(dx, dx), xx0, xx1);
+        nn_unpack(nn_mul2(dy, dy), yy0, yy1);
+        nn_unpack(nn_mul2(dz, dz), zz0, zz1);
+        const float d0 = __fadd_rn(__fadd_rn(xx0, yy0), zz0), d1 = __fadd_rn(__fadd_rn(xx1, yy1), zz1);
+        if (d0 < t.d3) top3_insert(t, d0, base + 2 * p);
+        if (d1 < t.d3) top3_insert(t, d1, base + 2 * p + 1);
+    }
+}
+
+template <int G>
 __global__ void __launch_bounds__(kNnThreads)
-three_nn_interp_kernel(int n, int m, int c, const float* __restrict__ xyz1, const float* __restrict__ xyz2,
-                       const float* __restrict__ points2, float* __restrict__ out, float* __restrict__ dist_o,
-                       int* __restrict__ idx_o, float* __restrict__ weight_o) {
+fp_front_kernel(int n, int m, int c2, int c1, const float* __restrict__ xyz1, const float* __restrict__ xyz2,
+                const float* __restrict__ points1, const float* __restrict__ points2, float* __restrict__ out,
+                float* __restrict__ dist_o, int* __restrict__ idx_o, float* __restrict__ weight_o) {
+    constexpr int PPB = kNnThreads / G;  // unknown points per CTA
     __shared__ KnownTile s_tile;
-    __shared__ int s_i[kNnThreads][3];
-    __shared__ float s_w[kNnThreads][3];
+    __shared__ int s_i[PPB][3];
+    __shared__ float s_w[PPB][3];
     const int tid = threadIdx.x;
+    const int g = tid % G, slot = tid / G;
     const int cloud = blockIdx.y;
-    const int j0 = blockIdx.x * kNnThreads;
-    const int j = j0 + tid;
+    const int j0 = blockIdx.x * PPB;
+    const int j = j0 + slot;
     const bool valid = j < n;
     const float* __restrict__ known = xyz2 + (size_t)cloud * m * 3;
     float ux = 0.f, uy = 0.f, uz = 0.f;
     if (valid) {
         const float* u = xyz1 + ((size_t)cloud * n + j) * 3;
-        ux = u[0];
-        uy = u[1];
-        uz = u[2];
+        ux = __ldg(u);
+        uy = __ldg(u + 1);
+        uz = __ldg(u + 2);
     }
     Top3 t;
     top3_init(t);
@@ -279,7 +348,21 @@ three_nn_interp_kernel(int n, int m, int c, const float* __restrict__ xyz1, cons
         if (base) __syncthreads();
         const int tp_pad = stage_known(s_tile, known, base, m, tid, kNnThreads);
         __syncthreads();
-        scan_tile(t, s_tile, tp_pad, base, ux, uy, uz);
+        if (G == 1) scan_tile(t, s_tile, tp_pad, base, ux, uy, uz);
+        else scan_tile_strided<G>(t, s_tile, tp_pad, base, g, ux, uy, uz);
+    }
+    if (G > 1) {  // merge the G partial lists of this point (all lanes end with the merged list)
+#pragma unroll
+        for (int o = 1; o < G; o <<= 1) {
+            const float e1 = __shfl_xor_sync(kFullMask, t.d1, o), e2 = __shfl_xor_sync(kFullMask, t.d2, o),
+                        e3 = __shfl_xor_sync(kFullMask, t.d3, o);
+            const int f1 = __shfl_xor_sync(kFullMask, t.i1, o), f2 = __shfl_xor_sync(kFullMask, t.i2, o),
+                      f3 = __shfl_xor_sync(kFullMask, t.i3, o);
+            // +inf entries are the (inf, 0) filler of an unfilled slot: never insert them (index 0 would win ties)
+            if (e1 < INFINITY) top3_insert_lex(t, e1, f1);
+            if (e2 < INFINITY) top3_insert_lex(t, e2, f2);
+            if (e3 < INFINITY) top3_insert_lex(t, e3, f3);
+        }
     }
     // dist = max(dist, 1e-10); norm = sum(1/dist); weight = (1/dist)/norm   (pointnet_util.py:212-215)
     const float r1 = __fdiv_rn(1.0f, fmaxf(t.d1, 1e-10f));
@@ -287,39 +370,223 @@ three_nn_interp_kernel(int n, int m, int c, const float* __restrict__ xyz1, cons
     const float r3 = __fdiv_rn(1.0f, fmaxf(t.d3, 1e-10f));
     const float norm = __fadd_rn(__fadd_rn(r1, r2), r3);
     const float w1 = __fdiv_rn(r1, norm), w2 = __fdiv_rn(r2, norm), w3 = __fdiv_rn(r3, norm);
-    s_i[tid][0] = t.i1; s_i[tid][1] = t.i2; s_i[tid][2] = t.i3;
-    s_w[tid][0] = w1;   s_w[tid][1] = w2;   s_w[tid][2] = w3;
-    if (valid) {
-        const size_t o = ((size_t)cloud * n + j) * 3;
-        if (dist_o) { dist_o[o] = t.d1; dist_o[o + 1] = t.d2; dist_o[o + 2] = t.d3; }
-        if (idx_o) { idx_o[o] = t.i1; idx_o[o + 1] = t.i2; idx_o[o + 2] = t.i3; }
-        if (weight_o) { weight_o[o] = w1; weight_o[o + 1] = w2; weight_o[o + 2] = w3; }
+    if (g == 0) {
+        s_i[slot][0] = t.i1; s_i[slot][1] = t.i2; s_i[slot][2] = t.i3;
+        s_w[slot][0] = w1;   s_w[slot][1] = w2;   s_w[slot][2] = w3;
+        if (valid) {
+            const size_t o = ((size_t)cloud * n + j) * 3;
+            if (dist_o) { dist_o[o] = t.d1; dist_o[o + 1] = t.d2; dist_o[o + 2] = t.d3; }
+            if (idx_o) { idx_o[o] = t.i1; idx_o[o + 1] = t.i2; idx_o[o + 2] = t.i3; }
+            if (weight_o) { weight_o[o] = w1; weight_o[o + 1] = w2; weight_o[o + 2] = w3; }
+        }
     }
     __syncthreads();
-    const int rows = min(kNnThreads, n - j0);
-    const float* __restrict__ pb = points2 + (size_t)cloud * m * c;
-    float* __restrict__ ob = out + ((size_t)cloud * n + j0) * c;
-    if ((c & 3) == 0 && ((reinterpret_cast<uintptr_t>(pb) | reinterpret_cast<uintptr_t>(ob)) & 15u) == 0) {
-        const int c4 = c >> 2;
+    if (!out) return;
+    const int rows = min(PPB, n - j0);
+    const int cw = c2 + c1;  // output row width
+    const float* __restrict__ pb = points2 + (size_t)cloud * m * c2;
+    const float* __restrict__ p1 = points1 ? points1 + ((size_t)cloud * n + j0) * c1 : nullptr;
+    float* __restrict__ ob = out + ((size_t)cloud * n + j0) * cw;
+    const bool vec = ((c2 | c1) & 3) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(pb) | reinterpret_cast<uintptr_t>(ob) | reinterpret_cast<uintptr_t>(p1)) & 15u) == 0;
+    if (vec) {
+        const int c24 = c2 >> 2, cw4 = cw >> 2, c14 = c1 >> 2;
         const float4* pb4 = reinterpret_cast<const float4*>(pb);
+        const float4* p14 = reinterpret_cast<const float4*>(p1);
         float4* ob4 = reinterpret_cast<float4*>(ob);
-        for (int e = tid; e < rows * c4; e += kNnThreads) {
-            const int r = e / c4, l = e - r * c4;
-            const float4 a = __ldg(pb4 + (size_t)s_i[r][0] * c4 + l), b = __ldg(pb4 + (size_t)s_i[r][1] * c4 + l),
-                         cc = __ldg(pb4 + (size_t)s_i[r][2] * c4 + l);
-            const float x1 = s_w[r][0], x2 = s_w[r][1], x3 = s_w[r][2];
+        for (int e = tid; e < rows * cw4; e += kNnThreads) {
+            const int r = e / cw4, l = e - r * cw4;
             float4 o;
-            o.x = interp3(a.x, b.x, cc.x, x1, x2, x3);
-            o.y = interp3(a.y, b.y, cc.y, x1, x2, x3);
-            o.z = interp3(a.z, b.z, cc.z, x1, x2, x3);
-            o.w = interp3(a.w, b.w, cc.w, x1, x2, x3);
+            if (l < c24) {
+                const float4 a = __ldg(pb4 + (size_t)s_i[r][0] * c24 + l), b = __ldg(pb4 + (size_t)s_i[r][1] * c24 + l),
+                             cc = __ldg(pb4 + (size_t)s_i[r][2] * c24 + l);
+                const float x1 = s_w[r][0], x2 = s_w[r][1], x3 = s_w[r][2];
+                o.x = interp3(a.x, b.x, cc.x, x1, x2, x3);
+                o.y = interp3(a.y, b.y, cc.y, x1, x2, x3);
+                o.z = interp3(a.z, b.z, cc.z, x1, x2, x3);
+                o.w = interp3(a.w, b.w, cc.w, x1, x2, x3);
+            } else {
+                o = __ldcs(p14 + (size_t)r * c14 + (l - c24));  // points1, read once
+            }
             st_stream_f4(ob4 + e, o);
         }
     } else {
-        for (int e = tid; e < rows * c; e += kNnThreads) {
-            const int r = e / c, l = e - r * c;
-            ob[e] = interp3(__ldg(pb + (size_t)s_i[r][0] * c + l), __ldg(pb + (size_t)s_i[r][1] * c + l),
-                            __ldg(pb + (size_t)s_i[r][2] * c + l), s_w[r][0], s_w[r][1], s_w[r][2]);
+        for (int e = tid; e < rows * cw; e += kNnThreads) {
+            const int r = e / cw, l = e - r * cw;
+            float o;
+            if (l < c2)
+                o = interp3(__ldg(pb + (size_t)s_i[r][0] * c2 + l), __ldg(pb + (size_t)s_i[r][1] * c2 + l),
+                            __ldg(pb + (size_t)s_i[r][2] * c2 + l), s_w[r][0], s_w[r][1], s_w[r][2]);
+            else
+                o = __ldcs(p1 + (size_t)r * c1 + (l - c2));
+            ob[e] = o;
+        }
+    }
+}
+
+template <int G>
+static int launch_fp_front(int b, int n, int m, int c2, int c1, const float* xyz1, const float* xyz2, const float* points1,
+                           const float* points2, float* out, float* dist, int* idx, float* weight, cudaStream_t st) {
+    constexpr int PPB = kNnThreads / G;
+    dim3 grid((n + PPB - 1) / PPB, b, 1);
+    fp_front_kernel<G><<<grid, kNnThreads, 0, st>>>(n, m, c2, c1, xyz1, xyz2, points1, points2, out, dist, idx, weight);
+    return finish_launch();
+}
+
+static int fp_front_dispatch(int b, int n, int m, int c2, int c1, const float* xyz1, const float* xyz2, const float* points1,
+                             const float* points2, float* out, float* dist, int* idx, float* weight, cudaStream_t st) {
+    // lanes per unknown point: as many as it takes to put ~2 CTAs on every SM (a CTA covers 128/G points),
+    // but never more lanes than there are pairs of known points to share
+    const long long pts = (long long)b * n;
+    int G = 1;
+    while (G < 32 && pts * G < 2LL * 148 * kNnThreads && 2 * G <= (m + 1) / 2) G *= 2;
+    switch (G) {
+        case 1: return launch_fp_front<1>(b, n, m, c2, c1, xyz1, xyz2, points1, points2, out, dist, idx, weight, st);
+        case 2: return launch_fp_front<2>(b, n, m, c2, c1, xyz1, xyz2, points1, points2, out, dist, idx, weight, st);
+        case 4: return launch_fp_front<4>(b, n, m, c2, c1, xyz1, xyz2, points1, points2, out, dist, idx, weight, st);
+        case 8: return launch_fp_front<8>(b, n, m, c2, c1, xyz1, xyz2, points1, points2, out, dist, idx, weight, st);
+        case 16: return launch_fp_front<16>(b, n, m, c2, c1, xyz1, xyz2, points1, points2, out, dist, idx, weight, st);
+        default: return launch_fp_front<32>(b, n, m, c2, c1, xyz1, xyz2, points1, points2, out, dist, idx, weight, st);
+    }
+}
+
+// ---- three_interpolate_grad without atomics: an inverse index, then one warp per known point ------
+// grad_points[b,i,:] = sum over the entries e = 3j+t with idx[b,j,t] == i of grad_out[b,j,:] * weight[b,j,t],
+// accumulated in ASCENDING e — the very order threeinterpolate_grad_cpu (tf_interpolate.cpp:131-153: j outer,
+// t = 1,2,3 inner) adds them, each product and sum rounded on its own — so the result is not only
+// deterministic but bit-identical to the reference's CPU function, and grad_points needs no zero-fill.
+// Build: count entries per known point (int atomics), exclusive scan per cloud, fill the CSR lists (order
+// inside a list is arbitrary), then every warp sorts its own list (<= 128 entries: bitonic sort in
+// registers; longer lists — degenerate layers where most unknown points share a neighbour — are served
+// by an index-ordered scan of the cloud's entries instead).
+constexpr int kInvThreads = 256;
+constexpr int kInvSortCap = 128;
+
+__global__ void __launch_bounds__(kInvThreads)
+inv_count_kernel(int n3, int m, long long total, const int* __restrict__ idx, int* __restrict__ cnt) {
+    for (long long e = (long long)blockIdx.x * kInvThreads + threadIdx.x; e < total; e += (long long)gridDim.x * kInvThreads) {
+        const long long cloud = e / n3;
+        atomicAdd(cnt + cloud * (m + 1) + __ldg(idx + e), 1);
+    }
+}
+
+// one CTA per cloud: off[i] = exclusive prefix of cnt[i], i = 0..m (off[m] = 3n); cur[i] = off[i]
+__global__ void __launch_bounds__(1024)
+inv_scan_kernel(int m, int* __restrict__ cnt_off, int* __restrict__ cur) {
+    __shared__ int s_w[32];
+    __shared__ int s_carry;
+    int* __restrict__ c = cnt_off + (size_t)blockIdx.x * (m + 1);
+    int* __restrict__ cu = cur + (size_t)blockIdx.x * m;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base <= m; base += 1024) {
+        const int i = base + tid;
+        const int v = (i < m) ? c[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        int wv = s_w[lane], winc = wv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(kFullMask, winc, o);
+            if (lane >= o) winc += t;
+        }
+        const int carry = s_carry;
+        const int excl = carry + __shfl_sync(kFullMask, winc - wv, warp) + incl - v;
+        if (i <= m) c[i] = excl;
+        if (i < m) cu[i] = excl;
+        __syncthreads();
+        if (tid == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kInvThreads)
+inv_fill_kernel(int n3, int m, long long total, const int* __restrict__ idx, int* __restrict__ cur, int* __restrict__ entries) {
+    for (long long e = (long long)blockIdx.x * kInvThreads + threadIdx.x; e < total; e += (long long)gridDim.x * kInvThreads) {
+        const long long cloud = e / n3;
+        const int pos = atomicAdd(cur + cloud * m + __ldg(idx + e), 1);
+        entries[cloud * n3 + pos] = (int)(e - cloud * n3);
+    }
+}
+
+// one warp per known point (b, i); lanes over channels (float4 when VEC)
+template <bool VEC>
+__global__ void __launch_bounds__(kInvThreads)
+inv_gather_kernel(int n, int c, int m, long long warps_total, const float* __restrict__ grad_out, const int* __restrict__ idx,
+                  const float* __restrict__ weight, const int* __restrict__ off, const int* __restrict__ entries,
+                  float* __restrict__ grad_points) {
+    __shared__ int s_e[kInvThreads / 32][kInvSortCap];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const long long gw = ((long long)blockIdx.x * kInvThreads + threadIdx.x) >> 5;
+    if (gw >= warps_total) return;
+    const long long cloud = gw / m;
+    const int i = (int)(gw - cloud * m);
+    const int n3 = 3 * n;
+    const int* __restrict__ o = off + cloud * (m + 1);
+    const int beg = o[i], len = o[i + 1] - beg;
+    const float* __restrict__ go = grad_out + (size_t)cloud * n * c;
+    const float* __restrict__ wt = weight + (size_t)cloud * n3;
+    float* __restrict__ gp = grad_points + ((size_t)cloud * m + i) * c;
+    const bool sorted = len <= kInvSortCap;
+    if (sorted) {
+        int key[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) key[q] = (32 * q + lane < len) ? __ldg(entries + cloud * n3 + beg + 32 * q + lane) : 0x7fffffff;
+        const int nreg = (len + 31) >> 5;
+        if (nreg <= 1) bitonic_sort_keys<1>(key, lane);
+        else if (nreg == 2) bitonic_sort_keys<2>(key, lane);
+        else bitonic_sort_keys<4>(key, lane);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (32 * q + lane < len) s_e[wib][32 * q + lane] = key[q];
+        __syncwarp();
+    }
+    const int* __restrict__ cidx = idx + cloud * n3;
+    constexpr int W = VEC ? 4 : 1;
+    for (int l0 = 0; l0 < c; l0 += 32 * W) {  // 128 (VEC) or 32 channels per pass
+        const int l = l0 + lane * W;
+        const bool act = l < c;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        auto accumulate = [&](int e) {
+            const float w = __ldg(wt + e);
+            const float* __restrict__ src = go + (size_t)(e / 3) * c + l;
+            if (VEC) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(src));
+                a0 = __fadd_rn(a0, __fmul_rn(g.x, w));
+                a1 = __fadd_rn(a1, __fmul_rn(g.y, w));
+                a2 = __fadd_rn(a2, __fmul_rn(g.z, w));
+                a3 = __fadd_rn(a3, __fmul_rn(g.w, w));
+            } else {
+                a0 = __fadd_rn(a0, __fmul_rn(__ldg(src), w));
+            }
+        };
+        if (sorted) {
+            if (act) {
+#pragma unroll 4
+                for (int sidx = 0; sidx < len; ++sidx) accumulate(s_e[wib][sidx]);
+            }
+        } else {
+            // long list: walk the cloud's entries in order and pick the ones that point at i
+            for (int base = 0; base < n3; base += 32) {
+                const int e = base + lane;
+                unsigned hit = __ballot_sync(kFullMask, e < n3 && __ldg(cidx + e) == i);
+                while (hit) {
+                    const int src = __ffs(hit) - 1;
+                    hit &= hit - 1;
+                    if (act) accumulate(base + src);
+                }
+            }
+        }
+        if (act) {
+            if (VEC) *reinterpret_cast<float4*>(gp + l) = make_float4(a0, a1, a2, a3);
+            else gp[l] = a0;
         }
     }
 }
@@ -359,11 +626,11 @@ int pn2_three_interpolate(int b, int m, int c, int n, const float* points, const
     cudaStream_t st = as_stream(stream);
     if (c % 4 == 0 && al16(points) && al16(out)) {
         const unsigned long long tv = total / 4;
-        const unsigned grid = it_grid(tv, kItThreads);
+        const unsigned grid = it_grid((tv + 3) / 4, kItThreads);  // 4 outputs per thread
         if (tv < (1ull << 31))
-            three_interp_vec4_kernel<unsigned><<<grid, kItThreads, 0, st>>>(m, c / 4, (unsigned)n, (unsigned)tv, (const float4*)points, idx, weight, (float4*)out);
+            three_interp_vec4_kernel<unsigned, 4><<<grid, kItThreads, 0, st>>>(m, c / 4, (unsigned)n, (unsigned)tv, (const float4*)points, idx, weight, (float4*)out);
         else
-            three_interp_vec4_kernel<unsigned long long><<<grid, kItThreads, 0, st>>>(m, c / 4, (unsigned long long)n, tv, (const float4*)points, idx, weight, (float4*)out);
+            three_interp_vec4_kernel<unsigned long long, 4><<<grid, kItThreads, 0, st>>>(m, c / 4, (unsigned long long)n, tv, (const float4*)points, idx, weight, (float4*)out);
     } else {
         const unsigned grid = it_grid(total, kItThreads);
         if (total < (1ull << 31))
@@ -406,8 +673,55 @@ int pn2_three_nn_interpolate(int b, int n, int m, int c, const float* xyz1, cons
     if (b == 0 || n == 0) return 0;
     if (!xyz1 || !xyz2 || (c > 0 && (!points2 || !out))) return (int)cudaErrorInvalidValue;
     if (b > 65535) return (int)cudaErrorInvalidValue;
-    dim3 grid((n + kNnThreads - 1) / kNnThreads, b, 1);
-    three_nn_interp_kernel<<<grid, kNnThreads, 0, as_stream(stream)>>>(n, m, c, xyz1, xyz2, points2, out, dist, idx, weight);
+    return fp_front_dispatch(b, n, m, c, 0, xyz1, xyz2, nullptr, points2, c > 0 ? out : nullptr, dist, idx, weight, as_stream(stream));
+}
+
+int pn2_fp_interpolate_concat(int b, int n, int m, int c2, int c1, const float* xyz1, const float* xyz2, const float* points1,
+                              const float* points2, float* out, void* stream) {
+    using namespace pn2;
+    if (b < 0 || n < 0 || m <= 0 || c2 <= 0 || c1 < 0) return (int)cudaErrorInvalidValue;
+    if (b == 0 || n == 0) return 0;
+    if (!xyz1 || !xyz2 || !points2 || !out || (c1 > 0 && !points1)) return (int)cudaErrorInvalidValue;
+    if (b > 65535) return (int)cudaErrorInvalidValue;
+    return fp_front_dispatch(b, n, m, c2, c1, xyz1, xyz2, c1 > 0 ? points1 : nullptr, points2, out, nullptr, nullptr, nullptr,
+                             as_stream(stream));
+}
+
+size_t pn2_three_interpolate_grad_det_workspace_bytes(int b, int n, int m) {
+    if (b <= 0 || n <= 0 || m <= 0) return 0;
+    // offsets (b, m+1) + cursors (b, m) + entries (b, 3n), ints
+    return sizeof(int) * ((size_t)b * (m + 1) + (size_t)b * m + (size_t)b * 3 * (size_t)n);
+}
+
+int pn2_three_interpolate_grad_det(int b, int n, int c, int m, const float* grad_out, const int* idx, const float* weight,
+                                   float* grad_points, void* workspace, size_t workspace_bytes, void* stream) {
+    using namespace pn2;
+    if (b < 0 || m <= 0 || c < 0 || n < 0) return (int)cudaErrorInvalidValue;
+    if ((unsigned long long)b * m * c == 0) return 0;
+    if (!grad_points) return (int)cudaErrorInvalidValue;
+    cudaStream_t st = as_stream(stream);
+    if (n == 0) return (int)cudaMemsetAsync(grad_points, 0, sizeof(float) * (size_t)b * m * c, st);
+    if (!grad_out || !idx || !weight || !workspace) return (int)cudaErrorInvalidValue;
+    if (workspace_bytes < pn2_three_interpolate_grad_det_workspace_bytes(b, n, m) || (long long)n * 3 > 0x7fffffffLL)
+        return (int)cudaErrorInvalidValue;
+    int* off = static_cast<int*>(workspace);
+    int* cur = off + (size_t)b * (m + 1);
+    int* entries = cur + (size_t)b * m;
+    cudaError_t e = cudaMemsetAsync(off, 0, sizeof(int) * (size_t)b * (m + 1), st);
+    if (e != cudaSuccess) return (int)e;
+    const long long total = (long long)b * n * 3;
+    const unsigned g1 = it_grid((unsigned long long)total, kInvThreads);
+    inv_count_kernel<<<g1, kInvThreads, 0, st>>>(3 * n, m, total, idx, off);
+    inv_scan_kernel<<<b, 1024, 0, st>>>(m, off, cur);
+    inv_fill_kernel<<<g1, kInvThreads, 0, st>>>(3 * n, m, total, idx, cur, entries);
+    const long long warps = (long long)b * m;
+    const unsigned long long blocks = ((unsigned long long)warps * 32 + kInvThreads - 1) / kInvThreads;
+    if (blocks > 0x7fffffffull) return (int)cudaErrorInvalidValue;
+    if (c % 4 == 0 && al16(grad_out) && al16(grad_points))
+        inv_gather_kernel<true><<<(unsigned)blocks, kInvThreads, 0, st>>>(n, c, m, warps, grad_out, idx, weight, off, entries, grad_points);
+    else
+        inv_gather_kernel<false><<<(unsigned)blocks, kInvThreads, 0, st>>>(n, c, m, warps, grad_out, idx, weight, off, entries, grad_points);
+    count_launch(3);
     return finish_launch();
 }
 

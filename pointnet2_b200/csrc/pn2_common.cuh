@@ -64,6 +64,39 @@ __device__ __forceinline__ void warp_max_pair(unsigned& hi, unsigned& lo) {
     lo = ml;
 }
 
+// Ascending bitonic sort of 32*K ints held K per lane (element i = register i/32 of lane i%32).
+template <int K>
+__device__ __forceinline__ void bitonic_sort_keys(int (&key)[4], int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32 * K; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 32) {  // partner in the same lane, another register
+                const int js = stride >> 5;
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    if ((j & js) == 0) {
+                        const bool up = (((32 * j) & size) == 0);  // lane bits are below 32 <= stride < size: direction depends on j only
+                        const int a = key[j], b = key[j | js];
+                        const bool sw = up ? (a > b) : (a < b);
+                        key[j] = sw ? b : a;
+                        key[j | js] = sw ? a : b;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < K; ++j) {
+                    const int i = 32 * j + lane;
+                    const int other = __shfl_xor_sync(kFullMask, key[j], stride);
+                    const bool up = ((i & size) == 0), lower = ((lane & stride) == 0);
+                    // the lower element of an ascending pair keeps the minimum
+                    key[j] = (up == lower) ? min(key[j], other) : max(key[j], other);
+                }
+            }
+        }
+    }
+}
+
 // brute-force ball query launcher (ball_query.cu); clouds whose grid_params[cloud*grid_stride] != 0
 // are skipped (they are served by the uniform-grid kernels of ball_query_grid.cu)
 int launch_ball_query_brute(int b, int n, int m, float thr, int nsample, const float* xyz1, const float* xyz2,

@@ -89,7 +89,6 @@ ball_group_kernel(int n, int m, float radius, float thr, int nsample, const floa
     int(*s_hits)[kBgHitCap] = reinterpret_cast<int(*)[kBgHitCap]>(s_cur);               // query: per-warp hit positions
     __shared__ float s_red[6][32];
     __shared__ int s_wsum[32];
-    __shared__ int s_heavy;
     __shared__ float4 s_first[NW];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -116,7 +115,6 @@ ball_group_kernel(int n, int m, float radius, float thr, int nsample, const floa
         }
     }
     for (int c = tid; c < kBgMaxCells; c += T) s_cur[c] = 0;
-    if (tid == 0) s_heavy = 0;
     __syncthreads();
     float ext[3];
 #pragma unroll
@@ -138,11 +136,9 @@ ball_group_kernel(int n, int m, float radius, float thr, int nsample, const floa
     }
     const int ncell = dims[0] * dims[1] * dims[2];
     const int nb = min(dims[0], 3) * min(dims[1], 3) * min(dims[2], 3);
-    const float vol = fmaxf(ext[0], h) * fmaxf(ext[1], h) * fmaxf(ext[2], h);
-    const float expect = (float)n * 4.18879f * radius * radius * radius / vol;
-    // same rules as ball_query_grid.cu: the neighbourhood must prune >= 70 % of the cloud, and the balls
-    // must be sparse (when they fill up, the ordered scan exits early and wins)
-    bool use_grid = finite_box && n >= kBgMinGridN && 10 * nb <= 3 * ncell && expect < 0.75f * (float)nsample;
+    // the neighbourhood must prune >= 70 % of the grid; whether the BALLS are sparse enough is judged from
+    // the cell histogram below (a box-uniform estimate misjudges both surfaces and duplicate clusters)
+    bool use_grid = finite_box && n >= kBgMinGridN && 10 * nb <= 3 * ncell;
     __syncthreads();  // s_red is reused below
     if (use_grid) {   // CTA-uniform
         for (int k = tid; k < n; k += T) {
@@ -155,18 +151,31 @@ ball_group_kernel(int n, int m, float radius, float thr, int nsample, const floa
         __syncthreads();
         const int per = (ncell + T - 1) / T;
         const int c0 = min(tid * per, ncell), c1 = min(c0 + per, ncell);
-        int local = 0, heavy = 0;
-        float sq = 0.f;
+        // density seen by a typical point: a point of cell i has about c_i * (ball volume / cell volume)
+        // neighbours, so the point-weighted mean is sum(c_i^2)/sum(c_i) * 4.19 (r/h)^3.  Counts are CLIPPED at
+        // 4*nsample first: beyond that a ball is full whatever the exact count, and an unclipped sum lets one
+        // cell of coincident points (ScanNet-style duplicates: 80 % of the cloud in one spot) pass the whole
+        // cloud off as dense although every other ball is nearly empty.  Surface-like clouds fill few cells
+        // densely: their balls fill up, the ordered scan exits early and wins.
+        const float clipc = 4.0f * (float)nsample;
+        int local = 0;
+        float sq = 0.f, sw = 0.f;
         for (int c = c0; c < c1; ++c) {
             const int cntc = s_cur[c];
             local += cntc;
-            sq += (float)cntc * (float)cntc;
-            heavy |= (cntc > 256) ? 1 : 0;
+            const float cc = fminf((float)cntc, clipc);
+            sq += cc * cc;
+            sw += cc;
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(kFullMask, sq, o);
-        if (lane == 0) s_red[0][warp] = sq;
-        if (heavy) s_heavy = 1;
+        for (int o = 16; o > 0; o >>= 1) {
+            sq += __shfl_xor_sync(kFullMask, sq, o);
+            sw += __shfl_xor_sync(kFullMask, sw, o);
+        }
+        if (lane == 0) {
+            s_red[0][warp] = sq;
+            s_red[1][warp] = sw;
+        }
         int incl = local;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -190,13 +199,16 @@ ball_group_kernel(int n, int m, float radius, float thr, int nsample, const floa
             run += cntc;
         }
         if (tid == 0) s_cell[ncell] = n;
-        float sqsum = s_red[0][lane];
+        float sqsum = s_red[0][lane], swsum = s_red[1][lane];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sqsum += __shfl_xor_sync(kFullMask, sqsum, o);
+        for (int o = 16; o > 0; o >>= 1) {
+            sqsum += __shfl_xor_sync(kFullMask, sqsum, o);
+            swsum += __shfl_xor_sync(kFullMask, swsum, o);
+        }
         const float rh = radius * inv_h;
-        const float expect_local = 4.18879f * rh * rh * rh * sqsum / (float)n;
+        const float expect_local = 4.18879f * rh * rh * rh * sqsum / fmaxf(swsum, 1.0f);
         __syncthreads();
-        use_grid = (s_heavy == 0) && (expect_local < kBgDenseFrac * (float)nsample);
+        use_grid = expect_local < kBgDenseFrac * (float)nsample;
         if (use_grid) {
             for (int k = tid; k < n; k += T) {
                 const float x = __ldg(pts + 3 * (size_t)k), y = __ldg(pts + 3 * (size_t)k + 1), z = __ldg(pts + 3 * (size_t)k + 2);
@@ -256,10 +268,11 @@ ball_group_kernel(int n, int m, float radius, float thr, int nsample, const floa
         auto emit = [&](int r, int k, float x, float y, float z) {
             row[r] = k;
             if (grow) {
-                // centred: xyz[idx] - new_xyz, one rounding per coordinate (utils/pointnet_util.py:46); x - 0 == x otherwise
-                grow[3 * r + 0] = __fsub_rn(x, ox);
-                grow[3 * r + 1] = __fsub_rn(y, oy);
-                grow[3 * r + 2] = __fsub_rn(z, oz);
+                // centred: xyz[idx] - new_xyz, one rounding per coordinate (utils/pointnet_util.py:46); a raw copy
+                // otherwise (x - 0 would canonicalise a NaN payload, which a gather never does)
+                grow[3 * r + 0] = center ? __fsub_rn(x, ox) : x;
+                grow[3 * r + 1] = center ? __fsub_rn(y, oy) : y;
+                grow[3 * r + 2] = center ? __fsub_rn(z, oz) : z;
             }
         };
 
@@ -270,45 +283,81 @@ ball_group_kernel(int n, int m, float radius, float thr, int nsample, const floa
             const int cx = bg_cell(qx, mn[0], inv_h, dxs), cy = bg_cell(qy, mn[1], inv_h, dys), cz = bg_cell(qz, mn[2], inv_h, dzs);
             const int x0 = max(cx - 1, 0), x1 = min(cx + 1, dxs - 1);
             // 9 rows (dy, dz in {-1,0,1}) of up to 3 x-adjacent cells = 9 contiguous candidate ranges;
-            // lanes 3r..3r+2 walk range r with stride 3
+            // lanes 3r..3r+2 own range r
             int p = 0, p1 = 0;
+            const int rr = lane / 3, sub = lane - 3 * rr;
             {
-                const int r = lane / 3, sub = lane - 3 * r;
-                const int y = cy + (r % 3) - 1, z = cz + (r / 3) - 1;
+                const int y = cy + (rr % 3) - 1, z = cz + (rr / 3) - 1;
                 if (lane < 27 && x0 <= x1 && y >= 0 && y < dys && z >= 0 && z < dzs) {
                     const int rowbase = (z * dys + y) * dxs;
-                    p = s_cell[rowbase + x0] + sub;
+                    p = s_cell[rowbase + x0];
                     p1 = s_cell[rowbase + x1 + 1];
                 }
             }
+            const int len = (sub == 0) ? p1 - p : 0;
+            const int total = __reduce_add_sync(kFullMask, len), longest = __reduce_max_sync(kFullMask, len);
             int hcount = 0;
-            while (__any_sync(kFullMask, p < p1)) {
+            auto test = [&](bool active, int pos) {  // one candidate per active lane; warp-uniform overflow flag
                 bool hit = false;
-                if (p < p1) {
-                    const float4 c = s_pts[p];
+                int key = 0;
+                if (active) {
+                    const float4 c = s_pts[pos];
                     hit = !(d2_fma_pattern(qx, qy, qz, c.x, c.y, c.z) > thr);
+                    key = (__float_as_int(c.w) << kBgPosBits) | pos;  // (data index, position): indices are distinct
                 }
                 const unsigned bal = __ballot_sync(kFullMask, hit);
                 if (bal) {
                     const int r = hcount + __popc(bal & lt_mask);
-                    // key = (data index << 14 | position): indices are distinct, so keys order by index
-                    if (hit && r < kBgHitCap) s_hits[warp][r] = (__float_as_int(s_pts[p].w) << kBgPosBits) | p;
+                    if (hit && r < kBgHitCap) s_hits[warp][r] = key;
                     hcount += __popc(bal);
-                    if (hcount > kBgHitCap) break;  // warp-uniform: dense ball, take the ordered scan
                 }
-                p += 3;
+                return hcount > kBgHitCap;
+            };
+            bool overflow = 2 * total > n;  // the neighbourhood is most of the cloud (a cell of coincident points): scan instead
+            if (!overflow) {
+                if (longest <= 48) {
+                    // balanced ranges: lanes 3r..3r+2 walk range r with stride 3
+                    p += sub;
+                    while (__any_sync(kFullMask, p < p1)) {
+                        if (test(p < p1, p)) {
+                            overflow = true;
+                            break;
+                        }
+                        p += 3;
+                    }
+                } else {
+                    // a crowded cell in the neighbourhood: all 32 lanes walk one range after the other
+                    for (int r = 0; r < 9 && !overflow; ++r) {
+                        const int a = __shfl_sync(kFullMask, p, 3 * r), e = __shfl_sync(kFullMask, p1, 3 * r);
+                        for (int pos = a + lane; pos - lane < e; pos += 32) {
+                            if (test(pos < e, pos)) {
+                                overflow = true;
+                                break;
+                            }
+                        }
+                    }
+                }
             }
-            if (hcount <= kBgHitCap) {
-                // order the (distinct) hits by data index: rank = number of hits with a smaller index
+            if (!overflow) {
+                // order the hits by data index: bitonic sort of the (index, position) keys in registers
+                // (<= 128 keys, 4 per lane: element i lives in register i/32 of lane i%32)
                 __syncwarp();
                 cnt = min(hcount, nsample);
-                for (int e = lane; e < hcount; e += 32) {
-                    const int key = s_hits[warp][e];
-                    int r = 0;
-                    for (int f = 0; f < hcount; ++f) r += (s_hits[warp][f] < key) ? 1 : 0;
-                    const float4 c = s_pts[key & ((1 << kBgPosBits) - 1)];
-                    if (r < nsample) emit(r, key >> kBgPosBits, c.x, c.y, c.z);
-                    if (r == 0) s_first[warp] = c;
+                int key[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) key[j] = (32 * j + lane < hcount) ? s_hits[warp][32 * j + lane] : 0x7fffffff;
+                const int nreg = (hcount + 31) >> 5;  // registers that hold real keys (warp-uniform)
+                if (nreg <= 1) bitonic_sort_keys<1>(key, lane);
+                else if (nreg == 2) bitonic_sort_keys<2>(key, lane);
+                else bitonic_sort_keys<4>(key, lane);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int r = 32 * j + lane;
+                    if (r < cnt) {
+                        const float4 c = s_pts[key[j] & ((1 << kBgPosBits) - 1)];
+                        emit(r, key[j] >> kBgPosBits, c.x, c.y, c.z);
+                        if (r == 0) s_first[warp] = c;
+                    }
                 }
                 scanned = true;
             }
@@ -349,15 +398,11 @@ ball_group_kernel(int n, int m, float radius, float thr, int nsample, const floa
         for (int l = cnt + lane; l < nsample; l += 32) {
             row[l] = fk;
             if (grow) {
-                if (cnt > 0) {
-                    grow[3 * l + 0] = __fsub_rn(f.x, ox);
-                    grow[3 * l + 1] = __fsub_rn(f.y, oy);
-                    grow[3 * l + 2] = __fsub_rn(f.z, oz);
-                } else {  // index 0 is what an unfused group_point would gather for an all-zero row
-                    grow[3 * l + 0] = __fsub_rn(__ldg(pts + 0), ox);
-                    grow[3 * l + 1] = __fsub_rn(__ldg(pts + 1), oy);
-                    grow[3 * l + 2] = __fsub_rn(__ldg(pts + 2), oz);
-                }
+                // rows with no hit: index 0 is what an unfused group_point would gather for an all-zero row
+                const float px = (cnt > 0) ? f.x : __ldg(pts + 0), py = (cnt > 0) ? f.y : __ldg(pts + 1), pz = (cnt > 0) ? f.z : __ldg(pts + 2);
+                grow[3 * l + 0] = center ? __fsub_rn(px, ox) : px;
+                grow[3 * l + 1] = center ? __fsub_rn(py, oy) : py;
+                grow[3 * l + 2] = center ? __fsub_rn(pz, oz) : pz;
             }
         }
         if (lane == 0) pts_cnt[(size_t)cloud * m + q] = cnt;
@@ -369,24 +414,37 @@ ball_group_kernel(int n, int m, float radius, float thr, int nsample, const floa
 }
 
 struct BgOnce {
-    std::atomic<unsigned long long> done{0ull};
+    std::atomic<long long> max_dyn[64];  // per device: largest dynamic shared memory the kernel may request (0 = not asked yet)
 };
 
 static int launch_ball_group(int b, int n, int m, float radius, float thr, int nsample, const float* xyz1, const float* xyz2,
                              const int* q_idx, int* idx, int* pts_cnt, float* grouped, int center, int ctas_per_cloud,
                              bool dependent, cudaStream_t st) {
     static BgOnce once;
-    const size_t dyn = bg_smem_bytes(n);
+    size_t dyn = bg_smem_bytes(n);
     if (dyn > kBgSmemMax) return (int)cudaErrorInvalidValue;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;
-    const unsigned long long bit = 1ull << (dev & 63);
-    if (dev >= 64 || !(once.done.load(std::memory_order_acquire) & bit)) {
-        e = cudaFuncSetAttribute(ball_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBgSmemMax);
+    if (dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
+    long long max_dyn = once.max_dyn[dev].load(std::memory_order_acquire);
+    if (max_dyn == 0) {
+        int optin = 0;
+        cudaFuncAttributes fa;
+        e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, ball_group_kernel);
         if (e != cudaSuccess) return (int)e;
-        if (dev < 64) once.done.fetch_or(bit, std::memory_order_release);
+        max_dyn = (long long)optin - (long long)fa.sharedSizeBytes;
+        if (max_dyn < (long long)kBgSmemMax) return (int)cudaErrorInvalidValue;
+        e = cudaFuncSetAttribute(ball_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn);
+        if (e != cudaSuccess) return (int)e;
+        once.max_dyn[dev].store(max_dyn, std::memory_order_release);
     }
+    // Overlapped with the sampling kernel, the consumer must have an SM to ITSELF: a 1024-thread CTA next
+    // to a sampling CTA would take issue slots from the serial chain the whole layer waits for (measured:
+    // cfg3 layer 1, N=1024, +50 us).  Asking for every byte of shared memory the SM has makes co-residency
+    // with any other CTA impossible.
+    if (dependent) dyn = (size_t)max_dyn;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)b * (unsigned)ctas_per_cloud, 1, 1);
     cfg.blockDim = dim3(kBgThreads, 1, 1);

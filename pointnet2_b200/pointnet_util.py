@@ -22,7 +22,7 @@ import torch
 from . import _lib
 from ._tensor import on_device, ptr, require_cuda, same_device, stream_ptr
 from .tf_grouping import group_point, knn_point, query_ball_point
-from .tf_interpolate import three_interpolate, three_nn, three_nn_interpolate
+from .tf_interpolate import fp_interpolate_concat, three_interpolate, three_nn, three_nn_interpolate
 from .sa_layer import sample_group
 from .tf_sampling import farthest_point_sample, farthest_point_sample_and_gather, gather_point
 
@@ -230,18 +230,23 @@ def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp: Optional[Callable] = N
         xyz1 (b,n1,3) dense, xyz2 (b,n2,3) sparser, points1 (b,n1,c1) or None, points2 (b,n2,c2).
         Return: new_points (b,n1,mlp[-1]) (or (b,n1,c2+c1) when mlp is None)
     '''
-    if fused and not points2.requires_grad:
-        interpolated_points = three_nn_interpolate(xyz1, xyz2, points2)
+    no_grad = not points2.requires_grad and (points1 is None or not points1.requires_grad)
+    if fused and no_grad and points2.shape[2] > 0:
+        # one kernel: 3-NN, weights, interpolation and the concat of :219
+        new_points1 = fp_interpolate_concat(xyz1, xyz2, points1, points2)
     else:
-        dist, idx = three_nn(xyz1, xyz2)
-        dist = torch.clamp(dist, min=1e-10)
-        norm = (1.0 / dist).sum(dim=2, keepdim=True)
-        weight = (1.0 / dist) / norm
-        interpolated_points = three_interpolate(points2, idx, weight)
-    if points1 is not None:
-        new_points1 = torch.cat([interpolated_points, points1], dim=2)  # B,ndataset1,nchannel1+nchannel2
-    else:
-        new_points1 = interpolated_points
+        if fused and not points2.requires_grad:
+            interpolated_points = three_nn_interpolate(xyz1, xyz2, points2)
+        else:
+            dist, idx = three_nn(xyz1, xyz2)
+            dist = torch.clamp(dist, min=1e-10)
+            norm = (1.0 / dist).sum(dim=2, keepdim=True)
+            weight = (1.0 / dist) / norm
+            interpolated_points = three_interpolate(points2, idx, weight)
+        if points1 is not None:
+            new_points1 = torch.cat([interpolated_points, points1], dim=2)  # B,ndataset1,nchannel1+nchannel2
+        else:
+            new_points1 = interpolated_points
     if mlp is not None:
         new_points1 = mlp(new_points1.unsqueeze(2)).squeeze(2)
     return new_points1

@@ -42,6 +42,11 @@ def three_nn(xyz1: torch.Tensor, xyz2: torch.Tensor):
     return dist, idx
 
 
+# three_interpolate's backward: True = inverse index + ordered sums (deterministic, bit-identical to the reference's CPU
+# function); False = the float-atomic scatter (the reference-signature pn2_three_interpolate_grad)
+DETERMINISTIC_GRAD = True
+
+
 class _ThreeInterpolate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, points, idx, weight):
@@ -63,12 +68,25 @@ class _ThreeInterpolate(torch.autograd.Function):
         b, m, c = ctx.shape
         n = idx.shape[1]
         grad_out = grad_out.contiguous()
+        lib = _lib.load()
+        dev = grad_out.device
+        if DETERMINISTIC_GRAD and b * m * c:
+            # inverse index + ordered accumulation: deterministic, bit-identical to threeinterpolate_grad_cpu
+            # (tf_interpolate.cpp:131-153), and ~3x faster than the atomics at the sem-seg sizes
+            grad_points = torch.empty((b, m, c), dtype=torch.float32, device=dev)
+            with on_device(grad_out):
+                wsb = int(lib.pn2_three_interpolate_grad_det_workspace_bytes(b, max(n, 1), m))
+                ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+                rc = lib.pn2_three_interpolate_grad_det(b, n, c, m, ptr(grad_out), ptr(idx), ptr(weight), ptr(grad_points),
+                                                        ptr(ws), wsb, stream_ptr(dev))
+            _lib.check(rc, "pn2_three_interpolate_grad_det")
+            return grad_points, None, None
         # zero-filled by the caller, as ThreeInterpolateGradOp does (tf_interpolate.cpp:258)
-        grad_points = torch.zeros((b, m, c), dtype=torch.float32, device=grad_out.device)
+        grad_points = torch.zeros((b, m, c), dtype=torch.float32, device=dev)
         if grad_out.numel():
             with on_device(grad_out):
-                rc = _lib.load().pn2_three_interpolate_grad(b, n, c, m, ptr(grad_out), ptr(idx), ptr(weight),
-                                                            ptr(grad_points), stream_ptr(grad_out.device))
+                rc = lib.pn2_three_interpolate_grad(b, n, c, m, ptr(grad_out), ptr(idx), ptr(weight),
+                                                    ptr(grad_points), stream_ptr(dev))
             _lib.check(rc, "pn2_three_interpolate_grad")
         return grad_points, None, None
 
@@ -131,4 +149,37 @@ def three_nn_interpolate(xyz1: torch.Tensor, xyz2: torch.Tensor, points2: torch.
         _lib.check(rc, "pn2_three_nn_interpolate")
     if return_aux:
         return out, dist, idx, weight
+    return out
+
+
+def fp_interpolate_concat(xyz1: torch.Tensor, xyz2: torch.Tensor, points1, points2: torch.Tensor) -> torch.Tensor:
+    """The front end of pointnet_fp_module in one kernel (utils/pointnet_util.py:211-219): three_nn, the
+    inverse-distance weights, three_interpolate AND the concat with ``points1``:
+    returns (b, n, c2 + c1) = [interpolated points2 | points1] (c1 = 0 when ``points1`` is None).  Forward only."""
+    xyz1 = require_cuda(xyz1, "xyz1", torch.float32)
+    xyz2 = require_cuda(xyz2, "xyz2", torch.float32)
+    points2 = require_cuda(points2, "points2", torch.float32)
+    same_device(xyz1, xyz2, points2)
+    if xyz1.dim() != 3 or xyz1.shape[2] != 3 or xyz2.dim() != 3 or xyz2.shape[2] != 3 or xyz1.shape[0] != xyz2.shape[0]:
+        raise ValueError("fp_interpolate_concat expects (b,n,3) xyz1 and (b,m,3) xyz2")
+    if points2.dim() != 3 or points2.shape[:2] != xyz2.shape[:2]:
+        raise ValueError("fp_interpolate_concat expects (b,m,c2) points2 matching xyz2")
+    b, n, _ = xyz1.shape
+    m, c2 = xyz2.shape[1], points2.shape[2]
+    c1 = 0
+    if points1 is not None:
+        points1 = require_cuda(points1, "points1", torch.float32)
+        same_device(xyz1, points1)
+        if points1.dim() != 3 or points1.shape[:2] != xyz1.shape[:2]:
+            raise ValueError("fp_interpolate_concat expects (b,n,c1) points1 matching xyz1")
+        c1 = points1.shape[2]
+    if m <= 0 or c2 <= 0:
+        raise ValueError("fp_interpolate_concat expects at least one known point and one channel")
+    out = torch.empty((b, n, c2 + c1), dtype=torch.float32, device=xyz1.device)
+    if b * n:
+        with on_device(xyz1):
+            rc = _lib.load().pn2_fp_interpolate_concat(b, n, m, c2, c1, ptr(xyz1), ptr(xyz2),
+                                                       ptr(points1.detach()) if c1 else None, ptr(points2.detach()), ptr(out),
+                                                       stream_ptr(xyz1.device))
+        _lib.check(rc, "pn2_fp_interpolate_concat")
     return out

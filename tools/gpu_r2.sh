@@ -15,14 +15,17 @@ for stage in "$@"; do
       timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/smoke.log ;;
     bench)
       timeout 900 python bench.py --steps 50 --warmup 5 > gpurun_out/bench_r2.json 2> gpurun_out/bench_r2.err; tail -c 600 gpurun_out/bench_r2.err; head -c 1500 gpurun_out/bench_r2.json ;;
+    benchquick)
+      timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; tail -c 400 gpurun_out/bench_quick.err
+      python tools/show_bench.py gpurun_out/bench_quick.json ;;
+    occupancy)
+      timeout 300 python tools/cluster_occupancy.py 2>&1 | tee gpurun_out/cluster_occupancy.txt | tail -80 ;;
     benchref)
       timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_ref_r2.json 2> gpurun_out/bench_ref_r2.err; head -c 600 gpurun_out/bench_ref_r2.json ;;
     report)
       timeout 1200 python bench.py --report gpurun_out/report_r2.json > gpurun_out/report_r2.log 2>&1; tail -3 gpurun_out/report_r2.log ;;
     sweep)
       PN2_SWEEP_LARGE=1 timeout 900 python bench.py --fps-sweep > gpurun_out/fps_sweep_large.log 2>&1; cp gpurun_out/fps_sweep.json gpurun_out/fps_sweep_large_r2.json 2>/dev/null; tail -3 gpurun_out/fps_sweep_large.log ;;
-    sweep262)
-      timeout 600 python tools/fps_large_bench.py > gpurun_out/fps_262k.log 2>&1; tail -20 gpurun_out/fps_262k.log ;;
     launches)
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-configs > gpurun_out/ncu_bench.log 2>&1; tail -2 gpurun_out/ncu_bench.log | head -c 300 ;;
     ncufull)
