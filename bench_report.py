@@ -270,6 +270,30 @@ def config_rows(torch, lib, dev, flush, peak, kind, world=1, rank=0, reps=10, fu
     feats = T(W.features(c3["b"], L1["npoint"], L2["c"], 103))
     for r, s in zip(L2["radii"], L2["nsamples"]):
         sa_layer("cfg3.L2", nx1, feats, L2["npoint"], r, s, xyz_first=False)
+
+    def msg_layer(tag, x, L):
+        """One pn2_sa_layer_msg_device call: the sampling pass + all three scales' ball query and xyz grouping."""
+        import ctypes
+        b, n, _ = x.shape
+        m, k = L["npoint"], len(L["radii"])
+        fi = torch.empty((b, m), dtype=torch.int32, device=dev)
+        nx = torch.empty((b, m, 3), dtype=torch.float32, device=dev)
+        idx = [torch.empty((b, m, s), dtype=torch.int32, device=dev) for s in L["nsamples"]]
+        cnt = [torch.empty((b, m), dtype=torch.int32, device=dev) for _ in L["nsamples"]]
+        grp = [torch.empty((b, m, s, 3), dtype=torch.float32, device=dev) for s in L["nsamples"]]
+        radii = (ctypes.c_float * k)(*L["radii"])
+        ns = (ctypes.c_int * k)(*L["nsamples"])
+        pi = (ctypes.c_void_p * k)(*[t.data_ptr() for t in idx])
+        pc = (ctypes.c_void_p * k)(*[t.data_ptr() for t in cnt])
+        pg = (ctypes.c_void_p * k)(*[t.data_ptr() for t in grp])
+        ms = timeit(torch, flush, lambda: lib.pn2_sa_layer_msg_device(b, n, m, k, radii, ns, x.data_ptr(), fi.data_ptr(), nx.data_ptr(), pi, pc, pg, 1,
+                                                                      None, 0, None), reps=reps)
+        nbytes = W.bytes_fps(b, n, m) + W.bytes_gather(b, m) + sum(W.bytes_ball_query(b, n, m, s) + W.bytes_group(b, n, m, s, 3) for s in L["nsamples"])
+        add(tag, f"sa_layer_msg_device (one sampling pass + {k} scales of ball query + group xyz, overlapped)", ms, nbytes,
+            dict(points_per_s=b * n / (ms * 1e-3)))
+
+    msg_layer("cfg3.L1", xyz, L1)
+    msg_layer("cfg3.L2", nx1, L2)
     del feats
     # cfg4 sem-seg: SA chain + FP chain.  --report: B=16 on one GPU and the 2-clouds-per-GPU shard;
     # driver line: this rank's shard of the 16 clouds

@@ -203,6 +203,16 @@ int pn2_ball_group(int b, int n, int m, float radius, int nsample, const float* 
  * and the ball-query grid.  Independent batches may be issued on different streams: one layer
  * occupies 2*b SMs. */
 size_t pn2_sa_layer_device_workspace_bytes(int b, int n, int m, int nsample);
+/* The multi-scale form (pointnet_sa_module_msg, utils/pointnet_util.py:156-196: ONE farthest_point_sample +
+ * gather_point, then query_ball_point + group_point(xyz) per scale): radii / nsamples / idx / pts_cnt /
+ * grouped_xyz are HOST arrays of nscales (<= 16) entries (grouped_xyz, or any entry of it, may be NULL).
+ * On the overlapped path every scale's grouping grid runs while the sampling chain is still going. */
+int pn2_sa_layer_msg_device(int b, int n, int m, int nscales, const float* radii, const int* nsamples,
+                            const float* xyz, int* fps_idx, float* new_xyz, int* const* idx,
+                            int* const* pts_cnt, float* const* grouped_xyz, int center, void* workspace,
+                            size_t workspace_bytes, void* stream);
+/* tuning: grouping CTAs per cloud and scale on the overlapped path (0 = automatic: one) */
+void pn2_set_sa_consumer_ctas(int ctas_per_cloud);
 int pn2_sa_layer_device(int b, int n, int m, float radius, int nsample, const float* xyz, int* fps_idx,
                         float* new_xyz, int* idx, int* pts_cnt, float* grouped_xyz, int center,
                         void* workspace, size_t workspace_bytes, void* stream);

@@ -15,7 +15,7 @@ from . import _lib  # noqa: F401  (does not load the library until an op is call
 from .tf_sampling import farthest_point_sample, farthest_point_sample_and_gather, gather_point, prob_sample  # noqa: F401
 from .tf_grouping import group_point, knn_point, query_ball_point, select_top_k  # noqa: F401
 from .tf_interpolate import fp_interpolate_concat, three_interpolate, three_nn, three_nn_interpolate  # noqa: F401
-from .sa_layer import SetAbstractionDevice, ball_group, sample_group  # noqa: F401
+from .sa_layer import SetAbstractionDevice, ball_group, sample_group, sample_group_msg  # noqa: F401
 from .pointnet_util import (  # noqa: F401
     group_and_concat,
     pointnet_fp_module,

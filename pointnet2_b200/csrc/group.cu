@@ -177,7 +177,8 @@ template <int UNR>
 __global__ void __launch_bounds__(kCopyThreads)
 group_concat_flat_kernel(int n, int c, int nsample, unsigned rows_per_cloud, const float* __restrict__ xyz,
                          const float* __restrict__ new_xyz, const float* __restrict__ points, const int* __restrict__ idx,
-                         int xyz_lo, int feat_lo, float* __restrict__ out, float* __restrict__ grouped_xyz, unsigned magic) {
+                         int xyz_lo, int feat_lo, float* __restrict__ out, float* __restrict__ grouped_xyz, unsigned magic,
+                         unsigned rb) {  // rb = rows per warp block (1..32): small for wide rows / few rows, so every SM gets warps
     const int lane = threadIdx.x & 31;
     const unsigned cloud = blockIdx.y;
     const unsigned w = (unsigned)c + 3u;
@@ -189,8 +190,8 @@ group_concat_flat_kernel(int n, int c, int nsample, unsigned rows_per_cloud, con
     const float* __restrict__ cpts = points + (size_t)cloud * n * c;
     const float* __restrict__ cxyz = xyz + (size_t)cloud * n * 3;
     const float* __restrict__ cctr = new_xyz + (size_t)cloud * m * 3;
-    for (unsigned r0 = warp * 32u; r0 < rows_per_cloud; r0 += warps * 32u) {
-        const unsigned nrows = min(32u, rows_per_cloud - r0);
+    for (unsigned r0 = warp * rb; r0 < rows_per_cloud; r0 += warps * rb) {
+        const unsigned nrows = min(rb, rows_per_cloud - r0);
         const unsigned r = r0 + lane;
         int a = 0;
         float vx = 0.f, vy = 0.f, vz = 0.f;
@@ -209,12 +210,13 @@ group_concat_flat_kernel(int n, int c, int nsample, unsigned rows_per_cloud, con
             __stcs(d + 1, vy);
             __stcs(d + 2, vz);
         }
-        if (grouped_xyz) {  // the 32 triples are one run of 96 floats: transpose through shuffles, 3 coalesced stores
+        if (grouped_xyz) {  // the block's triples are one run of 3*nrows floats: transpose through shuffles, coalesced stores
             float* __restrict__ g = grouped_xyz + (cloud_row0 + r0) * 3;
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
                 const unsigned t = (unsigned)lane + 32u * j, row = t / 3u, comp = t - 3u * row;
-                const float x = __shfl_sync(kFullMask, vx, row), y = __shfl_sync(kFullMask, vy, row), z = __shfl_sync(kFullMask, vz, row);
+                const float x = __shfl_sync(kFullMask, vx, row & 31u), y = __shfl_sync(kFullMask, vy, row & 31u),
+                            z = __shfl_sync(kFullMask, vz, row & 31u);
                 if (row < nrows) __stcs(g + t, comp == 0 ? x : (comp == 1 ? y : z));
             }
         }
@@ -287,14 +289,18 @@ static int launch_group_rows(int b, int n, int c, int m, int nsample, const floa
     }
     if (HAS_XYZ && c > 0 && w <= 8192) {  // (the multiply-high row lookup is exact for 32*w*w < 2^32)
         // fused tail with features: flat 32-row blocks (see group_concat_flat_kernel)
-        const unsigned blocks_needed = (rpc + 32u * (kCopyThreads / 32) - 1) / (32u * (kCopyThreads / 32));
-        unsigned gx = blocks_needed;
-        const unsigned cap = (148u * 16u + b - 1) / b;
+        // rows per warp block: ~1024 floats per block for wide rows, and never so many that the machine
+        // (148 SMs x 64 warps) is left with fewer blocks than warp slots
+        unsigned rb = 32;
+        while (rb > 1 && ((unsigned long long)rb * w > 1536ull || (unsigned long long)b * rpc / rb < 2ull * 148 * 64)) rb >>= 1;
+        const unsigned rows_per_cta = rb * (kCopyThreads / 32);
+        unsigned gx = (rpc + rows_per_cta - 1) / rows_per_cta;
+        const unsigned cap = (148u * 32u + b - 1) / b;
         if (gx > cap) gx = cap;
         if (gx < 1) gx = 1;
         const unsigned magic = (unsigned)((0x100000000ull + (unsigned)w - 1) / (unsigned)w);  // ceil(2^32 / w)
-        group_concat_flat_kernel<4><<<dim3(gx, b, 1), kCopyThreads, 0, st>>>(n, c, nsample, rpc, xyz, new_xyz, points, idx, xyz_lo, feat_lo,
-                                                                              out, grouped_xyz, magic);
+        group_concat_flat_kernel<8><<<dim3(gx, b, 1), kCopyThreads, 0, st>>>(n, c, nsample, rpc, xyz, new_xyz, points, idx, xyz_lo, feat_lo,
+                                                                              out, grouped_xyz, magic, rb);
         return finish_launch();
     }
     const int lpr = w <= 4 ? 4 : (w <= 8 ? 8 : (w <= 16 ? 16 : 32));

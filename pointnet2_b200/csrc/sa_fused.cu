@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kBgThreads, 1)
 ball_group_kernel(int n, int m, float radius, float thr, int nsample, const float* __restrict__ xyz1,
                   const float* __restrict__ xyz2, const int* q_idx, int* __restrict__ idx,
                   int* __restrict__ pts_cnt, float* __restrict__ grouped, int center, int ctas_per_cloud,
-                  int wait_primary) {
+                  int wait_primary, int trigger_next) {
     constexpr int T = kBgThreads, NW = kBgWarps;
     extern __shared__ __align__(16) unsigned char s_raw[];
     float4* __restrict__ s_pts = reinterpret_cast<float4*>(s_raw);                     // [n]
@@ -91,6 +91,9 @@ ball_group_kernel(int n, int m, float radius, float thr, int nsample, const floa
     __shared__ int s_wsum[32];
     __shared__ float4 s_first[NW];
 
+    // multi-scale grouping chains several of these grids behind one sampling kernel: let the next one start
+    // as soon as this one is resident (it polls the same index buffer)
+    if (trigger_next) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cloud = blockIdx.x / ctas_per_cloud, part = blockIdx.x - cloud * ctas_per_cloud;
     const float* __restrict__ pts = xyz1 + (size_t)cloud * n * 3;
@@ -295,7 +298,7 @@ ball_group_kernel(int n, int m, float radius, float thr, int nsample, const floa
                 }
             }
             const int len = (sub == 0) ? p1 - p : 0;
-            const int total = __reduce_add_sync(kFullMask, len), longest = __reduce_max_sync(kFullMask, len);
+            const int total = 0, longest = __reduce_max_sync(kFullMask, len);
             int hcount = 0;
             auto test = [&](bool active, int pos) {  // one candidate per active lane; warp-uniform overflow flag
                 bool hit = false;
@@ -313,8 +316,9 @@ ball_group_kernel(int n, int m, float radius, float thr, int nsample, const floa
                 }
                 return hcount > kBgHitCap;
             };
-            bool overflow = 2 * total > n;  // the neighbourhood is most of the cloud (a cell of coincident points): scan instead
-            if (!overflow) {
+            bool overflow = false;
+            (void)total;
+            {
                 if (longest <= 48) {
                     // balanced ranges: lanes 3r..3r+2 walk range r with stride 3
                     p += sub;
@@ -419,7 +423,7 @@ struct BgOnce {
 
 static int launch_ball_group(int b, int n, int m, float radius, float thr, int nsample, const float* xyz1, const float* xyz2,
                              const int* q_idx, int* idx, int* pts_cnt, float* grouped, int center, int ctas_per_cloud,
-                             bool dependent, cudaStream_t st) {
+                             bool dependent, bool trigger_next, cudaStream_t st) {
     static BgOnce once;
     size_t dyn = bg_smem_bytes(n);
     if (dyn > kBgSmemMax) return (int)cudaErrorInvalidValue;
@@ -456,13 +460,25 @@ static int launch_ball_group(int b, int n, int m, float radius, float thr, int n
     cfg.attrs = attr;
     cfg.numAttrs = dependent ? 1 : 0;
     e = cudaLaunchKernelEx(&cfg, ball_group_kernel, n, m, radius, thr, nsample, xyz1, xyz2, q_idx, idx, pts_cnt, grouped, center,
-                           ctas_per_cloud, dependent ? 1 : 0);
+                           ctas_per_cloud, dependent ? 1 : 0, trigger_next ? 1 : 0);
     count_launch();
     if (e != cudaSuccess) return (int)e;
     return (int)cudaGetLastError();
 }
 
 static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+// Consumer CTAs per cloud and scale in the overlapped layer.  One is enough to keep up with the sampling chain
+// when balls are sparse (cfg2: the layer ends 4 us after the sampling kernel); it leaves the other SMs to
+// further batches on other streams.  pn2_set_sa_consumer_ctas overrides (0 = automatic).
+static std::atomic<int> g_sa_consumer_ctas{0};
+static int sa_consumer_ctas(int b, int nscales) {
+    int r = g_sa_consumer_ctas.load(std::memory_order_relaxed);
+    const int room = (148 - (b < 148 ? b : 148)) / ((b < 148 ? b : 148) * nscales);  // SMs left per cloud and scale
+    if (r <= 0) r = 1;
+    if (r > room) r = room;
+    return r < 1 ? 1 : r;
+}
 
 }  // namespace pn2
 
@@ -486,7 +502,7 @@ int pn2_ball_group(int b, int n, int m, float radius, int nsample, const float* 
     const int rmax = (m + kBgWarps - 1) / kBgWarps;
     if (r > rmax) r = rmax;
     if (r < 1) r = 1;
-    return launch_ball_group(b, n, m, radius, thr, nsample, xyz1, xyz2, nullptr, idx, pts_cnt, grouped_xyz, center, r, false,
+    return launch_ball_group(b, n, m, radius, thr, nsample, xyz1, xyz2, nullptr, idx, pts_cnt, grouped_xyz, center, r, false, false,
                              as_stream(stream));
 }
 
@@ -498,20 +514,28 @@ size_t pn2_sa_layer_device_workspace_bytes(int b, int n, int m, int nsample) {
     return pn2::align256(pn2_fps_scratch_bytes(b, n)) + pn2::align256(pn2_query_ball_point_workspace_bytes(b, n));
 }
 
-int pn2_sa_layer_device(int b, int n, int m, float radius, int nsample, const float* xyz, int* fps_idx, float* new_xyz,
-                        int* idx, int* pts_cnt, float* grouped_xyz, int center, void* workspace, size_t workspace_bytes,
-                        void* stream) {
+int pn2_sa_layer_msg_device(int b, int n, int m, int nscales, const float* radii, const int* nsamples, const float* xyz,
+                            int* fps_idx, float* new_xyz, int* const* idx, int* const* pts_cnt, float* const* grouped_xyz,
+                            int center, void* workspace, size_t workspace_bytes, void* stream) {
     using namespace pn2;
-    if (b < 0 || n <= 0 || m < 0 || nsample <= 0 || !(radius > 0.0f)) return (int)cudaErrorInvalidValue;
+    if (b < 0 || n <= 0 || m < 0 || nscales <= 0 || nscales > 16 || !radii || !nsamples || !idx || !pts_cnt)
+        return (int)cudaErrorInvalidValue;
+    for (int k = 0; k < nscales; ++k)
+        if (nsamples[k] <= 0 || !(radii[k] > 0.0f) || !idx[k] || !pts_cnt[k]) return (int)cudaErrorInvalidValue;
     if (b == 0 || m == 0) return 0;
-    if (!xyz || !fps_idx || !new_xyz || !idx || !pts_cnt) return (int)cudaErrorInvalidValue;
+    if (!xyz || !fps_idx || !new_xyz) return (int)cudaErrorInvalidValue;
     cudaStream_t st = as_stream(stream);
-    const float thr = pn2_ball_threshold(radius);
-    if (fps_single_cta(b, n) && pn2_ball_group_fits(n) && thr >= 0.0f) {
-        // overlapped pair: sampling (one CTA per cloud) + dependent ball_group grid (one CTA per cloud)
+    bool overlapped = fps_single_cta(b, n) && pn2_ball_group_fits(n);
+    for (int k = 0; k < nscales; ++k) overlapped = overlapped && pn2_ball_threshold(radii[k]) >= 0.0f;
+    if (overlapped) {
+        // sampling (one CTA per cloud) + one dependent ball_group grid per scale, chained so that all of them
+        // are resident while the sampling chain runs
         int rc = fps_dispatch(b, n, m, xyz, nullptr, fps_idx, new_xyz, /*sentinel=*/1, st);
-        if (rc) return rc;
-        return launch_ball_group(b, n, m, radius, thr, nsample, xyz, nullptr, fps_idx, idx, pts_cnt, grouped_xyz, center, 1, true, st);
+        const int r = sa_consumer_ctas(b, nscales);
+        for (int k = 0; k < nscales && rc == 0; ++k)
+            rc = launch_ball_group(b, n, m, radii[k], pn2_ball_threshold(radii[k]), nsamples[k], xyz, nullptr, fps_idx, idx[k], pts_cnt[k],
+                                   grouped_xyz ? grouped_xyz[k] : nullptr, center, r, true, k + 1 < nscales, st);
+        return rc;
     }
     // sequential path (clustered / global-scratch sampling, or clouds too large for the in-smem grid)
     const size_t fps_b = align256(pn2_fps_scratch_bytes(b, n)), bq_b = pn2_query_ball_point_workspace_bytes(b, n);
@@ -524,11 +548,27 @@ int pn2_sa_layer_device(int b, int n, int m, float radius, int nsample, const fl
     }
     if (bq_b && ws && workspace_bytes >= fps_b + bq_b) bq_ws = ws + fps_b;
     int rc = pn2_fps_gather(b, n, m, xyz, temp, fps_idx, new_xyz, stream);
-    if (rc) return rc;
-    rc = pn2_query_ball_point_ws(b, n, m, radius, nsample, xyz, new_xyz, idx, pts_cnt, bq_ws, bq_ws ? bq_b : 0, stream);
-    if (rc || !grouped_xyz) return rc;
-    if (center) return pn2_group_concat(b, n, 0, m, nsample, xyz, new_xyz, nullptr, idx, 1, grouped_xyz, nullptr, stream);
-    return pn2_group_point(b, n, 3, m, nsample, xyz, idx, grouped_xyz, stream);
+    for (int k = 0; k < nscales && rc == 0; ++k) {
+        rc = pn2_query_ball_point_ws(b, n, m, radii[k], nsamples[k], xyz, new_xyz, idx[k], pts_cnt[k], bq_ws, bq_ws ? bq_b : 0, stream);
+        float* g = grouped_xyz ? grouped_xyz[k] : nullptr;
+        if (rc || !g) continue;
+        rc = center ? pn2_group_concat(b, n, 0, m, nsamples[k], xyz, new_xyz, nullptr, idx[k], 1, g, nullptr, stream)
+                    : pn2_group_point(b, n, 3, m, nsamples[k], xyz, idx[k], g, stream);
+    }
+    return rc;
 }
+
+int pn2_sa_layer_device(int b, int n, int m, float radius, int nsample, const float* xyz, int* fps_idx, float* new_xyz,
+                        int* idx, int* pts_cnt, float* grouped_xyz, int center, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+    if (!idx || !pts_cnt) return (int)cudaErrorInvalidValue;
+    int* idxs[1] = {idx};
+    int* cnts[1] = {pts_cnt};
+    float* grps[1] = {grouped_xyz};
+    return pn2_sa_layer_msg_device(b, n, m, 1, &radius, &nsample, xyz, fps_idx, new_xyz, idxs, cnts, grouped_xyz ? grps : nullptr, center,
+                                   workspace, workspace_bytes, stream);
+}
+
+void pn2_set_sa_consumer_ctas(int ctas_per_cloud) { pn2::g_sa_consumer_ctas.store(ctas_per_cloud, std::memory_order_relaxed); }
 
 }  // extern "C"

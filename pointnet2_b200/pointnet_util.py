@@ -23,7 +23,7 @@ from . import _lib
 from ._tensor import on_device, ptr, require_cuda, same_device, stream_ptr
 from .tf_grouping import group_point, knn_point, query_ball_point
 from .tf_interpolate import fp_interpolate_concat, three_interpolate, three_nn, three_nn_interpolate
-from .sa_layer import sample_group
+from .sa_layer import sample_group, sample_group_msg
 from .tf_sampling import farthest_point_sample, farthest_point_sample_and_gather, gather_point
 
 
@@ -202,24 +202,37 @@ def pointnet_sa_module_msg(xyz, points, npoint, radius_list: Sequence[float], ns
         centre, concat in the MSG order [features, xyz] (:184), MLP, max-pool; scales concatenated.
         Return: new_xyz (b,npoint,3), new_points (b,npoint,sum of channels)
     '''
-    if fused and not xyz.requires_grad:
+    pre = None
+    if fused and not xyz.requires_grad and (points is None or use_xyz):
+        # one call: the sampling pass and every scale's ball query (+ centred grouped xyz when they are the features)
+        _, new_xyz, idx_list, _, gxyz_list = sample_group_msg(npoint, radius_list, nsample_list, xyz, center=True,
+                                                              want_grouped=points is None)
+        pre = (idx_list, gxyz_list)
+    elif fused and not xyz.requires_grad:
         _, new_xyz = farthest_point_sample_and_gather(npoint, xyz)
     else:
         new_xyz = gather_point(xyz, farthest_point_sample(npoint, xyz))
     new_points_list = []
     for i in range(len(radius_list)):
         radius, nsample = radius_list[i], nsample_list[i]
-        idx, pts_cnt = query_ball_point(radius, nsample, xyz, new_xyz)
-        if fused and (points is None or use_xyz):
-            grouped_points, _ = group_and_concat(xyz, new_xyz, points, idx, xyz_first=False)
-        else:
-            grouped_xyz = group_point(xyz, idx) - new_xyz.unsqueeze(2)
-            if points is not None:
-                grouped_points = group_point(points, idx)
-                if use_xyz:
-                    grouped_points = torch.cat([grouped_points, grouped_xyz], dim=-1)
+        if pre is not None:
+            idx = pre[0][i]
+            if points is None:
+                grouped_points = pre[1][i]
             else:
-                grouped_points = grouped_xyz
+                grouped_points, _ = group_and_concat(xyz, new_xyz, points, idx, xyz_first=False)
+        else:
+            idx, pts_cnt = query_ball_point(radius, nsample, xyz, new_xyz)
+            if fused and (points is None or use_xyz):
+                grouped_points, _ = group_and_concat(xyz, new_xyz, points, idx, xyz_first=False)
+            else:
+                grouped_xyz = group_point(xyz, idx) - new_xyz.unsqueeze(2)
+                if points is not None:
+                    grouped_points = group_point(points, idx)
+                    if use_xyz:
+                        grouped_points = torch.cat([grouped_points, grouped_xyz], dim=-1)
+                else:
+                    grouped_points = grouped_xyz
         grouped_points = _apply_mlp(None if mlp_list is None else mlp_list[i], grouped_points)
         new_points_list.append(grouped_points.max(dim=2).values)
     return new_xyz, torch.cat(new_points_list, dim=-1)

@@ -67,6 +67,42 @@ def sample_group(npoint: int, radius: float, nsample: int, xyz: torch.Tensor, ce
     return fps_idx, new_xyz, idx, pts_cnt, grouped
 
 
+def sample_group_msg(npoint: int, radius_list, nsample_list, xyz: torch.Tensor, center: bool = True, want_grouped: bool = True):
+    """The multi-scale form (pointnet_sa_module_msg, utils/pointnet_util.py:156-196): ONE sampling pass, then a
+    ball query + xyz grouping per scale — one C-ABI call, every scale's grouping grid overlapping the sampling chain.
+
+    Returns (fps_idx, new_xyz, [idx_k], [pts_cnt_k], [grouped_xyz_k] or None)."""
+    import ctypes
+    if len(radius_list) != len(nsample_list) or not len(radius_list):
+        raise ValueError("radius_list and nsample_list must be non-empty and of equal length")
+    k = len(radius_list)
+    npoint, _, _, xyz = _check_layer_args(npoint, radius_list[0], nsample_list[0], xyz)
+    for r, s in zip(radius_list, nsample_list):
+        _check_layer_args(npoint, r, s, xyz)
+    b, n, _ = xyz.shape
+    dev = xyz.device
+    fps_idx = torch.empty((b, npoint), dtype=torch.int32, device=dev)
+    new_xyz = torch.empty((b, npoint, 3), dtype=torch.float32, device=dev)
+    idx = [torch.empty((b, npoint, int(s)), dtype=torch.int32, device=dev) for s in nsample_list]
+    cnt = [torch.empty((b, npoint), dtype=torch.int32, device=dev) for _ in nsample_list]
+    grouped = [torch.empty((b, npoint, int(s), 3), dtype=torch.float32, device=dev) for s in nsample_list] if want_grouped else None
+    if b == 0:
+        return fps_idx, new_xyz, idx, cnt, grouped
+    lib = _lib.load()
+    radii = (ctypes.c_float * k)(*[float(r) for r in radius_list])
+    nsamples = (ctypes.c_int * k)(*[int(s) for s in nsample_list])
+    pidx = (ctypes.c_void_p * k)(*[t.data_ptr() for t in idx])
+    pcnt = (ctypes.c_void_p * k)(*[t.data_ptr() for t in cnt])
+    pgrp = (ctypes.c_void_p * k)(*[t.data_ptr() for t in grouped]) if want_grouped else None
+    with on_device(xyz):
+        wsb = int(lib.pn2_sa_layer_device_workspace_bytes(b, n, npoint, max(int(s) for s in nsample_list)))
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev) if wsb else None
+        rc = lib.pn2_sa_layer_msg_device(b, n, npoint, k, radii, nsamples, ptr(xyz.detach()), ptr(fps_idx), ptr(new_xyz), pidx, pcnt, pgrp,
+                                         1 if center else 0, ptr(ws), wsb, stream_ptr(dev))
+    _lib.check(rc, "pn2_sa_layer_msg_device")
+    return fps_idx, new_xyz, idx, cnt, grouped
+
+
 def ball_group(radius: float, nsample: int, xyz1: torch.Tensor, xyz2: torch.Tensor, center: bool = True,
                want_grouped: bool = True):
     """query_ball_point(radius, nsample, xyz1, xyz2) + group_point(xyz1, idx) [- xyz2] in one launch.

@@ -40,12 +40,17 @@ def test_fp_interpolate_concat_matches_unfused(dev, b, n, m, c2, c1):
     p1 = T(W.features(b, n, c1, 204), dev) if c1 else None
     got = fp_interpolate_concat(x1, x2, p1, p2)
     want = unfused_fp(x1, x2, p1, p2)
-    # the three_nn part is bit-exact; weights go through the same IEEE divisions -> whole result bit-exact
-    assert torch.equal(got, want)
-    assert torch.equal(pointnet_fp_module(x1, x2, p1, p2), want)
+    # neighbours and distances are bit-exact; the weights' 3-term sum is (r1+r2)+r3 here and whatever order torch's
+    # reduction uses in the unfused path, so the interpolated half is compared at the contract's 1e-5 ...
+    assert float((got[..., :c2] - want[..., :c2]).abs().max()) <= 1e-5 * max(1.0, float(want[..., :c2].abs().max()))
+    if c1:
+        assert torch.equal(got[..., c2:], p1)  # ... and the concatenated half is a copy
+    assert torch.equal(pointnet_fp_module(x1, x2, p1, p2), got)
     out, d, i, w = three_nn_interpolate(x1, x2, p2, return_aux=True)
     wd, wi = three_nn(x1, x2)
-    assert torch.equal(d, wd) and torch.equal(i, wi) and torch.equal(out, want[..., :c2])
+    assert torch.equal(d, wd) and torch.equal(i, wi)
+    # with the kernel's own weights the interpolation is bit-exact against the stand-alone op (and the oracle)
+    assert torch.equal(out, three_interpolate(p2, i, w)) and torch.equal(out, got[..., :c2])
 
 
 def test_fp_interpolate_concat_with_duplicate_known_points(dev):

@@ -12,7 +12,7 @@ import torch
 from oracle import oracle as O
 from pointnet2_b200 import _lib, workloads as W
 from pointnet2_b200.host import SetAbstractionHost
-from pointnet2_b200.sa_layer import SetAbstractionDevice, ball_group, sample_group
+from pointnet2_b200.sa_layer import SetAbstractionDevice, ball_group, sample_group, sample_group_msg
 from pointnet2_b200.tf_grouping import group_point, query_ball_point
 from pointnet2_b200.tf_sampling import farthest_point_sample, gather_point
 
@@ -145,6 +145,28 @@ def test_several_batches_in_flight(dev):
     for got, want in zip(out, wants):
         for a, w in zip(got, want):
             assert torch.equal(a, w)
+
+
+@pytest.mark.parametrize("gen,b,n,m,radii,nsamples", [("S", 32, 1024, 512, [0.1, 0.2, 0.4], [16, 32, 128]),   # cfg3 layer 1
+                                                      ("S", 32, 512, 128, [0.2, 0.4, 0.8], [32, 64, 128]),    # cfg3 layer 2
+                                                      ("U", 3, 4096, 300, [0.05, 0.3], [8, 40]),
+                                                      ("D", 2, 16384, 256, [0.1, 0.2], [16, 32])])             # sequential fallback
+@pytest.mark.parametrize("ctas", [0, 2])
+def test_multi_scale_layer_is_bit_identical_to_the_separate_ops(dev, gen, b, n, m, radii, nsamples, ctas):
+    x = T(W.DISTRIBUTIONS[gen](b, n, 59), dev)
+    lib = _lib.load()
+    lib.pn2_set_sa_consumer_ctas(ctas)
+    try:
+        fi, nx, idxs, cnts, grps = sample_group_msg(m, radii, nsamples, x, center=True)
+    finally:
+        lib.pn2_set_sa_consumer_ctas(0)
+    wfi = farthest_point_sample(m, x)
+    wnx = gather_point(x, wfi)
+    assert torch.equal(fi, wfi) and torch.equal(nx, wnx)
+    for r, s, idx, cnt, g in zip(radii, nsamples, idxs, cnts, grps):
+        widx, wcnt = query_ball_point(r, s, x, wnx)
+        assert torch.equal(idx, widx) and torch.equal(cnt, wcnt)
+        assert torch.equal(g, group_point(x, widx) - wnx.unsqueeze(2))
 
 
 @pytest.mark.parametrize("n,m", [(16384, 512), (12000, 128)])

@@ -8,7 +8,7 @@ for stage in "$@"; do
   echo "=== stage $stage ($(date +%T))"
   case "$stage" in
     newtests)
-      timeout 600 python -m pytest tests/test_sa_fused_gpu.py tests/test_full_size_parity_gpu.py -x -q -m gpu 2>&1 | tail -40 | tee gpurun_out/newtests.log ;;
+      timeout 600 python -m pytest tests/test_sa_fused_gpu.py tests/test_fp_and_concat_gpu.py tests/test_full_size_parity_gpu.py -q -m gpu 2>&1 | tail -40 | tee gpurun_out/newtests.log ;;
     alltests)
       timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -40 | tee gpurun_out/alltests.log ;;
     smoke)
@@ -30,6 +30,9 @@ for stage in "$@"; do
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-configs > gpurun_out/ncu_bench.log 2>&1; tail -2 gpurun_out/ncu_bench.log | head -c 300 ;;
     ncufull)
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:'fps_cta_kernel|ball_group_kernel' -s 4 -c 4 -o gpurun_out/r2_prof_layer python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-configs > gpurun_out/ncu_full.log 2>&1; tail -2 gpurun_out/ncu_full.log | head -c 300 ;;
+    prof_*)
+      c=${stage#prof_}
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:'ball_group|fps_c|group_concat|group_rows|three_interp|fp_front|knn_kernel|inv_' -c 8 -f -o gpurun_out/r2_prof_$c python tools/prof_kernels.py $c 3 > gpurun_out/prof_$c.log 2>&1; tail -2 gpurun_out/prof_$c.log | head -c 300 ;;
     sanitize)
       timeout 900 compute-sanitizer --tool memcheck python tools/sanitize_smoke.py > gpurun_out/sanitize_mem.log 2>&1; tail -3 gpurun_out/sanitize_mem.log
       timeout 900 compute-sanitizer --tool racecheck python tools/sanitize_smoke.py > gpurun_out/sanitize_race.log 2>&1; tail -3 gpurun_out/sanitize_race.log ;;
