@@ -48,6 +48,12 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def source_signature() -> str:
+    """Names the state of the sources a library is built from (newest modification time + file count)."""
+    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS + [__file__]
+    return f"{max(os.path.getmtime(d) for d in deps):.6f}:{len(deps)}"
+
+
 def _compile_one(nvcc: str, src: str, verbose: bool) -> str:
     obj = os.path.join(BUILD_DIR, os.path.splitext(src)[0] + ".o")
     srcp = os.path.join(CSRC, src)

@@ -75,18 +75,37 @@ def load() -> ctypes.CDLL:
     world = int(os.environ.get("WORLD_SIZE", "1") or "1")
     local_rank = int(os.environ.get("LOCAL_RANK", "0") or "0")
     if world > 1:
-        # one process per GPU: never race on the build tree.  A present library is used as is; a
-        # missing one is built by local rank 0 while the other ranks wait for it to appear.
-        if not os.path.exists(path):
-            if local_rank == 0:
-                _build.build()
+        # one process per GPU: never race on the build tree.  Local rank 0 checks staleness and rebuilds (the
+        # library is published with an atomic rename), then writes a stamp naming the source state it was built
+        # from; the other local ranks wait for a stamp that matches the sources THEY see, so a library older
+        # than the .cu files is never loaded silently.
+        want = _build.source_signature()
+        stamp = path + ".stamp"
+        if local_rank == 0:
+            if _build.is_stale():
+                try:
+                    _build.build()
+                except Exception as e:
+                    if not os.path.exists(path):
+                        raise ImportError(f"libpn2_b200.so is missing and could not be built: {e}") from e
+                    want = "prebuilt"  # no nvcc on this box: the library that travelled is what there is
+            tmp = stamp + f".tmp{os.getpid()}"
+            with open(tmp, "w") as f:
+                f.write(want)
+            os.replace(tmp, stamp)
+        else:
+            import time
+            deadline = time.time() + 600
+            while time.time() < deadline:
+                try:
+                    got = open(stamp).read()
+                except OSError:
+                    got = None
+                if got in (want, "prebuilt") and os.path.exists(path):
+                    break
+                time.sleep(0.2)
             else:
-                import time
-                deadline = time.time() + 600
-                while not os.path.exists(path) and time.time() < deadline:
-                    time.sleep(0.5)
-                if not os.path.exists(path):
-                    raise ImportError("libpn2_b200.so was not built by local rank 0 within 10 minutes")
+                raise ImportError("libpn2_b200.so was not (re)built by local rank 0 within 10 minutes")
     elif _build.is_stale():
         try:
             _build.build()

@@ -492,9 +492,16 @@ static int launch_cta(int b, int n, int m, const float* inp, int* out, float* ne
     static AttrOnce once;
     auto kern = fps_cta_kernel<P, T>;
     // the opt-in is set for the largest cloud this instantiation can serve, so one call per device is enough
-    const size_t dyn = (size_t)n * 3 * sizeof(float), dyn_max = (size_t)P * T * 3 * sizeof(float);
+    size_t dyn = (size_t)n * 3 * sizeof(float);
     if (dyn > 200 * 1024) return (int)cudaErrorInvalidValue;
-    cudaError_t e = ensure_attrs(once, kern, dyn_max > 200 * 1024 ? 200 * 1024 : dyn_max, false);
+    // One sampling CTA per SM whenever the SMs are there (b <= 74): the chain is bound by instruction issue on
+    // its SM, so a second sampling CTA of ANOTHER batch (another stream) placed on the same SM slows both down —
+    // which is what the block scheduler does when resources allow (measured: the host-buffer pipeline swung
+    // between 0.34 and 0.51 ms/step with the in-flight depth).  Asking for more than half of the SM's shared
+    // memory makes that placement impossible; the other SMs are there for the other batches.
+    constexpr size_t kExclusive = 116 * 1024;
+    if (2 * b <= 148 && dyn < kExclusive) dyn = kExclusive;
+    cudaError_t e = ensure_attrs(once, kern, 200 * 1024, false);
     if (e != cudaSuccess) return (int)e;
     kern<<<b, T, dyn, st>>>(n, m, inp, out, new_xyz, sentinel);
     return finish_launch();

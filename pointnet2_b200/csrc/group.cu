@@ -20,6 +20,8 @@ namespace pn2 {
 
 constexpr int kCopyThreads = 256;
 
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 // ---- gather_point: out[b,j,:] = inp[b,idx[b,j],:] (3 floats) -----------------------------------
 __global__ void __launch_bounds__(kCopyThreads)
 gather_point_kernel(int n, int m, long long total, const float* __restrict__ inp, const int* __restrict__ idx,
@@ -163,80 +165,98 @@ group_rows_kernel(int n, int c, int nsample, unsigned rows_per_cloud, const floa
     }
 }
 
-// ---- the fused sample_and_group tail with features (c > 0): one warp per block of 32 output rows ----
-// Output rows are w = 3 + c floats wide — 67, 131, 259, 323 in the reference's networks — so they are
-// not 16-byte aligned, but CONSECUTIVE ROWS ARE CONTIGUOUS: a block of 32 rows is one run of 32*w
-// floats.  The warp reads its 32 row indices (and computes the 32 centred xyz triples, one row per
-// lane) up front, then walks the run flat: lane l handles floats l, l+32, ... of the run, finds its
-// (row, channel) with one multiply-high, fetches the row's index by shuffle and copies one word —
-// every store instruction covers 128 consecutive bytes whatever w is, there are no partial chunks at
-// row ends, and UNR independent gathers are in flight per lane (round 1's row-at-a-time kernel had one
-// index -> gather -> store chain per warp and reached 17 % of the HBM peak at w = 67).  The 3 xyz words of
-// each row are written by that row's lane (they are 3 of w words: 32 scattered words per store).
-template <int UNR>
+// ---- the fused sample_and_group tail with features, c % 4 == 0: 16-byte gathers AND 16-byte stores ----
+// Output rows are w = 3 + c floats wide (67, 131, 259, 323 in the reference's networks), so a row's feature
+// segment starts 0..3 floats past a 16-byte boundary — differently for every row.  The source rows ARE
+// aligned (c % 4 == 0): lane k of the row's lane group loads source vector k (LDG.128); the output vector
+// that starts `head` floats into the segment is the last 4-head floats of source vector k followed by the
+// first head floats of vector k+1, which the lane gets from its neighbour by shuffle (the last lane of a
+// pass loads it).  So the body of every row goes out as aligned STG.128 with the data re-aligned in
+// registers; only the <= 3 head floats, <= 3 tail floats and the 3 xyz floats of a row are scalar stores.
+// Round 1's kernel moved every float with a 4-byte load and a 4-byte store: 4x the LSU instructions, 42-54 %
+// of the HBM peak at C = 320 where the aligned C % 4 == 0 gather (same bytes) reaches 84 %.
+// R rows are in flight per lane group (all their gathers are issued before the first store).
+template <int LPR, int R>
 __global__ void __launch_bounds__(kCopyThreads)
-group_concat_flat_kernel(int n, int c, int nsample, unsigned rows_per_cloud, const float* __restrict__ xyz,
-                         const float* __restrict__ new_xyz, const float* __restrict__ points, const int* __restrict__ idx,
-                         int xyz_lo, int feat_lo, float* __restrict__ out, float* __restrict__ grouped_xyz, unsigned magic,
-                         unsigned rb) {  // rb = rows per warp block (1..32): small for wide rows / few rows, so every SM gets warps
-    const int lane = threadIdx.x & 31;
+group_concat_vec_kernel(int n, int c4, int nsample, unsigned rows_per_cloud, const float* __restrict__ xyz,
+                        const float* __restrict__ new_xyz, const float4* __restrict__ points, const int* __restrict__ idx,
+                        int xyz_lo, int feat_lo, float* __restrict__ out, float* __restrict__ grouped_xyz) {
+    constexpr int RPW = 32 / LPR;
+    const int lane = threadIdx.x & 31, g = lane % LPR, sub = lane / LPR;
     const unsigned cloud = blockIdx.y;
-    const unsigned w = (unsigned)c + 3u;
     const unsigned warps = (gridDim.x * kCopyThreads) >> 5;
     const unsigned warp = (blockIdx.x * kCopyThreads + threadIdx.x) >> 5;
     const size_t cloud_row0 = (size_t)cloud * rows_per_cloud;
     const unsigned m = rows_per_cloud / (unsigned)nsample;
+    const int c = 4 * c4;
+    const size_t w = (size_t)c + 3;
     const int* __restrict__ cidx = idx + cloud_row0;
-    const float* __restrict__ cpts = points + (size_t)cloud * n * c;
+    const float4* __restrict__ cpts = points + (size_t)cloud * n * c4;
     const float* __restrict__ cxyz = xyz + (size_t)cloud * n * 3;
     const float* __restrict__ cctr = new_xyz + (size_t)cloud * m * 3;
-    for (unsigned r0 = warp * rb; r0 < rows_per_cloud; r0 += warps * rb) {
-        const unsigned nrows = min(rb, rows_per_cloud - r0);
-        const unsigned r = r0 + lane;
-        int a = 0;
-        float vx = 0.f, vy = 0.f, vz = 0.f;
-        if (lane < nrows) {
-            a = __ldg(cidx + r);
-            const float* __restrict__ s = cxyz + (size_t)a * 3;
-            const float* __restrict__ q = cctr + (size_t)(r / (unsigned)nsample) * 3;
-            vx = __fsub_rn(__ldg(s), __ldg(q));
-            vy = __fsub_rn(__ldg(s + 1), __ldg(q + 1));
-            vz = __fsub_rn(__ldg(s + 2), __ldg(q + 2));
-        }
-        float* __restrict__ obase = out + (cloud_row0 + r0) * w;
-        if (lane < nrows) {  // this row's centred xyz
-            float* __restrict__ d = obase + (size_t)lane * w + xyz_lo;
-            __stcs(d, vx);
-            __stcs(d + 1, vy);
-            __stcs(d + 2, vz);
-        }
-        if (grouped_xyz) {  // the block's triples are one run of 3*nrows floats: transpose through shuffles, coalesced stores
-            float* __restrict__ g = grouped_xyz + (cloud_row0 + r0) * 3;
+    for (unsigned r0 = (warp * RPW + sub) * R; r0 < rows_per_cloud; r0 += warps * RPW * R) {
+        const float4* __restrict__ src[R];
+        float* __restrict__ fdst[R];  // start of the row's feature segment
+        int head[R];
+        bool ok[R];
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const unsigned t = (unsigned)lane + 32u * j, row = t / 3u, comp = t - 3u * row;
-                const float x = __shfl_sync(kFullMask, vx, row & 31u), y = __shfl_sync(kFullMask, vy, row & 31u),
-                            z = __shfl_sync(kFullMask, vz, row & 31u);
-                if (row < nrows) __stcs(g + t, comp == 0 ? x : (comp == 1 ? y : z));
+        for (int rr = 0; rr < R; ++rr) {
+            const unsigned r = r0 + rr;
+            ok[rr] = r < rows_per_cloud;
+            const int a = ok[rr] ? __ldg(cidx + r) : 0;
+            src[rr] = cpts + (size_t)a * c4;
+            const size_t obase = (cloud_row0 + r) * w;
+            fdst[rr] = out + obase + feat_lo;
+            head[rr] = (int)((4u - (unsigned)((obase + (size_t)feat_lo) & 3u)) & 3u);
+            if (ok[rr] && g < 3) {  // the row's centred xyz: 3 lanes
+                const float v = __fsub_rn(__ldg(cxyz + (size_t)a * 3 + g), __ldg(cctr + (size_t)(r / (unsigned)nsample) * 3 + g));
+                __stcs(out + obase + xyz_lo + g, v);
+                if (grouped_xyz) __stcs(grouped_xyz + (cloud_row0 + r) * 3 + g, v);
             }
         }
-        // the feature words: flat walk over the nrows*w floats of this block
-        const unsigned total = nrows * w;
-        for (unsigned f0 = 0; f0 < total; f0 += 32u * UNR) {
-            float v[UNR];
-            bool ok[UNR];
+        for (int k0 = 0; k0 < c4; k0 += LPR) {
+            const int k = k0 + g;
+            float4 v[R], nx[R];
 #pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-                const unsigned f = f0 + 32u * u + lane;
-                const unsigned row = __umulhi(f, magic);       // f / w, exact for f < 32 * w
-                const int e = (int)(f - row * w) - feat_lo;     // channel within the feature part
-                const int ar = __shfl_sync(kFullMask, a, row & 31u);
-                ok[u] = f < total && e >= 0 && e < c;
-                if (ok[u]) v[u] = __ldg(cpts + (size_t)ar * c + e);
+            for (int rr = 0; rr < R; ++rr) {
+                v[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok[rr] && k < c4) v[rr] = __ldg(src[rr] + k);
             }
 #pragma unroll
-            for (int u = 0; u < UNR; ++u)
-                if (ok[u]) __stcs(obase + f0 + 32u * u + lane, v[u]);
+            for (int rr = 0; rr < R; ++rr) {
+                nx[rr].x = __shfl_down_sync(kFullMask, v[rr].x, 1, LPR);
+                nx[rr].y = __shfl_down_sync(kFullMask, v[rr].y, 1, LPR);
+                nx[rr].z = __shfl_down_sync(kFullMask, v[rr].z, 1, LPR);
+                nx[rr].w = 0.f;
+                if (g == LPR - 1 && ok[rr] && k + 1 < c4 && head[rr] != 0) nx[rr] = __ldg(src[rr] + k + 1);  // next pass's first vector
+            }
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+                if (!ok[rr] || k >= c4) continue;
+                const int h = head[rr];
+                float* __restrict__ d = fdst[rr];
+                if (h == 0) {
+                    st_stream_f4(reinterpret_cast<float4*>(d) + k, v[rr]);
+                    continue;
+                }
+                if (k + 1 < c4) {  // aligned body vector: floats [h + 4k, h + 4k + 4) of the segment
+                    float4 o;
+                    o.x = h == 1 ? v[rr].y : (h == 2 ? v[rr].z : v[rr].w);
+                    o.y = h == 1 ? v[rr].z : (h == 2 ? v[rr].w : nx[rr].x);
+                    o.z = h == 1 ? v[rr].w : (h == 2 ? nx[rr].x : nx[rr].y);
+                    o.w = h == 1 ? nx[rr].x : (h == 2 ? nx[rr].y : nx[rr].z);
+                    st_stream_f4(reinterpret_cast<float4*>(d + h + 4 * k), o);
+                } else {  // last source vector: its floats [h, 4) are the row's tail
+                    if (h <= 1) __stcs(d + 4 * k + 1, v[rr].y);
+                    if (h <= 2) __stcs(d + 4 * k + 2, v[rr].z);
+                    __stcs(d + 4 * k + 3, v[rr].w);
+                }
+                if (k == 0) {  // first source vector: its floats [0, h) are the row's head
+                    __stcs(d, v[rr].x);
+                    if (h >= 2) __stcs(d + 1, v[rr].y);
+                    if (h >= 3) __stcs(d + 2, v[rr].z);
+                }
+            }
         }
     }
 }
@@ -287,20 +307,21 @@ static int launch_group_rows(int b, int n, int c, int m, int nsample, const floa
                                                                                 grouped_xyz);
         return finish_launch();
     }
-    if (HAS_XYZ && c > 0 && w <= 8192) {  // (the multiply-high row lookup is exact for 32*w*w < 2^32)
-        // fused tail with features: flat 32-row blocks (see group_concat_flat_kernel)
-        // rows per warp block: ~1024 floats per block for wide rows, and never so many that the machine
-        // (148 SMs x 64 warps) is left with fewer blocks than warp slots
-        unsigned rb = 32;
-        while (rb > 1 && ((unsigned long long)rb * w > 1536ull || (unsigned long long)b * rpc / rb < 2ull * 148 * 64)) rb >>= 1;
-        const unsigned rows_per_cta = rb * (kCopyThreads / 32);
-        unsigned gx = (rpc + rows_per_cta - 1) / rows_per_cta;
-        const unsigned cap = (148u * 32u + b - 1) / b;
+    if (HAS_XYZ && c >= 8 && c % 4 == 0 && aligned16(points) && aligned16(out)) {
+        // vectorised tail (see group_concat_vec_kernel)
+        const int c4 = c / 4;
+        const int lpr = c4 <= 8 ? 8 : (c4 <= 16 ? 16 : 32);
+        constexpr int R = 4;
+        const unsigned rows_per_block = (kCopyThreads / 32) * (32 / lpr) * R;
+        unsigned gx = (rpc + rows_per_block - 1) / rows_per_block;
+        const unsigned cap = (148u * 16u + b - 1) / b;
         if (gx > cap) gx = cap;
         if (gx < 1) gx = 1;
-        const unsigned magic = (unsigned)((0x100000000ull + (unsigned)w - 1) / (unsigned)w);  // ceil(2^32 / w)
-        group_concat_flat_kernel<8><<<dim3(gx, b, 1), kCopyThreads, 0, st>>>(n, c, nsample, rpc, xyz, new_xyz, points, idx, xyz_lo, feat_lo,
-                                                                              out, grouped_xyz, magic, rb);
+        dim3 grid(gx, b, 1);
+        const float4* p4 = reinterpret_cast<const float4*>(points);
+        if (lpr == 8) group_concat_vec_kernel<8, R><<<grid, kCopyThreads, 0, st>>>(n, c4, nsample, rpc, xyz, new_xyz, p4, idx, xyz_lo, feat_lo, out, grouped_xyz);
+        else if (lpr == 16) group_concat_vec_kernel<16, R><<<grid, kCopyThreads, 0, st>>>(n, c4, nsample, rpc, xyz, new_xyz, p4, idx, xyz_lo, feat_lo, out, grouped_xyz);
+        else group_concat_vec_kernel<32, R><<<grid, kCopyThreads, 0, st>>>(n, c4, nsample, rpc, xyz, new_xyz, p4, idx, xyz_lo, feat_lo, out, grouped_xyz);
         return finish_launch();
     }
     const int lpr = w <= 4 ? 4 : (w <= 8 ? 8 : (w <= 16 ? 16 : 32));
@@ -412,7 +433,6 @@ static unsigned grid_for(unsigned long long work_items, unsigned per_block) {
     return (unsigned)blocks;
 }
 
-static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace pn2
 

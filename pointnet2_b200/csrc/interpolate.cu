@@ -168,10 +168,11 @@ __device__ __forceinline__ float interp3(float p1, float p2, float p3, float w1,
 
 constexpr int kItThreads = 256;
 
-// One thread per output float4, U outputs in flight per thread: the 6 small loads (3 indices, 3 weights) of
-// all U outputs are issued first, then the 3U 16-byte gathers, then the U streaming stores — round 1's
-// one-output-per-iteration loop had a single index -> gather -> store chain per thread (45 % of the HBM peak
-// at C = 128).
+// One thread per output float4 (U = 1).  Measured in round 2 (profiles/r2_interp_experiments.txt): U = 4 outputs in
+// flight per thread costs 96 registers and quarter occupancy (40 us against 27 us at 16 x 8192 <- 1024, C = 128);
+// staging channel slices of the known features in shared memory is worse still (73 us: one 160 KB CTA per SM
+// cannot hide its own slice load).  The kernel moves 78 MB in 27 us; 8 us of that is the fixed cost every
+// kernel shows in this harness (launch + cold TLB/L2 after the flush), see DESIGN.md section 4.
 template <typename IndexT, int U>
 __global__ void __launch_bounds__(kItThreads)
 three_interp_vec4_kernel(int m, int c4, IndexT rows_per_cloud, IndexT total_vec, const float4* __restrict__ points,
@@ -218,108 +219,6 @@ three_interp_vec4_kernel(int m, int c4, IndexT rows_per_cloud, IndexT total_vec,
             }
         }
     }
-}
-
-// ---- three_interpolate through shared-memory channel slices --------------------------------------
-// Gathering three 16-byte vectors from L2 per output vector makes the kernel L2-bandwidth bound: 3 bytes
-// cross L2->L1 for every byte written (ncu, C = 128: lts throughput is the top unit, DRAM at 45 %).  But
-// a cloud's known features are small — m rows — so a CTA stages a CHANNEL SLICE of them (m x cs floats,
-// <= 160 KB) in shared memory once and serves a share of the cloud's unknown points from there: the
-// gathers become conflict-free LDS.128 (a quarter-warp reads 128 contiguous bytes of one row), L2 only
-// sees the slice loads (tens of MB in total) and the kernel is left with its compulsory HBM traffic,
-// the (b,n,c) output.  LP lanes own one output row of the slice (LP = cs/4 up to 32).
-constexpr int kIsThreads = 256;
-constexpr size_t kIsSmemBudget = 160 * 1024;
-
-template <int LP>
-__global__ void __launch_bounds__(kIsThreads)
-three_interp_smem_kernel(int m, int c, int n, int cs, int rows_per_part, const float* __restrict__ points,
-                         const int* __restrict__ idx, const float* __restrict__ weight, float* __restrict__ out) {
-    extern __shared__ __align__(16) float s_feat[];  // [m][cw] slice of this cloud's known features
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int cloud = blockIdx.z, c0 = blockIdx.y * cs;
-    const int cw = min(cs, c - c0), cw4 = cw >> 2;
-    const float* __restrict__ pb = points + (size_t)cloud * m * c + c0;
-    for (int e = tid; e < m * cw4; e += kIsThreads) {
-        const int row = e / cw4, l4 = e - row * cw4;
-        reinterpret_cast<float4*>(s_feat)[e] = __ldg(reinterpret_cast<const float4*>(pb + (size_t)row * c) + l4);
-    }
-    __syncthreads();
-    constexpr int RPW = 32 / LP;  // output rows per warp per pass
-    const int g = lane % LP, sub = lane / LP;
-    const int warp = tid >> 5;
-    const int j_lo = blockIdx.x * rows_per_part, j_hi = min(n, j_lo + rows_per_part);
-    const float4* __restrict__ sf = reinterpret_cast<const float4*>(s_feat);
-    constexpr int U = 2;  // rows in flight per lane group
-    for (int j0 = j_lo + (warp * RPW + sub) * U; j0 < j_hi; j0 += (kIsThreads / 32) * RPW * U) {
-        int i1[U], i2[U], i3[U];
-        float w1[U], w2[U], w3[U];
-        bool ok[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int j = j0 + u;
-            ok[u] = j < j_hi;
-            const size_t o = ((size_t)cloud * n + (ok[u] ? j : j_lo)) * 3;
-            i1[u] = __ldg(idx + o);
-            i2[u] = __ldg(idx + o + 1);
-            i3[u] = __ldg(idx + o + 2);
-            w1[u] = __ldg(weight + o);
-            w2[u] = __ldg(weight + o + 1);
-            w3[u] = __ldg(weight + o + 2);
-        }
-        for (int l4 = g; l4 < cw4; l4 += LP) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (ok[u]) {
-                    const float4 a = sf[i1[u] * cw4 + l4], b = sf[i2[u] * cw4 + l4], cc = sf[i3[u] * cw4 + l4];
-                    float4 o;
-                    o.x = interp3(a.x, b.x, cc.x, w1[u], w2[u], w3[u]);
-                    o.y = interp3(a.y, b.y, cc.y, w1[u], w2[u], w3[u]);
-                    o.z = interp3(a.z, b.z, cc.z, w1[u], w2[u], w3[u]);
-                    o.w = interp3(a.w, b.w, cc.w, w1[u], w2[u], w3[u]);
-                    st_stream_f4(reinterpret_cast<float4*>(out + ((size_t)cloud * n + j0 + u) * c + c0) + l4, o);
-                }
-            }
-        }
-    }
-}
-
-// returns 0 if the shape does not suit the sliced kernel (the caller falls back to the L2-gather kernel)
-static int launch_three_interp_smem(int b, int m, int c, int n, const float* points, const int* idx, const float* weight,
-                                    float* out, cudaStream_t st) {
-    if (c % 4 != 0 || c < 32 || b > 65535) return 0;
-    long long cs = (long long)(kIsSmemBudget / sizeof(float)) / m;  // channels of one slice
-    if (cs >= c) cs = c;
-    else cs = cs / 32 * 32;  // full 128-byte lines per row
-    if (cs < 32) return 0;
-    const int slices = (int)((c + cs - 1) / cs);
-    if (slices > 65535) return 0;
-    // enough CTAs to fill the machine twice, each with at least 64 output rows
-    int parts = (2 * 148 + b * slices - 1) / (b * slices);
-    if (parts < 1) parts = 1;
-    int rows_per_part = (n + parts - 1) / parts;
-    if (rows_per_part < 64) rows_per_part = 64;
-    parts = (n + rows_per_part - 1) / rows_per_part;
-    const size_t dyn = (size_t)m * (size_t)cs * sizeof(float);
-    const int lp = cs >= 128 ? 32 : (cs >= 64 ? 16 : 8);
-    static std::atomic<unsigned long long> attr_done{0ull};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    if (dev >= 64 || !(attr_done.load(std::memory_order_acquire) & (1ull << dev))) {
-        cudaError_t e = cudaFuncSetAttribute(three_interp_smem_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kIsSmemBudget);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(three_interp_smem_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kIsSmemBudget);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(three_interp_smem_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kIsSmemBudget);
-        if (e != cudaSuccess) {
-            (void)cudaGetLastError();
-            return 0;
-        }
-        if (dev < 64) attr_done.fetch_or(1ull << dev, std::memory_order_release);
-    }
-    dim3 grid(parts, slices, b);
-    if (lp == 32) three_interp_smem_kernel<32><<<grid, kIsThreads, dyn, st>>>(m, c, n, (int)cs, rows_per_part, points, idx, weight, out);
-    else if (lp == 16) three_interp_smem_kernel<16><<<grid, kIsThreads, dyn, st>>>(m, c, n, (int)cs, rows_per_part, points, idx, weight, out);
-    else three_interp_smem_kernel<8><<<grid, kIsThreads, dyn, st>>>(m, c, n, (int)cs, rows_per_part, points, idx, weight, out);
-    return 1;
 }
 
 template <typename IndexT>
@@ -730,12 +629,11 @@ int pn2_three_interpolate(int b, int m, int c, int n, const float* points, const
     cudaStream_t st = as_stream(stream);
     if (c % 4 == 0 && al16(points) && al16(out)) {
         const unsigned long long tv = total / 4;
-        if (n >= 256 && launch_three_interp_smem(b, m, c, n, points, idx, weight, out, st)) return finish_launch();
-        const unsigned grid = it_grid((tv + 1) / 2, kItThreads);  // 2 outputs per thread
+        const unsigned grid = it_grid(tv, kItThreads);
         if (tv < (1ull << 31))
-            three_interp_vec4_kernel<unsigned, 2><<<grid, kItThreads, 0, st>>>(m, c / 4, (unsigned)n, (unsigned)tv, (const float4*)points, idx, weight, (float4*)out);
+            three_interp_vec4_kernel<unsigned, 1><<<grid, kItThreads, 0, st>>>(m, c / 4, (unsigned)n, (unsigned)tv, (const float4*)points, idx, weight, (float4*)out);
         else
-            three_interp_vec4_kernel<unsigned long long, 2><<<grid, kItThreads, 0, st>>>(m, c / 4, (unsigned long long)n, tv, (const float4*)points, idx, weight, (float4*)out);
+            three_interp_vec4_kernel<unsigned long long, 1><<<grid, kItThreads, 0, st>>>(m, c / 4, (unsigned long long)n, tv, (const float4*)points, idx, weight, (float4*)out);
     } else {
         const unsigned grid = it_grid(total, kItThreads);
         if (total < (1ull << 31))

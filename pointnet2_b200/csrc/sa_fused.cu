@@ -30,6 +30,7 @@
 // front: several CTAs per cloud, no polling) — one launch instead of grid build + grid query +
 // brute-force + group.
 #include <math.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -448,7 +449,8 @@ static int launch_ball_group(int b, int n, int m, float radius, float thr, int n
     // to a sampling CTA would take issue slots from the serial chain the whole layer waits for (measured:
     // cfg3 layer 1, N=1024, +50 us).  Asking for every byte of shared memory the SM has makes co-residency
     // with any other CTA impossible.
-    if (dependent) dyn = (size_t)max_dyn;
+    static const bool exclusive = [] { const char* e = getenv("PN2_SA_EXCLUSIVE"); return !e || e[0] != '0'; }();  // experiment switch
+    if (dependent && exclusive) dyn = (size_t)max_dyn;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)b * (unsigned)ctas_per_cloud, 1, 1);
     cfg.blockDim = dim3(kBgThreads, 1, 1);

@@ -19,41 +19,8 @@ from typing import Optional, Sequence
 import torch
 from torch import nn
 
+from .layers import SharedMLP, set_bn_momentum  # noqa: F401
 from .pointnet_util import pointnet_fp_module, pointnet_sa_module, pointnet_sa_module_msg
-
-
-class SharedMLP(nn.Module):
-    """conv2d(1x1)+BN+ReLU stack on (..., C) tensors — tf_util.conv2d with xavier weights, zero bias."""
-
-    def __init__(self, in_channels: int, widths: Sequence[int], bn: bool = True, last_activation: bool = True):
-        super().__init__()
-        layers = []
-        c = int(in_channels)
-        for i, w in enumerate(widths):
-            lin = nn.Linear(c, int(w))
-            nn.init.xavier_uniform_(lin.weight)
-            nn.init.zeros_(lin.bias)
-            layers.append(lin)
-            act = last_activation or i + 1 < len(widths)
-            if bn and act:
-                layers.append(nn.BatchNorm1d(int(w)))
-            if act:
-                layers.append(nn.ReLU(inplace=True))
-            c = int(w)
-        self.body = nn.Sequential(*layers)
-        self.in_channels, self.out_channels = int(in_channels), c
-
-    def forward(self, t: torch.Tensor) -> torch.Tensor:
-        lead = t.shape[:-1]
-        return self.body(t.reshape(-1, t.shape[-1])).reshape(*lead, self.out_channels)
-
-
-def set_bn_momentum(model: nn.Module, bn_decay: float) -> None:
-    """The reference's bn_decay is the weight of the OLD moving average (train_multi_gpu.py:139-147);
-    torch's momentum is the weight of the NEW batch statistic."""
-    for mod in model.modules():
-        if isinstance(mod, nn.BatchNorm1d):
-            mod.momentum = 1.0 - float(bn_decay)
 
 
 class SetAbstraction(nn.Module):

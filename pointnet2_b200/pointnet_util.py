@@ -3,11 +3,11 @@ set-abstraction / feature-propagation geometry path.
 
 ``sample_and_group`` / ``sample_and_group_all`` keep the reference's signatures and return tuples
 (utils/pointnet_util.py:22-56, :59-84).  ``pointnet_sa_module``, ``pointnet_sa_module_msg`` and
-``pointnet_fp_module`` keep the reference's argument names for the sampling/grouping/interpolation
-half; the dense half (1x1 conv + BN + ReLU stacks, :115-153, :187-195, :218-228) is cuDNN/cuBLAS
-territory and outside this path: pass an ``mlp`` callable (e.g. a torch.nn.Sequential of
-Conv2d(1x1)+BatchNorm2d+ReLU on a channels-last view) or leave it None to get the grouped tensor
-pooled as-is.
+``pointnet_fp_module`` keep the reference's full positional signatures (:87, :156, :199 — ``mlp`` lists of
+widths, ``is_training``, ``bn_decay``, ``scope``, ``bn`` ...), so the reference's model files call them
+unchanged; the dense half (1x1 conv + BN + ReLU stacks, :115-153, :187-195, :218-228) is cuDNN/cuBLAS
+territory and outside this path: width lists resolve to torch layers kept in a variable-scope registry
+(``layers.scoped_mlp``), or pass a callable, or None to get the grouped tensor pooled as-is.
 
 ``fused=True`` (default) routes through the fused kernels (FPS+gather in one launch,
 group+centre+concat in one pass); ``fused=False`` issues the reference's exact op sequence.  Both
@@ -19,7 +19,7 @@ from typing import Callable, Optional, Sequence
 
 import torch
 
-from . import _lib
+from . import _lib, layers
 from ._tensor import on_device, ptr, require_cuda, same_device, stream_ptr
 from .tf_grouping import group_point, knn_point, query_ball_point
 from .tf_interpolate import fp_interpolate_concat, three_interpolate, three_nn, three_nn_interpolate
@@ -160,16 +160,28 @@ def sample_and_group_all(xyz, points, use_xyz=True):
     return new_xyz, new_points, idx, grouped_xyz
 
 
-def _apply_mlp(mlp: Optional[Callable], t: torch.Tensor) -> torch.Tensor:
-    return t if mlp is None else mlp(t)
+def _apply_mlp(mlp, t: torch.Tensor, scope=None, name="mlp", bn=True, is_training=None, bn_decay=None) -> torch.Tensor:
+    """``mlp`` is None (identity), a callable on a (..., channel) tensor, or — the reference's form — a list of
+    output widths, resolved to the SharedMLP registered under ``scope/name`` (layers.scoped_mlp)."""
+    if mlp is None:
+        return t
+    if callable(mlp):
+        return mlp(t)
+    widths = [int(w) for w in mlp]
+    if not widths:
+        return t
+    return layers.scoped_mlp(scope, name, t.shape[-1], widths, bn, t.device, is_training, bn_decay)(t)
 
 
-def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp: Optional[Callable] = None,
-                       mlp2: Optional[Callable] = None, group_all=False, pooling='max', knn=False, use_xyz=True,
-                       fused=True):
-    ''' PointNet Set Abstraction (SA) Module — reference utils/pointnet_util.py:87-154.
-        mlp / mlp2 are callables on a (batch, npoint, nsample, channel) tensor (the reference's
-        1x1-conv stacks); None leaves the features untouched.
+def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp=None, mlp2=None, group_all=False, is_training=None,
+                       bn_decay=None, scope=None, bn=True, pooling='max', knn=False, use_xyz=True, use_nchw=False, fused=True):
+    ''' PointNet Set Abstraction (SA) Module — same positional arguments as the reference
+        (utils/pointnet_util.py:87-154), so its call sites run unchanged, e.g. models/pointnet2_sem_seg.py:28:
+            pointnet_sa_module(l0_xyz, l0_points, npoint=1024, radius=0.1, nsample=32, mlp=[32,32,64], mlp2=None,
+                               group_all=False, is_training=is_training, bn_decay=bn_decay, scope='layer1')
+        mlp / mlp2: lists of output widths (layers live in the variable-scope registry, layers.scoped_mlp; is_training
+        and bn_decay set their mode and batch-norm momentum), or callables on a (batch, npoint, nsample, channel) tensor,
+        or None.  use_nchw is accepted and ignored (a layout hint for TensorFlow's conv2d).
         Return: new_xyz (b,npoint,3), new_points (b,npoint,channels), idx (b,npoint,nsample)
     '''
     if group_all:
@@ -177,7 +189,7 @@ def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp: Optional[Calla
     else:
         new_xyz, new_points, idx, grouped_xyz = sample_and_group(npoint, radius, nsample, xyz, points, knn, use_xyz,
                                                                  fused=fused)
-    new_points = _apply_mlp(mlp, new_points)
+    new_points = _apply_mlp(mlp, new_points, scope, "conv", bn, is_training, bn_decay)
     if pooling == 'max':
         new_points = new_points.max(dim=2, keepdim=True).values
     elif pooling == 'avg':
@@ -191,15 +203,16 @@ def pointnet_sa_module(xyz, points, npoint, radius, nsample, mlp: Optional[Calla
         new_points = torch.cat([new_points.mean(dim=2, keepdim=True), new_points.max(dim=2, keepdim=True).values], dim=-1)
     else:
         raise ValueError(f"unknown pooling {pooling!r}")
-    new_points = _apply_mlp(mlp2, new_points)
+    new_points = _apply_mlp(mlp2, new_points, scope, "conv_post", bn, is_training, bn_decay)
     return new_xyz, new_points.squeeze(2), idx
 
 
-def pointnet_sa_module_msg(xyz, points, npoint, radius_list: Sequence[float], nsample_list: Sequence[int],
-                           mlp_list: Optional[Sequence[Optional[Callable]]] = None, use_xyz=True, fused=True):
-    ''' PointNet Set Abstraction (SA) module with Multi-Scale Grouping — reference
-        utils/pointnet_util.py:156-196.  One FPS+gather, then per scale: ball query, group,
+def pointnet_sa_module_msg(xyz, points, npoint, radius_list: Sequence[float], nsample_list: Sequence[int], mlp_list=None,
+                           is_training=None, bn_decay=None, scope=None, bn=True, use_xyz=True, use_nchw=False, fused=True):
+    ''' PointNet Set Abstraction (SA) module with Multi-Scale Grouping — same positional arguments as the
+        reference (utils/pointnet_util.py:156-196).  One FPS+gather, then per scale: ball query, group,
         centre, concat in the MSG order [features, xyz] (:184), MLP, max-pool; scales concatenated.
+        mlp_list: per scale a list of output widths (scope registry), a callable, or None.
         Return: new_xyz (b,npoint,3), new_points (b,npoint,sum of channels)
     '''
     pre = None
@@ -233,14 +246,16 @@ def pointnet_sa_module_msg(xyz, points, npoint, radius_list: Sequence[float], ns
                         grouped_points = torch.cat([grouped_points, grouped_xyz], dim=-1)
                 else:
                     grouped_points = grouped_xyz
-        grouped_points = _apply_mlp(None if mlp_list is None else mlp_list[i], grouped_points)
+        grouped_points = _apply_mlp(None if mlp_list is None else mlp_list[i], grouped_points, scope, f"conv{i}", bn, is_training, bn_decay)
         new_points_list.append(grouped_points.max(dim=2).values)
     return new_xyz, torch.cat(new_points_list, dim=-1)
 
 
-def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp: Optional[Callable] = None, fused=True):
-    ''' PointNet Feature Propogation (FP) Module — reference utils/pointnet_util.py:199-229.
-        xyz1 (b,n1,3) dense, xyz2 (b,n2,3) sparser, points1 (b,n1,c1) or None, points2 (b,n2,c2).
+def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp=None, is_training=None, bn_decay=None, scope=None, bn=True, fused=True):
+    ''' PointNet Feature Propogation (FP) Module — same positional arguments as the reference
+        (utils/pointnet_util.py:199-229).
+        xyz1 (b,n1,3) dense, xyz2 (b,n2,3) sparser, points1 (b,n1,c1) or None, points2 (b,n2,c2);
+        mlp: list of output widths (scope registry), a callable on a (b,n1,1,channel) tensor, or None.
         Return: new_points (b,n1,mlp[-1]) (or (b,n1,c2+c1) when mlp is None)
     '''
     no_grad = not points2.requires_grad and (points1 is None or not points1.requires_grad)
@@ -261,5 +276,5 @@ def pointnet_fp_module(xyz1, xyz2, points1, points2, mlp: Optional[Callable] = N
         else:
             new_points1 = interpolated_points
     if mlp is not None:
-        new_points1 = mlp(new_points1.unsqueeze(2)).squeeze(2)
+        new_points1 = _apply_mlp(mlp, new_points1.unsqueeze(2), scope, "conv", bn, is_training, bn_decay).squeeze(2)
     return new_points1

@@ -93,8 +93,14 @@ def test_python_surface_matches_reference_signatures():
     assert sg[:7] == ["npoint", "radius", "nsample", "xyz", "points", "knn", "use_xyz"]  # pointnet_util.py:22
     assert list(inspect.signature(pointnet_util.sample_and_group_all).parameters) == ["xyz", "points", "use_xyz"]
     assert list(inspect.signature(pointnet_util.pointnet_fp_module).parameters)[:5] == ["xyz1", "xyz2", "points1", "points2", "mlp"]
-    for n in ("pointnet_sa_module", "pointnet_sa_module_msg"):
-        assert list(inspect.signature(getattr(pointnet_util, n)).parameters)[:3] == ["xyz", "points", "npoint"]
+    # the module functions keep the reference's full positional order (utils/pointnet_util.py:87,156,199)
+    assert list(inspect.signature(pointnet_util.pointnet_sa_module).parameters)[:16] == [
+        "xyz", "points", "npoint", "radius", "nsample", "mlp", "mlp2", "group_all", "is_training", "bn_decay", "scope", "bn", "pooling",
+        "knn", "use_xyz", "use_nchw"]
+    assert list(inspect.signature(pointnet_util.pointnet_sa_module_msg).parameters)[:12] == [
+        "xyz", "points", "npoint", "radius_list", "nsample_list", "mlp_list", "is_training", "bn_decay", "scope", "bn", "use_xyz", "use_nchw"]
+    assert list(inspect.signature(pointnet_util.pointnet_fp_module).parameters)[:9] == [
+        "xyz1", "xyz2", "points1", "points2", "mlp", "is_training", "bn_decay", "scope", "bn"]
 
 
 def test_ops_refuse_cpu_tensors_no_fallback():

@@ -18,6 +18,8 @@ for stage in "$@"; do
     benchquick)
       timeout 600 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; tail -c 400 gpurun_out/bench_quick.err
       python tools/show_bench.py gpurun_out/bench_quick.json ;;
+    e2eprobe)
+      for ex in 1 0; do for fl in 1 0; do PN2_SA_EXCLUSIVE=$ex PROBE_FLUSH=$fl timeout 300 python tools/e2e_probe.py; done; done 2>&1 | tee gpurun_out/e2e_probe.log | tail -40 ;;
     occupancy)
       timeout 300 python tools/cluster_occupancy.py 2>&1 | tee gpurun_out/cluster_occupancy.txt | tail -80 ;;
     benchref)
