@@ -200,6 +200,15 @@ def config_rows(torch, lib, dev, flush, peak, kind, world=1, rank=0, reps=10, fu
     def T(a):
         return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
+    # what the harness itself costs: a kernel that moves 28 bytes, timed like every row below (event pair around
+    # one launch, right after the 256 MiB L2-flush memset).  Every row's ms contains this floor; a kernel that
+    # moves tens of MB cannot show more than bytes / (ms - floor) of the HBM peak however good it is.
+    one = torch.zeros((1, 1, 3), dtype=torch.float32, device=dev)
+    onei = torch.zeros((1, 1), dtype=torch.int32, device=dev)
+    oneo = torch.empty((1, 1, 3), dtype=torch.float32, device=dev)
+    ms = timeit(torch, flush, lambda: lib.pn2_gather_point(1, 1, 1, one.data_ptr(), onei.data_ptr(), oneo.data_ptr(), None), reps=max(reps, 9))
+    add("harness", "timing floor: a 1-thread kernel under the same event pair + L2 flush", ms, 28)
+
     def sa_layer(tag, xyz, feats, m, r, s, xyz_first=True):
         b, n, _ = xyz.shape
         fi = torch.empty((b, m), dtype=torch.int32, device=dev)

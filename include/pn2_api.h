@@ -77,9 +77,11 @@ int pn2_gather_point_grad(int b, int n, int m, const float* out_g, const int* id
 int pn2_query_ball_point(int b, int n, int m, float radius, int nsample, const float* xyz1,
                          const float* xyz2, int* idx, int* pts_cnt, void* stream);
 
-/* Same operation and bit-identical results, with a caller-provided device workspace of at least
- * pn2_query_ball_point_workspace_bytes(b, n) bytes: clouds whose balls are sparse are binned into
- * a uniform grid (cell edge >= 1.01 radius) and each query only tests its 3x3x3 cell neighbourhood;
+/* Same operation and bit-identical results through a uniform grid (cell edge >= 1.01 radius: each query
+ * only tests its 3x3x3 cell neighbourhood).  Clouds of 2048 <= n <= 9700 points are served by the
+ * shared-memory grid kernel of pn2_ball_group (one launch, no workspace used).  Larger clouds use a
+ * caller-provided device workspace of at least pn2_query_ball_point_workspace_bytes(b, n) bytes:
+ * clouds whose balls are sparse are binned into a grid in that workspace;
  * the other clouds (dense or badly skewed ones, and any call with workspace == NULL or n < 2048)
  * take the brute-force path above, as does the whole batch when fewer than a quarter of its clouds
  * qualify and any cloud with a NaN coordinate (the reference counts a NaN point as a hit in every
@@ -145,8 +147,10 @@ int pn2_three_interpolate_grad(int b, int n, int c, int m, const float* grad_out
 /* The same gradient WITHOUT atomics: an inverse index (which unknown points reference each known point) is
  * built in `workspace` (pn2_three_interpolate_grad_det_workspace_bytes(b,n,m) bytes), then one warp per
  * known point adds its contributions in ascending (j, t) order — the order threeinterpolate_grad_cpu adds
- * them, every product and sum rounded on its own — so the result is run-to-run deterministic AND bit-identical
- * to the reference's CPU function.  grad_points (b,m,c) is overwritten: no zero-fill needed. */
+ * them, every product and sum rounded on its own — so the result is run-to-run deterministic AND, for known
+ * points referenced by at most 256 (j, t) pairs (every point of a non-degenerate layer), bit-identical to the
+ * reference's CPU function; longer lists are summed in 8 consecutive pieces combined in order (deterministic,
+ * equal to the sequential sum up to rounding).  grad_points (b,m,c) is overwritten: no zero-fill needed. */
 size_t pn2_three_interpolate_grad_det_workspace_bytes(int b, int n, int m);
 int pn2_three_interpolate_grad_det(int b, int n, int c, int m, const float* grad_out, const int* idx,
                                    const float* weight, float* grad_points, void* workspace,
@@ -184,7 +188,7 @@ int pn2_fp_interpolate_concat(int b, int n, int m, int c2, int c1, const float* 
  * pn2_query_ball_point writes them, and grouped_xyz (b,m,nsample,3) = xyz1 gathered at idx (NULL to
  * skip), minus the query when center != 0 (the tile+sub of :46, one rounding per coordinate).
  * Each cloud is binned into a uniform grid held in shared memory (or kept in index order when its
- * balls are dense), so it applies when pn2_ball_group_fits(n) != 0 (n <= 10750); otherwise
+ * balls are dense), so it applies when pn2_ball_group_fits(n) != 0 (n <= 9700); otherwise
  * cudaErrorInvalidValue — use pn2_query_ball_point_ws + pn2_group_point. */
 int pn2_ball_group_fits(int n);
 int pn2_ball_group(int b, int n, int m, float radius, int nsample, const float* xyz1, const float* xyz2,
@@ -254,7 +258,8 @@ int pn2_fps_plan(int b, int n, int* threads, int* points_per_thread, int* cluste
 int pn2_fps_cluster_capacity(int threads, int points_per_thread, int cluster);
 /* tuning override: lanes cooperating on one ball query (1,2,4,..,32); 0 restores the heuristic */
 void pn2_set_bq_group(int lanes_per_query);
-/* tuning override for pn2_query_ball_point_ws: 0 = automatic, 1 = brute force only, 2 = same as 0 */
+/* tuning override for pn2_query_ball_point_ws: 0 = automatic, 1 = brute force only, 2 = the workspace
+ * (global-memory) grid path even where the shared-memory grid kernel would apply */
 void pn2_set_bq_mode(int mode);
 
 #ifdef __cplusplus

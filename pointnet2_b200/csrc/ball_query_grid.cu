@@ -301,7 +301,7 @@ bq_grid_query_kernel(int n, int m, float thr, int nsample, const float* __restri
     if (lane == 0) pts_cnt[(size_t)cloud * m + q] = cnt;
 }
 
-static int g_bq_mode = 0;  // 0 auto, 1 brute force only, 2 grid whenever it applies
+static int g_bq_mode = 0;  // 0 auto (shared-memory grid kernel when the cloud fits it), 1 brute force only, 2 the global-memory grid path
 
 }  // namespace pn2
 
@@ -355,6 +355,11 @@ int pn2_query_ball_point_ws(int b, int n, int m, float radius, int nsample, cons
     if (!xyz1 || !xyz2 || !idx || !pts_cnt) return (int)cudaErrorInvalidValue;
     const size_t need = pn2_query_ball_point_workspace_bytes(b, n);
     const float thr = pn2_ball_threshold(radius);
+    // clouds that fit the shared-memory grid of sa_fused.cu (n <= 9700): one launch that builds the grid in shared
+    // memory and serves the queries from it — faster than build + query + brute-force back to back from n = 2048 up
+    // (profiles/r2_report.json: cfg2[U] 0.035 against 0.050 ms, cfg4 SA1024 0.051 against 0.093); no workspace needed
+    if (g_bq_mode == 0 && n >= kGridMinN && pn2_ball_group_fits(n) && thr >= 0.0f)
+        return pn2_ball_group(b, n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt, nullptr, 0, stream);
     if (g_bq_mode == 1 || !workspace || need == 0 || workspace_bytes < need || thr < 0.0f || b > 65535)
         return pn2_query_ball_point(b, n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt, stream);
     int rc = pn2_ball_grid_build(b, n, radius, nsample, xyz1, workspace, workspace_bytes, stream);

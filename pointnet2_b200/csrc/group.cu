@@ -177,7 +177,7 @@ group_rows_kernel(int n, int c, int nsample, unsigned rows_per_cloud, const floa
 // of the HBM peak at C = 320 where the aligned C % 4 == 0 gather (same bytes) reaches 84 %.
 // R rows are in flight per lane group (all their gathers are issued before the first store).
 template <int LPR, int R>
-__global__ void __launch_bounds__(kCopyThreads)
+__global__ void __launch_bounds__(kCopyThreads, 4)  // <= 64 registers: at 114 (R = 4, unbounded) occupancy fell to 25 % and the kernel with it
 group_concat_vec_kernel(int n, int c4, int nsample, unsigned rows_per_cloud, const float* __restrict__ xyz,
                         const float* __restrict__ new_xyz, const float4* __restrict__ points, const int* __restrict__ idx,
                         int xyz_lo, int feat_lo, float* __restrict__ out, float* __restrict__ grouped_xyz) {
@@ -208,15 +208,32 @@ group_concat_vec_kernel(int n, int c4, int nsample, unsigned rows_per_cloud, con
             const size_t obase = (cloud_row0 + r) * w;
             fdst[rr] = out + obase + feat_lo;
             head[rr] = (int)((4u - (unsigned)((obase + (size_t)feat_lo) & 3u)) & 3u);
-            if (ok[rr] && g < 3) {  // the row's centred xyz: 3 lanes
-                const float v = __fsub_rn(__ldg(cxyz + (size_t)a * 3 + g), __ldg(cctr + (size_t)(r / (unsigned)nsample) * 3 + g));
-                __stcs(out + obase + xyz_lo + g, v);
-                if (grouped_xyz) __stcs(grouped_xyz + (cloud_row0 + r) * 3 + g, v);
+            // The row's scalar words — 3 centred xyz, `head` floats in front of the first aligned vector and 4-head
+            // behind the last one — go out as ONE predicated store instruction: lane t < 3 takes xyz[t], the next
+            // `head` lanes the head floats, the next 4-head lanes the tail floats (7 lanes at most).  (One store
+            // instruction per word, as a first version did, is 9 store instructions per row against the 2.5 that
+            // move the row's 80 vectors: the LSU queue, not the bytes, set the pace.)
+            if (ok[rr] && g < 7) {
+                const int h = head[rr];
+                float* dst = nullptr;
+                float val = 0.f;
+                if (g < 3) {
+                    val = __fsub_rn(__ldg(cxyz + (size_t)a * 3 + g), __ldg(cctr + (size_t)(r / (unsigned)nsample) * 3 + g));
+                    dst = out + obase + xyz_lo + g;
+                    if (grouped_xyz) __stcs(grouped_xyz + (cloud_row0 + r) * 3 + g, val);
+                } else if (h != 0) {
+                    const int t = g - 3;                  // 0..3
+                    const int e = t < h ? t : c - 4 + t;  // head float t, or the tail float (c - 4) + t for t >= h
+                    val = __ldg(reinterpret_cast<const float*>(src[rr]) + e);
+                    dst = fdst[rr] + e;
+                }
+                if (dst) __stcs(dst, val);
             }
         }
         for (int k0 = 0; k0 < c4; k0 += LPR) {
             const int k = k0 + g;
-            float4 v[R], nx[R];
+            float4 v[R];
+            float3 nx[R];
 #pragma unroll
             for (int rr = 0; rr < R; ++rr) {
                 v[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -227,8 +244,10 @@ group_concat_vec_kernel(int n, int c4, int nsample, unsigned rows_per_cloud, con
                 nx[rr].x = __shfl_down_sync(kFullMask, v[rr].x, 1, LPR);
                 nx[rr].y = __shfl_down_sync(kFullMask, v[rr].y, 1, LPR);
                 nx[rr].z = __shfl_down_sync(kFullMask, v[rr].z, 1, LPR);
-                nx[rr].w = 0.f;
-                if (g == LPR - 1 && ok[rr] && k + 1 < c4 && head[rr] != 0) nx[rr] = __ldg(src[rr] + k + 1);  // next pass's first vector
+                if (g == LPR - 1 && ok[rr] && k + 1 < c4 && head[rr] != 0) {  // next pass's first vector
+                    const float4 t = __ldg(src[rr] + k + 1);
+                    nx[rr] = make_float3(t.x, t.y, t.z);
+                }
             }
 #pragma unroll
             for (int rr = 0; rr < R; ++rr) {
@@ -246,16 +265,7 @@ group_concat_vec_kernel(int n, int c4, int nsample, unsigned rows_per_cloud, con
                     o.z = h == 1 ? v[rr].w : (h == 2 ? nx[rr].x : nx[rr].y);
                     o.w = h == 1 ? nx[rr].x : (h == 2 ? nx[rr].y : nx[rr].z);
                     st_stream_f4(reinterpret_cast<float4*>(d + h + 4 * k), o);
-                } else {  // last source vector: its floats [h, 4) are the row's tail
-                    if (h <= 1) __stcs(d + 4 * k + 1, v[rr].y);
-                    if (h <= 2) __stcs(d + 4 * k + 2, v[rr].z);
-                    __stcs(d + 4 * k + 3, v[rr].w);
-                }
-                if (k == 0) {  // first source vector: its floats [0, h) are the row's head
-                    __stcs(d, v[rr].x);
-                    if (h >= 2) __stcs(d + 1, v[rr].y);
-                    if (h >= 3) __stcs(d + 2, v[rr].z);
-                }
+                }  // (the head floats [0, h) and the tail floats behind the last aligned vector were written above)
             }
         }
     }
@@ -311,10 +321,10 @@ static int launch_group_rows(int b, int n, int c, int m, int nsample, const floa
         // vectorised tail (see group_concat_vec_kernel)
         const int c4 = c / 4;
         const int lpr = c4 <= 8 ? 8 : (c4 <= 16 ? 16 : 32);
-        constexpr int R = 4;
+        constexpr int R = 2;
         const unsigned rows_per_block = (kCopyThreads / 32) * (32 / lpr) * R;
         unsigned gx = (rpc + rows_per_block - 1) / rows_per_block;
-        const unsigned cap = (148u * 16u + b - 1) / b;
+        const unsigned cap = (148u * 32u + b - 1) / b;
         if (gx > cap) gx = cap;
         if (gx < 1) gx = 1;
         dim3 grid(gx, b, 1);

@@ -463,7 +463,7 @@ static int fp_front_dispatch(int b, int n, int m, int c2, int c1, const float* x
 // registers; longer lists — degenerate layers where most unknown points share a neighbour — are served
 // by an index-ordered scan of the cloud's entries instead).
 constexpr int kInvThreads = 256;
-constexpr int kInvSortCap = 128;
+constexpr int kInvSortCap = 256;
 
 __global__ void __launch_bounds__(kInvThreads)
 inv_count_kernel(int n3, int m, long long total, const int* __restrict__ idx, int* __restrict__ cnt) {
@@ -519,12 +519,13 @@ inv_fill_kernel(int n3, int m, long long total, const int* __restrict__ idx, int
     }
 }
 
-// one warp per known point (b, i); lanes over channels (float4 when VEC)
+// one warp per known point (b, i); lanes over channels (float4 when VEC).  Lists longer than kInvSortCap are
+// queued for inv_long_kernel.
 template <bool VEC>
 __global__ void __launch_bounds__(kInvThreads)
-inv_gather_kernel(int n, int c, int m, long long warps_total, const float* __restrict__ grad_out, const int* __restrict__ idx,
+inv_gather_kernel(int n, int c, int m, long long warps_total, const float* __restrict__ grad_out,
                   const float* __restrict__ weight, const int* __restrict__ off, const int* __restrict__ entries,
-                  float* __restrict__ grad_points) {
+                  float* __restrict__ grad_points, int* __restrict__ long_queue) {
     __shared__ int s_e[kInvThreads / 32][kInvSortCap];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long gw = ((long long)blockIdx.x * kInvThreads + threadIdx.x) >> 5;
@@ -534,30 +535,35 @@ inv_gather_kernel(int n, int c, int m, long long warps_total, const float* __res
     const int n3 = 3 * n;
     const int* __restrict__ o = off + cloud * (m + 1);
     const int beg = o[i], len = o[i + 1] - beg;
+    if (len > kInvSortCap) {  // warp-uniform
+        if (lane == 0) long_queue[1 + atomicAdd(long_queue, 1)] = (int)gw;  // the order of the queue does not matter
+        return;
+    }
     const float* __restrict__ go = grad_out + (size_t)cloud * n * c;
     const float* __restrict__ wt = weight + (size_t)cloud * n3;
     float* __restrict__ gp = grad_points + ((size_t)cloud * m + i) * c;
-    const bool sorted = len <= kInvSortCap;
-    if (sorted) {
-        int key[4];
+    {
+        int key[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) key[q] = (32 * q + lane < len) ? __ldg(entries + cloud * n3 + beg + 32 * q + lane) : 0x7fffffff;
+        for (int q = 0; q < 8; ++q) key[q] = (32 * q + lane < len) ? __ldg(entries + cloud * n3 + beg + 32 * q + lane) : 0x7fffffff;
         const int nreg = (len + 31) >> 5;
-        if (nreg <= 1) bitonic_sort_keys<1>(key, lane);
-        else if (nreg == 2) bitonic_sort_keys<2>(key, lane);
-        else bitonic_sort_keys<4>(key, lane);
+        if (nreg <= 1) bitonic_sort_keys<1, 8>(key, lane);
+        else if (nreg == 2) bitonic_sort_keys<2, 8>(key, lane);
+        else if (nreg <= 4) bitonic_sort_keys<4, 8>(key, lane);
+        else bitonic_sort_keys<8, 8>(key, lane);
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+        for (int q = 0; q < 8; ++q)
             if (32 * q + lane < len) s_e[wib][32 * q + lane] = key[q];
         __syncwarp();
     }
-    const int* __restrict__ cidx = idx + cloud * n3;
     constexpr int W = VEC ? 4 : 1;
     for (int l0 = 0; l0 < c; l0 += 32 * W) {  // 128 (VEC) or 32 channels per pass
         const int l = l0 + lane * W;
-        const bool act = l < c;
+        if (l >= c) continue;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        auto accumulate = [&](int e) {
+#pragma unroll 4
+        for (int sidx = 0; sidx < len; ++sidx) {
+            const int e = s_e[wib][sidx];
             const float w = __ldg(wt + e);
             const float* __restrict__ src = go + (size_t)(e / 3) * c + l;
             if (VEC) {
@@ -569,27 +575,80 @@ inv_gather_kernel(int n, int c, int m, long long warps_total, const float* __res
             } else {
                 a0 = __fadd_rn(a0, __fmul_rn(__ldg(src), w));
             }
-        };
-        if (sorted) {
-            if (act) {
-#pragma unroll 4
-                for (int sidx = 0; sidx < len; ++sidx) accumulate(s_e[wib][sidx]);
-            }
-        } else {
-            // long list: walk the cloud's entries in order and pick the ones that point at i
-            for (int base = 0; base < n3; base += 32) {
+        }
+        if (VEC) *reinterpret_cast<float4*>(gp + l) = make_float4(a0, a1, a2, a3);
+        else gp[l] = a0;
+    }
+}
+
+// Long lists (most unknown points share a neighbour: coincident points, m < 3, ...): one CTA per list.  The
+// cloud's 3n entries are cut into 8 consecutive pieces, one per warp; each warp walks its piece in index order
+// (coalesced index loads + ballot), adds the entries that point at i in that order, and the 8 partial sums are
+// combined in piece order — a fixed association, hence deterministic (it differs from one long sequential sum
+// only in rounding; short lists, the normal case, are bit-identical to the reference's loop).
+template <bool VEC>
+__global__ void __launch_bounds__(kInvThreads)
+inv_long_kernel(int n, int c, int m, const float* __restrict__ grad_out, const int* __restrict__ idx,
+                const float* __restrict__ weight, const int* __restrict__ long_queue, float* __restrict__ grad_points) {
+    constexpr int NW = kInvThreads / 32;
+    constexpr int W = VEC ? 4 : 1;
+    __shared__ float s_part[NW][32 * W];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nq = long_queue[0];
+    const int n3 = 3 * n;
+    const int piece = (n3 + NW - 1) / NW;
+    for (int q = blockIdx.x; q < nq; q += gridDim.x) {
+        const long long gw = long_queue[1 + q];
+        const long long cloud = gw / m;
+        const int i = (int)(gw - cloud * m);
+        const float* __restrict__ go = grad_out + (size_t)cloud * n * c;
+        const float* __restrict__ wt = weight + (size_t)cloud * n3;
+        const int* __restrict__ cidx = idx + cloud * n3;
+        float* __restrict__ gp = grad_points + ((size_t)cloud * m + i) * c;
+        const int e_lo = warp * piece, e_hi = min(n3, e_lo + piece);
+        for (int l0 = 0; l0 < c; l0 += 32 * W) {
+            const int l = l0 + lane * W;
+            const bool act = l < c;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            for (int base = e_lo; base < e_hi; base += 32) {
                 const int e = base + lane;
-                unsigned hit = __ballot_sync(kFullMask, e < n3 && __ldg(cidx + e) == i);
+                unsigned hit = __ballot_sync(kFullMask, e < e_hi && __ldg(cidx + e) == i);
                 while (hit) {
-                    const int src = __ffs(hit) - 1;
+                    const int src_lane = __ffs(hit) - 1;
                     hit &= hit - 1;
-                    if (act) accumulate(base + src);
+                    const int ee = base + src_lane;
+                    if (act) {
+                        const float w = __ldg(wt + ee);
+                        const float* __restrict__ src = go + (size_t)(ee / 3) * c + l;
+                        if (VEC) {
+                            const float4 g = __ldg(reinterpret_cast<const float4*>(src));
+                            a0 = __fadd_rn(a0, __fmul_rn(g.x, w));
+                            a1 = __fadd_rn(a1, __fmul_rn(g.y, w));
+                            a2 = __fadd_rn(a2, __fmul_rn(g.z, w));
+                            a3 = __fadd_rn(a3, __fmul_rn(g.w, w));
+                        } else {
+                            a0 = __fadd_rn(a0, __fmul_rn(__ldg(src), w));
+                        }
+                    }
                 }
             }
-        }
-        if (act) {
-            if (VEC) *reinterpret_cast<float4*>(gp + l) = make_float4(a0, a1, a2, a3);
-            else gp[l] = a0;
+            s_part[warp][lane * W] = a0;
+            if (VEC) {
+                s_part[warp][lane * W + 1] = a1;
+                s_part[warp][lane * W + 2] = a2;
+                s_part[warp][lane * W + 3] = a3;
+            }
+            __syncthreads();
+            if (warp == 0 && act) {
+#pragma unroll
+                for (int u = 0; u < W; ++u) {
+                    float t = s_part[0][lane * W + u];
+#pragma unroll
+                    for (int p = 1; p < NW; ++p) t = __fadd_rn(t, s_part[p][lane * W + u]);
+                    gp[l + u] = t;
+                }
+            }
+            __syncthreads();
         }
     }
 }
@@ -692,8 +751,9 @@ int pn2_fp_interpolate_concat(int b, int n, int m, int c2, int c1, const float* 
 
 size_t pn2_three_interpolate_grad_det_workspace_bytes(int b, int n, int m) {
     if (b <= 0 || n <= 0 || m <= 0) return 0;
-    // offsets (b, m+1) + cursors (b, m) + entries (b, 3n), ints
-    return sizeof(int) * ((size_t)b * (m + 1) + (size_t)b * m + (size_t)b * 3 * (size_t)n);
+    // offsets (b, m+1) + cursors (b, m) + entries (b, 3n) + queue of long lists (1 + b * ceil(3n / (cap+1))), ints
+    const size_t longs = (size_t)b * ((3 * (size_t)n) / (pn2::kInvSortCap + 1) + 1);
+    return sizeof(int) * ((size_t)b * (m + 1) + (size_t)b * m + (size_t)b * 3 * (size_t)n + 1 + longs);
 }
 
 int pn2_three_interpolate_grad_det(int b, int n, int c, int m, const float* grad_out, const int* idx, const float* weight,
@@ -710,7 +770,9 @@ int pn2_three_interpolate_grad_det(int b, int n, int c, int m, const float* grad
     int* off = static_cast<int*>(workspace);
     int* cur = off + (size_t)b * (m + 1);
     int* entries = cur + (size_t)b * m;
+    int* long_queue = entries + (size_t)b * 3 * (size_t)n;  // [0] = count, then (cloud * m + i) of every list > kInvSortCap
     cudaError_t e = cudaMemsetAsync(off, 0, sizeof(int) * (size_t)b * (m + 1), st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(long_queue, 0, sizeof(int), st);
     if (e != cudaSuccess) return (int)e;
     const long long total = (long long)b * n * 3;
     const unsigned g1 = it_grid((unsigned long long)total, kInvThreads);
@@ -720,11 +782,16 @@ int pn2_three_interpolate_grad_det(int b, int n, int c, int m, const float* grad
     const long long warps = (long long)b * m;
     const unsigned long long blocks = ((unsigned long long)warps * 32 + kInvThreads - 1) / kInvThreads;
     if (blocks > 0x7fffffffull) return (int)cudaErrorInvalidValue;
-    if (c % 4 == 0 && al16(grad_out) && al16(grad_points))
-        inv_gather_kernel<true><<<(unsigned)blocks, kInvThreads, 0, st>>>(n, c, m, warps, grad_out, idx, weight, off, entries, grad_points);
-    else
-        inv_gather_kernel<false><<<(unsigned)blocks, kInvThreads, 0, st>>>(n, c, m, warps, grad_out, idx, weight, off, entries, grad_points);
-    count_launch(3);
+    // long lists: a fixed grid walks the queue (usually empty: the CTAs read one word and leave)
+    const unsigned long_grid = 148u * 2u;
+    if (c % 4 == 0 && al16(grad_out) && al16(grad_points)) {
+        inv_gather_kernel<true><<<(unsigned)blocks, kInvThreads, 0, st>>>(n, c, m, warps, grad_out, weight, off, entries, grad_points, long_queue);
+        inv_long_kernel<true><<<long_grid, kInvThreads, 0, st>>>(n, c, m, grad_out, idx, weight, long_queue, grad_points);
+    } else {
+        inv_gather_kernel<false><<<(unsigned)blocks, kInvThreads, 0, st>>>(n, c, m, warps, grad_out, weight, off, entries, grad_points, long_queue);
+        inv_long_kernel<false><<<long_grid, kInvThreads, 0, st>>>(n, c, m, grad_out, idx, weight, long_queue, grad_points);
+    }
+    count_launch(4);
     return finish_launch();
 }
 

@@ -64,9 +64,9 @@ __device__ __forceinline__ void warp_max_pair(unsigned& hi, unsigned& lo) {
     lo = ml;
 }
 
-// Ascending bitonic sort of 32*K ints held K per lane (element i = register i/32 of lane i%32).
-template <int K>
-__device__ __forceinline__ void bitonic_sort_keys(int (&key)[4], int lane) {
+// Ascending bitonic sort of 32*K ints held K per lane (element i = register i/32 of lane i%32; K <= KMAX, a power of 2).
+template <int K, int KMAX>
+__device__ __forceinline__ void bitonic_sort_keys(int (&key)[KMAX], int lane) {
 #pragma unroll
     for (int size = 2; size <= 32 * K; size <<= 1) {
 #pragma unroll

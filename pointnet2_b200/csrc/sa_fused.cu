@@ -42,11 +42,11 @@ constexpr int kBgThreads = 1024;
 constexpr int kBgWarps = kBgThreads / 32;
 constexpr int kBgMaxDim = 16;                                   // cells per axis
 constexpr int kBgMaxCells = kBgMaxDim * kBgMaxDim * kBgMaxDim;  // 4096
-constexpr int kBgHitCap = 128;                                  // hits buffered per query before the ordered scan takes over
+constexpr int kBgHitCap = 256;                                  // hit buffer per query (compacted to the nsample smallest indices when it fills up)
+constexpr int kBgCompactMax = 128;                              // compaction needs nsample <= this (else a full buffer falls back to the ordered scan)
 constexpr int kBgMinGridN = 512;                                // below this the in-smem ordered scan is already short
-constexpr float kBgDenseFrac = 0.9f;
 constexpr size_t kBgSmemMax = 200 * 1024;
-constexpr int kBgPosBits = 14;  // positions and indices < 2^14 (n <= 10750 by the shared-memory budget): one int holds both
+constexpr int kBgPosBits = 14;  // positions and indices < 2^14 (n <= 9700 by the shared-memory budget): one int holds both
 
 __host__ __device__ inline size_t bg_smem_bytes(int n) {
     // float4 points + cell_start[kBgMaxCells + 1] (padded to 16 B) + cursors / hit buffers (aliased)
@@ -140,9 +140,11 @@ ball_group_kernel(int n, int m, float radius, float thr, int nsample, const floa
     }
     const int ncell = dims[0] * dims[1] * dims[2];
     const int nb = min(dims[0], 3) * min(dims[1], 3) * min(dims[2], 3);
-    // the neighbourhood must prune >= 70 % of the grid; whether the BALLS are sparse enough is judged from
-    // the cell histogram below (a box-uniform estimate misjudges both surfaces and duplicate clusters)
-    bool use_grid = finite_box && n >= kBgMinGridN && 10 * nb <= 3 * ncell;
+    // The grid is used whenever the 3x3x3 neighbourhood prunes >= 70 % of the cells — whatever the density:
+    // a ball with just over nsample points makes the index-ordered scan read most of the cloud before it
+    // has its nsample hits (surface-like clouds: 6x slower than the grid, profiles/r2_report.json cfg2[S]),
+    // while the grid tests ~27 cells and keeps the nsample smallest indices in a bounded buffer.
+    const bool use_grid = finite_box && n >= kBgMinGridN && 10 * nb <= 3 * ncell;
     __syncthreads();  // s_red is reused below
     if (use_grid) {   // CTA-uniform
         for (int k = tid; k < n; k += T) {
@@ -155,31 +157,8 @@ ball_group_kernel(int n, int m, float radius, float thr, int nsample, const floa
         __syncthreads();
         const int per = (ncell + T - 1) / T;
         const int c0 = min(tid * per, ncell), c1 = min(c0 + per, ncell);
-        // density seen by a typical point: a point of cell i has about c_i * (ball volume / cell volume)
-        // neighbours, so the point-weighted mean is sum(c_i^2)/sum(c_i) * 4.19 (r/h)^3.  Counts are CLIPPED at
-        // 4*nsample first: beyond that a ball is full whatever the exact count, and an unclipped sum lets one
-        // cell of coincident points (ScanNet-style duplicates: 80 % of the cloud in one spot) pass the whole
-        // cloud off as dense although every other ball is nearly empty.  Surface-like clouds fill few cells
-        // densely: their balls fill up, the ordered scan exits early and wins.
-        const float clipc = 4.0f * (float)nsample;
         int local = 0;
-        float sq = 0.f, sw = 0.f;
-        for (int c = c0; c < c1; ++c) {
-            const int cntc = s_cur[c];
-            local += cntc;
-            const float cc = fminf((float)cntc, clipc);
-            sq += cc * cc;
-            sw += cc;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            sq += __shfl_xor_sync(kFullMask, sq, o);
-            sw += __shfl_xor_sync(kFullMask, sw, o);
-        }
-        if (lane == 0) {
-            s_red[0][warp] = sq;
-            s_red[1][warp] = sw;
-        }
+        for (int c = c0; c < c1; ++c) local += s_cur[c];
         int incl = local;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -203,16 +182,7 @@ ball_group_kernel(int n, int m, float radius, float thr, int nsample, const floa
             run += cntc;
         }
         if (tid == 0) s_cell[ncell] = n;
-        float sqsum = s_red[0][lane], swsum = s_red[1][lane];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            sqsum += __shfl_xor_sync(kFullMask, sqsum, o);
-            swsum += __shfl_xor_sync(kFullMask, swsum, o);
-        }
-        const float rh = radius * inv_h;
-        const float expect_local = 4.18879f * rh * rh * rh * sqsum / fmaxf(swsum, 1.0f);
         __syncthreads();
-        use_grid = expect_local < kBgDenseFrac * (float)nsample;
         if (use_grid) {
             for (int k = tid; k < n; k += T) {
                 const float x = __ldg(pts + 3 * (size_t)k), y = __ldg(pts + 3 * (size_t)k + 1), z = __ldg(pts + 3 * (size_t)k + 2);
@@ -299,64 +269,80 @@ ball_group_kernel(int n, int m, float radius, float thr, int nsample, const floa
                 }
             }
             const int len = (sub == 0) ? p1 - p : 0;
-            const int total = 0, longest = __reduce_max_sync(kFullMask, len);
-            int hcount = 0;
-            auto test = [&](bool active, int pos) {  // one candidate per active lane; warp-uniform overflow flag
+            const int longest = __reduce_max_sync(kFullMask, len);
+            // Hits go into a per-warp buffer as (data index << 14 | position) keys (indices are distinct, so keys
+            // order by index).  When the buffer is nearly full it is sorted and cut back to its nsample smallest
+            // keys; from then on only hits below the largest kept key are accepted — so a dense ball costs a few
+            // sorts of 256 keys, never a scan of the cloud.
+            int hcount = 0, tau = 0x7fffffff;
+            bool dense = false;  // at least nsample hits were seen (then pts_cnt = nsample)
+            bool overflow = false;
+            auto compact = [&]() {
+                __syncwarp();
+                int key[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) key[j] = (32 * j + lane < hcount) ? s_hits[warp][32 * j + lane] : 0x7fffffff;
+                bitonic_sort_keys<8, 8>(key, lane);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s_hits[warp][32 * j + lane] = key[j];
+                __syncwarp();
+                if (hcount >= nsample) {
+                    hcount = nsample;
+                    tau = s_hits[warp][nsample - 1];
+                    dense = true;
+                }
+            };
+            auto test = [&](bool active, int pos) {  // one candidate per active lane
+                if (hcount > kBgHitCap - 32) {       // warp-uniform: make room before the buffer can overflow
+                    if (nsample > kBgCompactMax) {
+                        overflow = true;
+                        return;
+                    }
+                    compact();
+                }
                 bool hit = false;
                 int key = 0;
                 if (active) {
                     const float4 c = s_pts[pos];
-                    hit = !(d2_fma_pattern(qx, qy, qz, c.x, c.y, c.z) > thr);
-                    key = (__float_as_int(c.w) << kBgPosBits) | pos;  // (data index, position): indices are distinct
+                    key = (__float_as_int(c.w) << kBgPosBits) | pos;
+                    hit = !(d2_fma_pattern(qx, qy, qz, c.x, c.y, c.z) > thr) && key < tau;
                 }
                 const unsigned bal = __ballot_sync(kFullMask, hit);
                 if (bal) {
                     const int r = hcount + __popc(bal & lt_mask);
-                    if (hit && r < kBgHitCap) s_hits[warp][r] = key;
+                    if (hit) s_hits[warp][r] = key;
                     hcount += __popc(bal);
                 }
-                return hcount > kBgHitCap;
             };
-            bool overflow = false;
-            (void)total;
-            {
-                if (longest <= 48) {
-                    // balanced ranges: lanes 3r..3r+2 walk range r with stride 3
-                    p += sub;
-                    while (__any_sync(kFullMask, p < p1)) {
-                        if (test(p < p1, p)) {
-                            overflow = true;
-                            break;
-                        }
-                        p += 3;
-                    }
-                } else {
-                    // a crowded cell in the neighbourhood: all 32 lanes walk one range after the other
-                    for (int r = 0; r < 9 && !overflow; ++r) {
-                        const int a = __shfl_sync(kFullMask, p, 3 * r), e = __shfl_sync(kFullMask, p1, 3 * r);
-                        for (int pos = a + lane; pos - lane < e; pos += 32) {
-                            if (test(pos < e, pos)) {
-                                overflow = true;
-                                break;
-                            }
-                        }
-                    }
+            if (longest <= 48) {
+                // balanced ranges: lanes 3r..3r+2 walk range r with stride 3
+                p += sub;
+                while (!overflow && __any_sync(kFullMask, p < p1)) {
+                    test(p < p1, p);
+                    p += 3;
+                }
+            } else {
+                // a crowded cell in the neighbourhood: all 32 lanes walk one range after the other
+                for (int r = 0; r < 9 && !overflow; ++r) {
+                    const int a = __shfl_sync(kFullMask, p, 3 * r), e = __shfl_sync(kFullMask, p1, 3 * r);
+                    for (int pos = a + lane; pos - lane < e && !overflow; pos += 32) test(pos < e, pos);
                 }
             }
             if (!overflow) {
-                // order the hits by data index: bitonic sort of the (index, position) keys in registers
-                // (<= 128 keys, 4 per lane: element i lives in register i/32 of lane i%32)
+                // order the hits by data index: bitonic sort of the keys in registers (element i lives in
+                // register i/32 of lane i%32)
                 __syncwarp();
-                cnt = min(hcount, nsample);
-                int key[4];
+                cnt = dense ? nsample : min(hcount, nsample);
+                int key[8];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) key[j] = (32 * j + lane < hcount) ? s_hits[warp][32 * j + lane] : 0x7fffffff;
+                for (int j = 0; j < 8; ++j) key[j] = (32 * j + lane < hcount) ? s_hits[warp][32 * j + lane] : 0x7fffffff;
                 const int nreg = (hcount + 31) >> 5;  // registers that hold real keys (warp-uniform)
-                if (nreg <= 1) bitonic_sort_keys<1>(key, lane);
-                else if (nreg == 2) bitonic_sort_keys<2>(key, lane);
-                else bitonic_sort_keys<4>(key, lane);
+                if (nreg <= 1) bitonic_sort_keys<1, 8>(key, lane);
+                else if (nreg == 2) bitonic_sort_keys<2, 8>(key, lane);
+                else if (nreg <= 4) bitonic_sort_keys<4, 8>(key, lane);
+                else bitonic_sort_keys<8, 8>(key, lane);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < 8; ++j) {
                     const int r = 32 * j + lane;
                     if (r < cnt) {
                         const float4 c = s_pts[key[j] & ((1 << kBgPosBits) - 1)];

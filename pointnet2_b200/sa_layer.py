@@ -108,7 +108,7 @@ def ball_group(radius: float, nsample: int, xyz1: torch.Tensor, xyz2: torch.Tens
     """query_ball_point(radius, nsample, xyz1, xyz2) + group_point(xyz1, idx) [- xyz2] in one launch.
 
     Returns (idx, pts_cnt, grouped_xyz or None).  Falls back to the separate ops when the cloud does
-    not fit the kernel's shared-memory grid (n > 10750)."""
+    not fit the kernel's shared-memory grid (n > 9700)."""
     radius, nsample = float(radius), int(nsample)
     if not radius > 0:
         raise ValueError("QueryBallPoint expects positive radius")

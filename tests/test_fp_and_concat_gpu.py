@@ -68,7 +68,7 @@ def test_fp_interpolate_concat_with_duplicate_known_points(dev):
 
 # ------------------------------------------------------------------------------------------- deterministic gradient
 GRAD_CASES = [(16, 8192, 1024, 128), (4, 1024, 256, 256), (2, 300, 40, 7), (2, 64, 16, 512), (3, 500, 1, 8), (2, 500, 2, 33), (1, 20000, 5, 16),
-              (2, 10, 300, 4)]
+              (2, 10, 300, 4), (2, 3000, 60, 132)]
 
 
 @pytest.mark.parametrize("b,n,m,c", GRAD_CASES)
@@ -85,15 +85,25 @@ def test_three_interpolate_grad_deterministic_matches_reference_order(dev, b, n,
     wsb = int(lib.pn2_three_interpolate_grad_det_workspace_bytes(b, n, m))
     ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
     tg, ti, tw = T(go, dev), T(idx, dev), T(w, dev)
+    # lists of up to 256 (j, t) entries are summed in the reference's order: bit-exact.  Longer ones (degenerate layers:
+    # m < 3, ...) are summed in 8 ordered pieces: deterministic, equal up to rounding.
+    longest = max(int(np.bincount(idx[i].ravel(), minlength=m).max()) for i in range(b))
+    runs = []
     for _ in range(2):
         rc = lib.pn2_three_interpolate_grad_det(b, n, c, m, tg.data_ptr(), ti.data_ptr(), tw.data_ptr(), gp.data_ptr(), ws.data_ptr(), wsb, None)
         assert rc == 0
         torch.cuda.synchronize()
-        np.testing.assert_array_equal(gp.cpu().numpy(), want)  # bit-exact, twice
+        runs.append(gp.cpu().numpy().copy())
+        gp.fill_(7.0)
+    np.testing.assert_array_equal(runs[0], runs[1])  # run-to-run deterministic, always
+    if longest <= 256:
+        np.testing.assert_array_equal(runs[0], want)
+    else:
+        np.testing.assert_allclose(runs[0], want, rtol=2e-5, atol=2e-5 * float(np.abs(want).max()))
     # and through autograd (the default backward)
     p = T(W.features(b, m, c, 215), dev).requires_grad_(True)
     (three_interpolate(p, ti, tw) * tg).sum().backward()
-    np.testing.assert_array_equal(p.grad.cpu().numpy(), want)
+    np.testing.assert_array_equal(p.grad.cpu().numpy(), runs[0])
     TI.DETERMINISTIC_GRAD = False
     try:
         p2 = p.detach().clone().requires_grad_(True)

@@ -208,12 +208,14 @@ def _set_bq_group(g):
     _lib.load().pn2_set_bq_group(g)
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("gen,b,n,m,r,s", BQ_CASES + [("U", 4, 4096, 512, 0.1, 32), ("D", 3, 4096, 256, 0.1, 32), ("S", 4, 2048, 300, 0.15, 16),
                                                      ("D", 2, 8192, 200, 0.05, 8), ("U", 2, 16384, 100, 0.06, 64), ("U", 2, 300, 40, 0.02, 4)])
 def test_ball_query_grid_path_matches_oracle(dev, mode, gen, b, n, m, r, s):
-    """The workspace entry point (uniform grid for sparse balls, in-kernel ordered scan for dense
-    ones, brute force for flagged clouds) against the oracle; mode 1 forces brute force."""
+    """The workspace entry point against the oracle: mode 0 = automatic (shared-memory grid kernel for
+    2048 <= n <= 9700, the global-memory grid beyond), mode 1 = brute force, mode 2 = the global-memory
+    grid path (uniform grid for sparse balls, in-kernel ordered scan for dense ones, brute force for
+    flagged clouds) at every size."""
     xyz = W.DISTRIBUTIONS[gen](b, n, 46)
     new_xyz = O.oracle_gather_point(xyz, O.oracle_fps(m, xyz))
     lib = _lib.load()
@@ -245,10 +247,15 @@ def test_ball_query_mixed_batches_follow_the_batch_rule(dev, sparse_clouds):
     torch.cuda.synchronize()
     flags = ws.view(torch.int32)[:: ws_bytes // 32][:8].cpu().numpy() != 0
     assert flags[:sparse_clouds].all() and not flags[sparse_clouds:].any(), flags
-    idx, cnt = query_ball_point(r, s, t, T(new_xyz, dev))
-    oi, oc = O.oracle_query_ball_point(r, s, xyz, new_xyz)
-    np.testing.assert_array_equal(N(cnt), oc)
-    np.testing.assert_array_equal(N(idx), oi)
+    for mode in (2, 0):
+        lib.pn2_set_bq_mode(mode)
+        try:
+            idx, cnt = query_ball_point(r, s, t, T(new_xyz, dev))
+        finally:
+            lib.pn2_set_bq_mode(0)
+        oi, oc = O.oracle_query_ball_point(r, s, xyz, new_xyz)
+        np.testing.assert_array_equal(N(cnt), oc)
+        np.testing.assert_array_equal(N(idx), oi)
 
 
 def test_ball_query_grid_free_queries_outside_the_box(dev):

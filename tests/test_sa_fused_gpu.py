@@ -42,7 +42,10 @@ LAYER_CASES = [
     ("S", 2, 1024, 512, 0.4, 128),     # cfg3 L1 widest scale
     ("U", 2, 512, 128, 0.8, 128),      # every point in every ball
     ("U", 2, 700, 64, 0.02, 16),       # nearly empty balls
-    ("U", 1, 10000, 300, 0.05, 24),    # near the shared-memory limit
+    ("U", 1, 9700, 300, 0.05, 24),     # at the shared-memory limit
+    ("S", 2, 4096, 1024, 0.25, 32),    # dense balls in grid mode: the hit buffer is compacted several times
+    ("S", 2, 2048, 256, 0.3, 128),     # dense balls, nsample = the compaction limit
+    ("S", 2, 2048, 64, 0.3, 200),      # nsample beyond it: a full buffer falls back to the ordered scan
     ("U", 2, 40, 64, 0.3, 8),          # npoint > n
     ("U", 3, 1, 4, 0.5, 3),            # single point
     ("D", 2, 5000, 1, 0.2, 5),         # one centroid

@@ -8,7 +8,7 @@ for stage in "$@"; do
   echo "=== stage $stage ($(date +%T))"
   case "$stage" in
     newtests)
-      timeout 600 python -m pytest tests/test_sa_fused_gpu.py tests/test_fp_and_concat_gpu.py tests/test_full_size_parity_gpu.py -q -m gpu 2>&1 | tail -40 | tee gpurun_out/newtests.log ;;
+      timeout 600 python -m pytest tests/test_sa_fused_gpu.py tests/test_fp_and_concat_gpu.py tests/test_reference_callers_gpu.py tests/test_pointnet_util_gpu.py -q -m gpu 2>&1 | tail -40 | tee gpurun_out/newtests.log ;;
     alltests)
       timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -40 | tee gpurun_out/alltests.log ;;
     smoke)
