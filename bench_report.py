@@ -345,6 +345,30 @@ def config_rows(torch, lib, dev, flush, peak, kind, world=1, rank=0, reps=10, fu
                         2 * 4 * b * m_ * c_ + 24 * b * n_ + 4 * b * n_ * c_)
             ms = timeit(torch, flush, lambda: lib.pn2_three_nn_interpolate(b, n_, m_, c_, x1.data_ptr(), x2.data_ptr(), p2.data_ptr(), o.data_ptr(), None, None, None, None), reps=reps)
             add(f"cfg4[B={b}].FP{n_}<-{m_}", f"three_nn_interpolate (fused) C={c_}", ms, 12 * b * n_ + 12 * b * m_ + 4 * b * m_ * c_ + 4 * b * n_ * c_)
+    if full:
+        # the same last FP layer on a UNIFORM cloud (no coincident points): the inverse-index gradient's normal case —
+        # cfg4's duplicate-heavy clouds make three known points collect thousands of contributions each
+        b, n_, m_, c_ = 16, 8192, 1024, 128
+        x1 = T(W.cloud_uniform(b, n_, 131))
+        x2 = x1[:, :m_].contiguous()
+        d = torch.empty((b, n_, 3), dtype=torch.float32, device=dev)
+        i = torch.empty((b, n_, 3), dtype=torch.int32, device=dev)
+        lib.pn2_three_nn(b, n_, m_, x1.data_ptr(), x2.data_ptr(), d.data_ptr(), i.data_ptr(), None)
+        w = torch.full((b, n_, 3), 1 / 3, dtype=torch.float32, device=dev)
+        go = torch.randn((b, n_, c_), dtype=torch.float32, device=dev)
+        gp = torch.empty((b, m_, c_), dtype=torch.float32, device=dev)
+
+        def igrad_u():
+            gp.zero_()
+            lib.pn2_three_interpolate_grad(b, n_, c_, m_, go.data_ptr(), i.data_ptr(), w.data_ptr(), gp.data_ptr(), None)
+        nb = 2 * 4 * b * m_ * c_ + 24 * b * n_ + 4 * b * n_ * c_
+        add("uniform[B=16].FP8192<-1024", "three_interpolate_grad C=128 (atomics, incl. zero-fill)", timeit(torch, flush, igrad_u, reps=reps), nb)
+        dwb = int(lib.pn2_three_interpolate_grad_det_workspace_bytes(b, n_, m_))
+        dw = torch.empty(dwb, dtype=torch.uint8, device=dev)
+        ms = timeit(torch, flush, lambda: lib.pn2_three_interpolate_grad_det(b, n_, c_, m_, go.data_ptr(), i.data_ptr(), w.data_ptr(), gp.data_ptr(),
+                                                                             dw.data_ptr(), dwb, None), reps=reps)
+        add("uniform[B=16].FP8192<-1024", "three_interpolate_grad C=128 (deterministic, inverse index)", ms, nb)
+        del x1, x2, go, gp, dw
     # cfg5 sweep: FPS + gather + ball query.  --report: B=8 and B=1; driver line: this rank's 8/world clouds
     c5 = W.CFG5_SWEEP
     for n in c5["ns"]:

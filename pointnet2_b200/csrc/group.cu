@@ -317,8 +317,10 @@ static int launch_group_rows(int b, int n, int c, int m, int nsample, const floa
                                                                                 grouped_xyz);
         return finish_launch();
     }
-    if (HAS_XYZ && c >= 8 && c % 4 == 0 && aligned16(points) && aligned16(out)) {
-        // vectorised tail (see group_concat_vec_kernel)
+    if (HAS_XYZ && c >= 8 && c <= 64 && c % 4 == 0 && aligned16(points) && aligned16(out)) {
+        // vectorised tail (see group_concat_vec_kernel).  Measured (profiles/r2_report.json): it wins at C = 64 (30.7 against
+        // 34.8 us, cfg4 SA256) and loses to the plain row kernel below from C = 128 up (C = 320: 125 against 103 us), so
+        // only narrow rows take it
         const int c4 = c / 4;
         const int lpr = c4 <= 8 ? 8 : (c4 <= 16 ? 16 : 32);
         constexpr int R = 2;

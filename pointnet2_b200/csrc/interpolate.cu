@@ -519,6 +519,57 @@ inv_fill_kernel(int n3, int m, long long total, const int* __restrict__ idx, int
     }
 }
 
+// count + scan + fill of one cloud in ONE CTA, with the counters and cursors in shared memory (m <= 16000): the
+// inverse index of a layer costs one launch instead of two memsets and three kernels.
+constexpr int kInvBuildMaxM = 16000;
+__global__ void __launch_bounds__(1024)
+inv_build_kernel(int n3, int m, const int* __restrict__ idx, int* __restrict__ off, int* __restrict__ entries,
+                 int* __restrict__ long_queue) {
+    extern __shared__ int s_c[];  // [m + 1]: counts -> exclusive offsets (kept as the fill cursors)
+    __shared__ int s_w[32];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long cloud = blockIdx.x;
+    const int* __restrict__ cidx = idx + cloud * n3;
+    for (int i = tid; i <= m; i += 1024) s_c[i] = 0;
+    if (tid == 0) {
+        s_carry = 0;
+        if (cloud == 0) long_queue[0] = 0;
+    }
+    __syncthreads();
+    for (int e = tid; e < n3; e += 1024) atomicAdd(&s_c[__ldg(cidx + e)], 1);
+    __syncthreads();
+    int* __restrict__ o = off + cloud * (m + 1);
+    for (int base = 0; base <= m; base += 1024) {
+        const int i = base + tid;
+        const int v = (i < m) ? s_c[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) {
+            const int t = __shfl_up_sync(kFullMask, incl, sft);
+            if (lane >= sft) incl += t;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        int wv = s_w[lane], winc = wv;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) {
+            const int t = __shfl_up_sync(kFullMask, winc, sft);
+            if (lane >= sft) winc += t;
+        }
+        const int excl = s_carry + __shfl_sync(kFullMask, winc - wv, warp) + incl - v;
+        if (i <= m) {
+            o[i] = excl;
+            s_c[i] = excl;
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+    int* __restrict__ ent = entries + cloud * n3;
+    for (int e = tid; e < n3; e += 1024) ent[atomicAdd(&s_c[__ldg(cidx + e)], 1)] = e;
+}
+
 // one warp per known point (b, i); lanes over channels (float4 when VEC).  Lists longer than kInvSortCap are
 // queued for inv_long_kernel.
 template <bool VEC>
@@ -613,21 +664,38 @@ inv_long_kernel(int n, int c, int m, const float* __restrict__ grad_out, const i
             for (int base = e_lo; base < e_hi; base += 32) {
                 const int e = base + lane;
                 unsigned hit = __ballot_sync(kFullMask, e < e_hi && __ldg(cidx + e) == i);
-                while (hit) {
-                    const int src_lane = __ffs(hit) - 1;
-                    hit &= hit - 1;
-                    const int ee = base + src_lane;
-                    if (act) {
-                        const float w = __ldg(wt + ee);
-                        const float* __restrict__ src = go + (size_t)(ee / 3) * c + l;
-                        if (VEC) {
-                            const float4 g = __ldg(reinterpret_cast<const float4*>(src));
-                            a0 = __fadd_rn(a0, __fmul_rn(g.x, w));
-                            a1 = __fadd_rn(a1, __fmul_rn(g.y, w));
-                            a2 = __fadd_rn(a2, __fmul_rn(g.z, w));
-                            a3 = __fadd_rn(a3, __fmul_rn(g.w, w));
-                        } else {
-                            a0 = __fadd_rn(a0, __fmul_rn(__ldg(src), w));
+                while (hit) {  // up to 4 matching entries at a time: their rows are loaded together, then added in order
+                    int ee[4];
+                    float w[4];
+                    float4 g[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        ee[u] = -1;
+                        if (hit) {
+                            ee[u] = base + __ffs(hit) - 1;
+                            hit &= hit - 1;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        w[u] = 0.f;
+                        if (ee[u] >= 0 && act) {
+                            w[u] = __ldg(wt + ee[u]);
+                            const float* __restrict__ src = go + (size_t)(ee[u] / 3) * c + l;
+                            if (VEC) g[u] = __ldg(reinterpret_cast<const float4*>(src));
+                            else g[u].x = __ldg(src);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (ee[u] >= 0 && act) {
+                            a0 = __fadd_rn(a0, __fmul_rn(g[u].x, w[u]));
+                            if (VEC) {
+                                a1 = __fadd_rn(a1, __fmul_rn(g[u].y, w[u]));
+                                a2 = __fadd_rn(a2, __fmul_rn(g[u].z, w[u]));
+                                a3 = __fadd_rn(a3, __fmul_rn(g[u].w, w[u]));
+                            }
                         }
                     }
                 }
@@ -771,14 +839,30 @@ int pn2_three_interpolate_grad_det(int b, int n, int c, int m, const float* grad
     int* cur = off + (size_t)b * (m + 1);
     int* entries = cur + (size_t)b * m;
     int* long_queue = entries + (size_t)b * 3 * (size_t)n;  // [0] = count, then (cloud * m + i) of every list > kInvSortCap
-    cudaError_t e = cudaMemsetAsync(off, 0, sizeof(int) * (size_t)b * (m + 1), st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(long_queue, 0, sizeof(int), st);
-    if (e != cudaSuccess) return (int)e;
-    const long long total = (long long)b * n * 3;
-    const unsigned g1 = it_grid((unsigned long long)total, kInvThreads);
-    inv_count_kernel<<<g1, kInvThreads, 0, st>>>(3 * n, m, total, idx, off);
-    inv_scan_kernel<<<b, 1024, 0, st>>>(m, off, cur);
-    inv_fill_kernel<<<g1, kInvThreads, 0, st>>>(3 * n, m, total, idx, cur, entries);
+    int launches = 2;
+    if (m <= kInvBuildMaxM) {
+        static std::atomic<unsigned long long> attr_done{0ull};
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return (int)e;
+        if (dev >= 64 || !(attr_done.load(std::memory_order_acquire) & (1ull << dev))) {
+            e = cudaFuncSetAttribute(inv_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(int) * (kInvBuildMaxM + 1));
+            if (e != cudaSuccess) return (int)e;
+            if (dev < 64) attr_done.fetch_or(1ull << dev, std::memory_order_release);
+        }
+        inv_build_kernel<<<b, 1024, sizeof(int) * (size_t)(m + 1), st>>>(3 * n, m, idx, off, entries, long_queue);
+        launches += 1;
+    } else {
+        cudaError_t e = cudaMemsetAsync(off, 0, sizeof(int) * (size_t)b * (m + 1), st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(long_queue, 0, sizeof(int), st);
+        if (e != cudaSuccess) return (int)e;
+        const long long total = (long long)b * n * 3;
+        const unsigned g1 = it_grid((unsigned long long)total, kInvThreads);
+        inv_count_kernel<<<g1, kInvThreads, 0, st>>>(3 * n, m, total, idx, off);
+        inv_scan_kernel<<<b, 1024, 0, st>>>(m, off, cur);
+        inv_fill_kernel<<<g1, kInvThreads, 0, st>>>(3 * n, m, total, idx, cur, entries);
+        launches += 3;
+    }
     const long long warps = (long long)b * m;
     const unsigned long long blocks = ((unsigned long long)warps * 32 + kInvThreads - 1) / kInvThreads;
     if (blocks > 0x7fffffffull) return (int)cudaErrorInvalidValue;
@@ -791,7 +875,7 @@ int pn2_three_interpolate_grad_det(int b, int n, int c, int m, const float* grad
         inv_gather_kernel<false><<<(unsigned)blocks, kInvThreads, 0, st>>>(n, c, m, warps, grad_out, weight, off, entries, grad_points, long_queue);
         inv_long_kernel<false><<<long_grid, kInvThreads, 0, st>>>(n, c, m, grad_out, idx, weight, long_queue, grad_points);
     }
-    count_launch(4);
+    count_launch(launches - 1);
     return finish_launch();
 }
 

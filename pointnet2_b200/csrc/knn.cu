@@ -117,6 +117,7 @@ knn_kernel(int n, int m, int k, const float* __restrict__ xyz1, const float* __r
                     }
                     __syncwarp();
                 }
+                __syncwarp();  // every lane's reads of the list above are done before the slot is written
                 if (lane == 0) {
                     bv[ins] = dv;
                     bo[ins] = dpos;

@@ -269,12 +269,12 @@ ball_group_kernel(int n, int m, float radius, float thr, int nsample, const floa
                 }
             }
             const int len = (sub == 0) ? p1 - p : 0;
-            const int longest = __reduce_max_sync(kFullMask, len);
+            const int total = __reduce_add_sync(kFullMask, len), longest = __reduce_max_sync(kFullMask, len);
             // Hits go into a per-warp buffer as (data index << 14 | position) keys (indices are distinct, so keys
             // order by index).  When the buffer is nearly full it is sorted and cut back to its nsample smallest
             // keys; from then on only hits below the largest kept key are accepted — so a dense ball costs a few
             // sorts of 256 keys, never a scan of the cloud.
-            int hcount = 0, tau = 0x7fffffff;
+            int hcount = 0, tau = 0x7fffffff, tested = 0;
             bool dense = false;  // at least nsample hits were seen (then pts_cnt = nsample)
             bool overflow = false;
             auto compact = [&]() {
@@ -294,7 +294,13 @@ ball_group_kernel(int n, int m, float radius, float thr, int nsample, const floa
             };
             auto test = [&](bool active, int pos) {  // one candidate per active lane
                 if (hcount > kBgHitCap - 32) {       // warp-uniform: make room before the buffer can overflow
-                    if (nsample > kBgCompactMax) {
+                    // The first time the buffer fills, hits/tested estimates the ball's population.  A VERY dense ball
+                    // (a cell of coincident points: thousands of candidates, nearly all hits) is served faster by the
+                    // index-ordered scan, which stops after ~n*nsample/population points (x3: it reads global memory),
+                    // than by testing the rest of the neighbourhood; a moderately dense one by carrying on.
+                    const float scan_cost = 3.0f * (float)n * (float)nsample * (float)tested / ((float)hcount * (float)total);
+                    const float grid_cost = (float)(total - tested) + 2240.0f;  // + a few sorts of the buffer
+                    if (nsample > kBgCompactMax || (!dense && scan_cost < grid_cost)) {
                         overflow = true;
                         return;
                     }
@@ -307,6 +313,7 @@ ball_group_kernel(int n, int m, float radius, float thr, int nsample, const floa
                     key = (__float_as_int(c.w) << kBgPosBits) | pos;
                     hit = !(d2_fma_pattern(qx, qy, qz, c.x, c.y, c.z) > thr) && key < tau;
                 }
+                tested += __popc(__ballot_sync(kFullMask, active));
                 const unsigned bal = __ballot_sync(kFullMask, hit);
                 if (bal) {
                     const int r = hcount + __popc(bal & lt_mask);

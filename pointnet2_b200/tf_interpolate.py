@@ -42,8 +42,10 @@ def three_nn(xyz1: torch.Tensor, xyz2: torch.Tensor):
     return dist, idx
 
 
-# three_interpolate's backward: True = inverse index + ordered sums (deterministic, bit-identical to the reference's CPU
-# function); False = the float-atomic scatter (the reference-signature pn2_three_interpolate_grad)
+# three_interpolate's backward: True = inverse index + ordered sums (run-to-run deterministic, bit-identical to the
+# reference's CPU function on non-degenerate layers); False = the float-atomic scatter (the reference-signature
+# pn2_three_interpolate_grad, the reference's own semantics on a GPU).  Measured at 16 x 8192 <- 1024, C = 128
+# (profiles/r2_report.json): see DESIGN.md section 5.4 for which is faster where.
 DETERMINISTIC_GRAD = True
 
 

@@ -1,6 +1,6 @@
 """Condensed view of a bench.py JSON line (python tools/show_bench.py FILE)."""
 import json, sys
-d = json.load(open(sys.argv[1]))
+d = json.loads([ln for ln in open(sys.argv[1]).read().splitlines() if ln.startswith("{")][-1])
 for k in ("value", "ms_per_step", "launch", "gpu_launches"):
     print(k, d.get(k))
 e = d["e2e"]
