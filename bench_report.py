@@ -346,6 +346,29 @@ def config_rows(torch, lib, dev, flush, peak, kind, world=1, rank=0, reps=10, fu
             ms = timeit(torch, flush, lambda: lib.pn2_three_nn_interpolate(b, n_, m_, c_, x1.data_ptr(), x2.data_ptr(), p2.data_ptr(), o.data_ptr(), None, None, None, None), reps=reps)
             add(f"cfg4[B={b}].FP{n_}<-{m_}", f"three_nn_interpolate (fused) C={c_}", ms, 12 * b * n_ + 12 * b * m_ + 4 * b * m_ * c_ + 4 * b * n_ * c_)
     if full:
+        # n3: knn_point at cfg2's shape — one tiled top-k kernel against the reference's composite
+        # (materialised (b,m,n) matrix + selection sort of whole rows, here as torch ops + pn2_selection_sort)
+        b, n_, m_, k_ = 32, 4096, 1024, 32
+        x1 = T(W.cloud_uniform(b, n_, 141))
+        x2 = x1[:, :m_].contiguous()
+        val = torch.empty((b, m_, k_), dtype=torch.float32, device=dev)
+        ind = torch.empty((b, m_, k_), dtype=torch.int32, device=dev)
+        ms = timeit(torch, flush, lambda: lib.pn2_knn_point(b, n_, m_, k_, x1.data_ptr(), x2.data_ptr(), val.data_ptr(), ind.data_ptr(), None), reps=reps)
+        add("knn[B=32,N=4096,M=1024,k=32]", "knn_point (tiled top-k, no matrix)", ms, 12 * b * n_ + 12 * b * m_ + 8 * b * m_ * k_,
+            dict(pairs_per_s=b * m_ * n_ / (ms * 1e-3)))
+        bs = 8  # the composite needs 3 (b,m,n) tensors + the (b,m,n,3) differences: 8 clouds at a time
+        x1s, x2s = x1[:bs].contiguous(), x2[:bs].contiguous()
+        outi = torch.empty((bs, m_, n_), dtype=torch.int32, device=dev)
+        outv = torch.empty((bs, m_, n_), dtype=torch.float32, device=dev)
+
+        def composite():
+            diff = x1s.unsqueeze(1) - x2s.unsqueeze(2)
+            dist = (diff * diff).sum(-1)
+            lib.pn2_selection_sort(bs, n_, m_, k_, dist.data_ptr(), outi.data_ptr(), outv.data_ptr(), None)
+        ms = timeit(torch, flush, composite, reps=3, warm=1)
+        add("knn[B=8 of 32,N=4096,M=1024,k=32]", "reference composite: (b,m,n) matrix (torch) + selection sort (pn2_selection_sort), 8 of the 32 clouds", ms,
+            12 * bs * n_ + 12 * bs * m_ + 8 * bs * m_ * k_, dict(pairs_per_s=bs * m_ * n_ / (ms * 1e-3)))
+        del x1, x2, x1s, x2s, outi, outv
         # the same last FP layer on a UNIFORM cloud (no coincident points): the inverse-index gradient's normal case —
         # cfg4's duplicate-heavy clouds make three known points collect thousands of contributions each
         b, n_, m_, c_ = 16, 8192, 1024, 128

@@ -210,6 +210,18 @@ def oracle_selection_sort(k: int, dist):
     return outi, out
 
 
+def oracle_knn_point(k: int, xyz1, xyz2):
+    """knn_point as the reference composes it (tf_grouping.py:48-73): the (b,m,n) matrix of squared distances
+    sum((xyz1 - xyz2)**2, -1) — element-wise float32 squares summed left to right — then selection sort
+    (oracle_selection_sort, restating tf_grouping_g.cu:83-123) and the first k columns.  Returns (val, idx)."""
+    x1, x2 = _f(xyz1), _f(xyz2)
+    diff = (x1[:, None, :, :] - x2[:, :, None, :]).astype(_F)
+    sq = (diff * diff).astype(_F)
+    dist = ((sq[..., 0] + sq[..., 1]).astype(_F) + sq[..., 2]).astype(_F)
+    outi, out = oracle_selection_sort(k, dist)
+    return np.ascontiguousarray(out[:, :, :k]), np.ascontiguousarray(outi[:, :, :k])
+
+
 # ------------------------------------------------------------------ reference CPU functions
 def refcpu_query_ball_point(radius: float, nsample: int, xyz1, xyz2):
     """tf_ops/grouping/test/query_ball_point.cpp:19 (no pts_cnt output). idx pre-zeroed."""

@@ -22,8 +22,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import oracle as O  # noqa: E402
 from pointnet2_b200 import workloads as W  # noqa: E402
-from pointnet2_b200.tf_grouping import group_point, query_ball_point, select_top_k  # noqa: E402
-from pointnet2_b200.tf_interpolate import three_interpolate, three_nn, three_nn_interpolate  # noqa: E402
+from pointnet2_b200 import _lib  # noqa: E402
+from pointnet2_b200.sa_layer import ball_group, sample_group, sample_group_msg  # noqa: E402
+from pointnet2_b200.tf_grouping import group_point, knn_point, query_ball_point, select_top_k  # noqa: E402
+from pointnet2_b200.tf_interpolate import fp_interpolate_concat, three_interpolate, three_nn, three_nn_interpolate  # noqa: E402
 from pointnet2_b200.tf_sampling import farthest_point_sample_and_gather, gather_point, prob_sample  # noqa: E402
 from pointnet2_b200.pointnet_util import group_and_concat  # noqa: E402
 
@@ -165,7 +167,90 @@ def case_prob(rs):
     return np.array_equal(N(prob_sample(T(pr), T(r))), O.oracle_prob_sample(pr, r)), p
 
 
-CASES = [case_fps, case_ball, case_group, case_interp, case_sort, case_prob]
+def case_layer(rs):
+    """The overlapped sampling+grouping layer (and its multi-scale form, and ball_group on its own) against the
+    oracle's op-by-op composite."""
+    b, n = int(rs.randint(1, 6)), log_n(rs, 1, 12000)
+    m = min(max(1, int(rs.choice([1, n // 9 + 1, n // 4 + 1, n, n + 2]))), 400)
+    kind, xyz = cloud(rs, b, n)
+    ext = float(xyz.max() - xyz.min()) + 1e-3
+    scales = int(rs.choice([1, 1, 2, 3]))
+    radii = [float(np.float32(ext * np.exp(rs.uniform(np.log(0.01), np.log(0.6))))) for _ in range(scales)]
+    ns = [int(rs.choice([1, 4, 16, 32, 64, 128, 150])) for _ in range(scales)]
+    center = bool(rs.rand() < 0.5)
+    p = dict(op="layer", b=b, n=n, m=m, radii=radii, ns=ns, kind=kind, center=center)
+    o_fi = O.oracle_fps(m, xyz)
+    o_nx = O.oracle_gather_point(xyz, o_fi)
+    x = T(xyz)
+    if scales == 1:
+        fi, nx, idx, cnt, g = sample_group(m, radii[0], ns[0], x, center=center)
+        idxs, cnts, gs = [idx], [cnt], [g]
+    else:
+        fi, nx, idxs, cnts, gs = sample_group_msg(m, radii, ns, x, center=center)
+    ok = np.array_equal(N(fi), o_fi) and np.array_equal(N(nx), o_nx)
+    for r, s, idx, cnt, g in zip(radii, ns, idxs, cnts, gs):
+        oi, oc = O.oracle_query_ball_point(r, s, xyz, o_nx)
+        og = O.oracle_group_point(xyz, oi)
+        if center:
+            og = og - o_nx[:, :, None, :]
+        ok = ok and np.array_equal(N(idx), oi) and np.array_equal(N(cnt), oc) and np.array_equal(N(g), og)
+    if n <= 9700:  # the same kernel with free queries
+        q = (xyz.min() + (xyz.max() - xyz.min() + 1e-3) * rs.random_sample((b, m, 3)) * 1.2 - 0.1).astype(np.float32)
+        idx, cnt, g = ball_group(radii[0], ns[0], x, T(q), center=center)
+        oi, oc = O.oracle_query_ball_point(radii[0], ns[0], xyz, q)
+        og = O.oracle_group_point(xyz, oi) - (q[:, :, None, :] if center else 0)
+        ok = ok and np.array_equal(N(idx), oi) and np.array_equal(N(cnt), oc) and np.array_equal(N(g), og.astype(np.float32))
+    return ok, p
+
+
+def case_knn(rs):
+    b, n, m = int(rs.randint(1, 4)), log_n(rs, 1, 3000), log_n(rs, 1, 200)
+    k = int(min(n, rs.choice([1, 2, 3, 8, 16, 32, 64, 128])))
+    kind, xyz = cloud(rs, b, n)  # G / D / L clouds: exact ties, where the selection sort's swaps decide the order
+    q = xyz[:, rs.randint(0, n, m)].copy() if rs.rand() < 0.6 else cloud(rs, b, m)[1]
+    p = dict(op="knn", b=b, n=n, m=m, k=k, kind=kind)
+    val, idx = knn_point(k, T(xyz), T(q))
+    wv, wi = O.oracle_knn_point(k, xyz, q)
+    return np.array_equal(N(idx), wi) and np.array_equal(N(val), wv), p
+
+
+def case_fp(rs):
+    """Fused FP front end + concat, and the deterministic gradient of three_interpolate."""
+    b, n, m = int(rs.randint(1, 4)), log_n(rs, 1, 5000), log_n(rs, 1, 1200)
+    c2, c1 = int(rs.choice([1, 4, 5, 64, 128, 256])), int(rs.choice([0, 0, 3, 4, 64]))
+    k1, xyz1 = cloud(rs, b, n)
+    k2, xyz2 = cloud(rs, b, m)
+    p2, p1 = W.features(b, m, c2, int(rs.randint(1 << 30))), (W.features(b, n, c1, 3) if c1 else None)
+    p = dict(op="fp", b=b, n=n, m=m, c2=c2, c1=c1, kinds=k1 + k2)
+    got = N(fp_interpolate_concat(T(xyz1), T(xyz2), T(p1) if c1 else None, T(p2)))
+    od, oi = O.oracle_three_nn(xyz1, xyz2)
+    out, d, i, w = three_nn_interpolate(T(xyz1), T(xyz2), T(p2), return_aux=True)
+    ok = np.array_equal(N(d), od) and np.array_equal(N(i), oi)
+    ok = ok and np.array_equal(got[..., :c2], O.oracle_three_interpolate(p2, oi, N(w)))  # the kernel's own weights: bit-exact
+    if c1:
+        ok = ok and np.array_equal(got[..., c2:], p1)
+    # deterministic gradient: bit-exact with the reference's accumulation order when no list exceeds 256 entries
+    lib = _lib.load()
+    go = W.features(b, n, c2, 11)
+    wts = np.abs(W.features(b, n, 3, 12)).astype(np.float32)
+    gp = torch.empty((b, m, c2), dtype=torch.float32, device=dev)
+    wsb = int(lib.pn2_three_interpolate_grad_det_workspace_bytes(b, n, m))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    tg, ti, tw = T(go), T(oi), T(wts)
+    rc = lib.pn2_three_interpolate_grad_det(b, n, c2, m, tg.data_ptr(), ti.data_ptr(), tw.data_ptr(), gp.data_ptr(), ws.data_ptr(), wsb, None)
+    torch.cuda.synchronize()
+    want = O.oracle_three_interpolate_grad((b, m, c2), oi, wts, go)
+    longest = max(int(np.bincount(oi[j].ravel(), minlength=m).max()) for j in range(b))
+    if longest <= 256:
+        ok = ok and rc == 0 and np.array_equal(N(gp), want)
+    else:
+        mass = O.oracle_three_interpolate_grad((b, m, c2), oi, wts, np.abs(go))
+        ok = ok and rc == 0 and bool((np.abs(N(gp) - want) <= 1e-5 * mass + 1e-6).all())
+    p["longest_list"] = longest
+    return ok, p
+
+
+CASES = [case_fps, case_ball, case_group, case_interp, case_sort, case_prob, case_layer, case_knn, case_fp]
 
 
 def run(seed: int, iterations: int):

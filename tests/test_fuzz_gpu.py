@@ -9,5 +9,5 @@ pytestmark = pytest.mark.gpu
 def test_random_cases_match_oracle(dev, seed):
     import fuzz_gpu
     counts, fails = fuzz_gpu.run(seed, 180)
-    assert sum(counts.values()) == 180 and len(counts) == 6
+    assert sum(counts.values()) == 180 and len(counts) == 9
     assert not fails, fails

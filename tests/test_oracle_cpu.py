@@ -160,3 +160,22 @@ def test_prob_sample_known_answer():
     np.testing.assert_array_equal(O.oracle_prob_cumsum(p), [[0.5, 0.75, 0.75, 1.0, 2.0]])
     r = np.array([[0.0, 0.25, 0.3, 0.375, 0.4, 0.5, 0.75, 1.0]], np.float32)
     np.testing.assert_array_equal(O.oracle_prob_sample(p, r), [[0, 0, 1, 1, 3, 3, 4, 4]])
+
+
+def test_oracle_knn_composite_returns_the_k_nearest_in_order():
+    """The kNN oracle (distance matrix + selection sort restatement): with distinct distances it is the plain
+    ascending k-nearest list; with ties its order is whatever the selection sort's swaps produce, which is what
+    the CUDA kernel is held to (tests/test_full_size_parity_gpu.py compares both with the rebuilt reference kernel)."""
+    rs = np.random.RandomState(5)
+    x1 = rs.random_sample((2, 60, 3)).astype(np.float32)
+    x2 = rs.random_sample((2, 7, 3)).astype(np.float32)
+    val, idx = O.oracle_knn_point(5, x1, x2)
+    d = ((x1[:, None] - x2[:, :, None]) ** 2).sum(-1)
+    order = np.argsort(d, axis=2, kind="stable")[:, :, :5]
+    np.testing.assert_array_equal(idx, order.astype(np.int32))
+    np.testing.assert_allclose(val, np.take_along_axis(d, order, 2), rtol=1e-6)
+    # ties: 4 coincident data points -> the swap order decides; the toy case of the reference's own test
+    # (test/selection_sort.cpp:68-92) is covered by the selection-sort goldens
+    x1[0, 10] = x1[0, 3] = x1[0, 40] = x1[0, 0]
+    val, idx = O.oracle_knn_point(6, x1, x1[:, :1].copy())
+    assert sorted(idx[0, 0, :4].tolist()) == [0, 3, 10, 40] and (val[0, 0, :4] == 0).all()

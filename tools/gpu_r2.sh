@@ -22,6 +22,8 @@ for stage in "$@"; do
       for ex in 1 0; do for fl in 1 0; do PN2_SA_EXCLUSIVE=$ex PROBE_FLUSH=$fl timeout 300 python tools/e2e_probe.py; done; done 2>&1 | tee gpurun_out/e2e_probe.log | tail -40 ;;
     occupancy)
       timeout 300 python tools/cluster_occupancy.py 2>&1 | tee gpurun_out/cluster_occupancy.txt | tail -80 ;;
+    fuzz)
+      timeout 600 python tests/fuzz_gpu.py --seconds 150 --seed 7 --json gpurun_out/fuzz_r2.json 2>&1 | tail -4 ;;
     benchref)
       timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_ref_r2.json 2> gpurun_out/bench_ref_r2.err; head -c 600 gpurun_out/bench_ref_r2.json ;;
     report)
