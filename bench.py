@@ -12,15 +12,21 @@ clouds).  Prints ONE JSON line (rank 0).
 
   value      whole-job points/s (B*N per rank per step, summed over ranks / max-over-ranks time),
              inputs resident in HBM, CUDA-event timed per step, L2 flushed between steps.
-             One batch at a time (each step waits for the previous one).
+             One batch at a time; a step is ONE pn2_sa_layer_device call (the ball query + grouping
+             run as a programmatically dependent grid while the sampling chain is still going).
   e2e        the same metric through the host-buffer C-ABI call (pn2_sa_layer_host): pinned host
-             xyz -> H2D -> 3 kernels -> D2H of new_xyz/idx/pts_cnt/grouped_xyz, every step, all
-             inside the timed region.  Headline: a stream of batches through
-             SetAbstractionPipeline (--e2e-depth in flight, default 3: copy-in/sampling of the next
-             batch overlaps copy-out of the previous); e2e.serial is one batch in flight.
+             xyz -> H2D -> layer -> D2H of new_xyz/idx/pts_cnt/grouped_xyz, every step, all inside the
+             timed region.  Headline: a stream of batches through SetAbstractionPipeline (--e2e-depth
+             in flight, default 3); e2e.serial is one batch in flight; e2e.idx_only is the same pipeline
+             for a caller that does not ask for grouped_xyz.
   device_batches_in_flight   secondary: `value`'s graph with --in-flight batches on separate
-             streams (one FPS launch occupies only b of the 148 SMs).
+             streams (one layer occupies 2*b of the 148 SMs).
   roofline   dominant kernel (FPS): algorithmic bytes / its CUDA-event time vs the measured HBM peak.
+  kernels_ms the three sequential launches of the same step (per-kernel times; their outputs must
+             equal the overlapped layer's bit for bit).
+  configs    per-kernel rows for BASELINE.json's other configs (cfg3 MSG stack, cfg4 sem-seg SA+FP,
+             cfg5 sweep) at this rank's shard, max over ranks — outside every timed region above.
+  reference_cuda   the reference's OWN CUDA kernels (oracle/_ref, unmodified) timed on this box.
   cpu_baseline  the same workload on the host cores (FPS: oracle port — the reference has no CPU
              FPS; ball query + group: the reference's own CPU functions when oracle/_ref travelled).
 

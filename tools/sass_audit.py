@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Static audit of libpn2_b200.so (no GPU needed): per kernel, registers / shared memory / spills from
 `cuobjdump -res-usage` and the count of the SASS opcodes the design relies on (warp reductions, packed
-FP32x2, vector atomics, async cluster stores, barriers).  Writes profiles/r1_sass_audit.txt."""
+FP32x2, vector atomics, async cluster stores, barriers).  Writes profiles/r2_sass_audit.txt."""
 import collections
 import os
 import re
@@ -14,14 +14,15 @@ LIB = os.path.join(ROOT, "pointnet2_b200", "libpn2_b200.so")
 WATCH = [("CREDUX", r"^CREDUX"), ("REDUX", r"^REDUX"), ("FADD2", r"^FADD2"), ("FMUL2", r"^FMUL2"), ("FFMA2", r"^FFMA2"), ("FFMA", r"^FFMA"),
          ("FMNMX", r"^FMNMX"), ("FSETP", r"^FSETP"), ("REDG.F32x4", r"^REDG.*F32x4"), ("REDG.F32", r"^REDG"), ("ATOMG", r"^ATOMG"),
          ("ATOMS", r"^ATOMS"), ("STAS(st.async)", r"^STAS"), ("SYNCS(mbarrier)", r"^SYNCS"), ("UCGABAR(cluster barrier)", r"^UCGABAR"),
-         ("BAR.SYNC", r"^BAR"), ("LDS.128", r"^LDS.*128"), ("LDS.64", r"^LDS.*64"), ("LDS", r"^LDS"), ("STS", r"^STS"),
+         ("PREEXIT(griddepcontrol.launch_dependents)", r"^PREEXIT"), ("ACQBULK(griddepcontrol.wait)", r"^ACQBULK"), ("BAR.SYNC", r"^BAR"), ("LDS.128", r"^LDS.*128"), ("LDS.64", r"^LDS.*64"), ("LDS", r"^LDS"), ("STS", r"^STS"),
          ("LDG.128", r"^LDG.*128"), ("STG.128", r"^STG.*128"), ("LDG", r"^LDG"), ("STG", r"^STG"), ("SHFL", r"^SHFL"), ("VOTE", r"^VOTE"),
          ("POPC", r"^POPC"), ("MUFU", r"^MUFU"), ("LDL", r"^LDL"), ("STL", r"^STL")]
-SHOW = ["fps_cta_kernel<16, 256>", "fps_cluster_kernel<8, 128, false>", "fps_cluster_kernel<32, 512, true>", "ball_query_kernel<16>",
-        "bq_grid_build_kernel", "bq_grid_query_kernel", "group_rows_vec4_kernel<32, 4>", "group_narrow_kernel<0>",
-        "group_rows_kernel<32, true>", "group_point_grad_vec4_kernel<unsigned int>", "three_nn_kernel", "three_nn_interp_kernel",
-        "three_interp_vec4_kernel<unsigned int>", "three_interp_grad_vec4_kernel<unsigned int>", "selection_sort_kernel",
-        "prob_cumsum_kernel", "prob_search_kernel"]
+SHOW = ["fps_cta_kernel<16, 256>", "fps_cluster_kernel<16, 128, 16>", "fps_cluster_kernel<32, 128, 32>", "fps_cluster_kernel<32, 512, 16>",
+        "ball_group_kernel", "knn_kernel", "ball_query_kernel<16>", "bq_grid_build_kernel", "bq_grid_query_kernel",
+        "group_rows_vec4_kernel<32, 4>", "group_narrow_kernel<0>", "group_rows_kernel<32, true>", "group_concat_vec_kernel<16, 2>",
+        "group_point_grad_vec4_kernel<unsigned int>", "three_nn_kernel", "fp_front_kernel<1>", "fp_front_kernel<8>",
+        "three_interp_vec4_kernel<unsigned int, 1>", "three_interp_grad_vec4_kernel<unsigned int>", "inv_build_kernel",
+        "inv_gather_kernel<true>", "inv_long_kernel<true>", "selection_sort_kernel", "prob_cumsum_kernel", "prob_search_kernel"]
 
 
 def demangle(names):
@@ -71,7 +72,7 @@ def main():
             c = counts[k]
             lines.append(f"{nice}\n    REG {u.get('REG')}  STACK {u.get('STACK')}  SHARED {u.get('SHARED')}  instructions {total[k]}\n    "
                          + "  ".join(f"{w}:{c[w]}" for w, _ in WATCH if c[w]))
-    out = os.path.join(ROOT, "profiles", "r1_sass_audit.txt")
+    out = os.path.join(ROOT, "profiles", "r2_sass_audit.txt")
     with open(out, "w") as f:
         f.write("\n".join(lines) + "\n")
     print(open(out).read())
