@@ -52,6 +52,10 @@ __host__ __device__ inline size_t bg_smem_bytes(int n) {
     // float4 points + cell_start[kBgMaxCells + 1] (padded to 16 B) + cursors / hit buffers (aliased)
     return (size_t)n * 16 + (size_t)(kBgMaxCells + 4) * 4 + (size_t)kBgWarps * kBgHitCap * 4;
 }
+// Small clouds keep BOTH layouts in shared memory — cell-sorted for the grid walk and index-ordered for the scan — so
+// each query can take whichever is cheaper for its own ball (a ball that covers a quarter of the cloud is served by
+// an index-ordered scan of a few dozen iterations; a small one by its 27 cells).
+__host__ __device__ inline bool bg_dual_layout(int n) { return bg_smem_bytes(n) + (size_t)n * 16 <= kBgSmemMax; }
 
 __device__ __forceinline__ int bg_cell(float x, float origin, float inv_h, int dim) {
     float f = floorf(__fmul_rn(__fsub_rn(x, origin), inv_h));
@@ -88,6 +92,8 @@ ball_group_kernel(int n, int m, float radius, float thr, int nsample, const floa
     int* __restrict__ s_cell = reinterpret_cast<int*>(s_raw + (size_t)n * 16);          // [kBgMaxCells + 1]: cell_start
     int* __restrict__ s_cur = s_cell + (kBgMaxCells + 4);                               // build: histogram / cursors
     int(*s_hits)[kBgHitCap] = reinterpret_cast<int(*)[kBgHitCap]>(s_cur);               // query: per-warp hit positions
+    const bool dual = bg_dual_layout(n);                                                // index-ordered copy behind the hit buffers
+    float4* __restrict__ s_orig = reinterpret_cast<float4*>(s_raw + bg_smem_bytes(n));  // [n], valid when dual && use_grid
     __shared__ float s_red[6][32];
     __shared__ int s_wsum[32];
     __shared__ float4 s_first[NW];
@@ -191,6 +197,7 @@ ball_group_kernel(int n, int m, float radius, float thr, int nsample, const floa
                 const int cz = min(max(bg_cell(z, mn[2], inv_h, dims[2]), 0), dims[2] - 1);
                 const int pos = atomicAdd(&s_cur[(cz * dims[1] + cy) * dims[0] + cx], 1);
                 s_pts[pos] = make_float4(x, y, z, __int_as_float(k));
+                if (dual) s_orig[k] = make_float4(x, y, z, __int_as_float(k));
             }
         }
     }
@@ -274,9 +281,13 @@ ball_group_kernel(int n, int m, float radius, float thr, int nsample, const floa
             // order by index).  When the buffer is nearly full it is sorted and cut back to its nsample smallest
             // keys; from then on only hits below the largest kept key are accepted — so a dense ball costs a few
             // sorts of 256 keys, never a scan of the cloud.
+            // a neighbourhood that holds more than a quarter of the cloud (large radius, or a cell of coincident
+            // points next door): the index-ordered scan from shared memory is at most n/32 cheap iterations and stops
+            // early when the ball is dense — skip the grid walk for this query
+            const bool scan_instead = dual && 4 * total > n;
             int hcount = 0, tau = 0x7fffffff, tested = 0;
             bool dense = false;  // at least nsample hits were seen (then pts_cnt = nsample)
-            bool overflow = false;
+            bool overflow = scan_instead;
             auto compact = [&]() {
                 __syncwarp();
                 int key[8];
@@ -298,7 +309,7 @@ ball_group_kernel(int n, int m, float radius, float thr, int nsample, const floa
                     // (a cell of coincident points: thousands of candidates, nearly all hits) is served faster by the
                     // index-ordered scan, which stops after ~n*nsample/population points (x3: it reads global memory),
                     // than by testing the rest of the neighbourhood; a moderately dense one by carrying on.
-                    const float scan_cost = 3.0f * (float)n * (float)nsample * (float)tested / ((float)hcount * (float)total);
+                    const float scan_cost = (dual ? 1.0f : 3.0f) * (float)n * (float)nsample * (float)tested / ((float)hcount * (float)total);
                     const float grid_cost = (float)(total - tested) + 2240.0f;  // + a few sorts of the buffer
                     if (nsample > kBgCompactMax || (!dense && scan_cost < grid_cost)) {
                         overflow = true;
@@ -321,7 +332,9 @@ ball_group_kernel(int n, int m, float radius, float thr, int nsample, const floa
                     hcount += __popc(bal);
                 }
             };
-            if (longest <= 48) {
+            if (overflow) {
+                // (scan_instead)
+            } else if (longest <= 48) {
                 // balanced ranges: lanes 3r..3r+2 walk range r with stride 3
                 p += sub;
                 while (!overflow && __any_sync(kFullMask, p < p1)) {
@@ -361,31 +374,70 @@ ball_group_kernel(int n, int m, float radius, float thr, int nsample, const floa
             }
         }
         if (!scanned) {
-            // ordered scan with early exit: from shared memory when the cloud is stored in index order,
-            // from global memory (L1/L2) when it is stored cell-sorted
-            for (int base = 0; base < n && cnt < nsample; base += 32) {
-                const int k = base + lane;
-                bool hit = false;
-                float x = 0.f, y = 0.f, z = 0.f;
-                if (k < n) {
-                    if (use_grid) {
-                        x = __ldg(pts + 3 * (size_t)k);
-                        y = __ldg(pts + 3 * (size_t)k + 1);
-                        z = __ldg(pts + 3 * (size_t)k + 2);
-                    } else {
-                        const float4 c = s_pts[k];
-                        x = c.x;
-                        y = c.y;
-                        z = c.z;
-                    }
-                    hit = !(d2_fma_pattern(qx, qy, qz, x, y, z) > thr);
+            // ordered scan with early exit: from shared memory when an index-ordered copy of the cloud is there (scan
+            // mode, or the dual layout of small clouds), from global memory (L1/L2) when only the cell-sorted one is.
+            // Hit indices are buffered (they arrive in order) and the row is written afterwards, 32 consecutive
+            // entries per store instruction — storing hit by hit costs 4 sparsely populated store instructions per
+            // 32 points scanned, which made dense balls slower here than in the grid walk.
+            const bool buffered = nsample <= kBgHitCap;
+            auto load_point = [&](int k, float& x, float& y, float& z) {
+                if (use_grid && !dual) {
+                    x = __ldg(pts + 3 * (size_t)k);
+                    y = __ldg(pts + 3 * (size_t)k + 1);
+                    z = __ldg(pts + 3 * (size_t)k + 2);
+                } else {
+                    const float4 c = use_grid ? s_orig[k] : s_pts[k];
+                    x = c.x;
+                    y = c.y;
+                    z = c.z;
                 }
-                const unsigned bal = __ballot_sync(kFullMask, hit);
-                if (bal) {
-                    const int r = cnt + __popc(bal & lt_mask);
-                    if (hit && r < nsample) emit(r, k, x, y, z);
-                    if (hit && r == 0) s_first[warp] = make_float4(x, y, z, __int_as_float(k));
-                    cnt = min(cnt + __popc(bal), nsample);
+            };
+            if (buffered) {
+                // two points per lane and trip, indices only (ncu, cfg3 layer 1 at r = 0.4: the loop is issue-bound —
+                // 80 % issue-active — so what counts is instructions per point tested)
+                for (int base = 0; base < n && cnt < nsample; base += 64) {
+                    const int k0 = base + lane, k1 = k0 + 32;
+                    float x0, y0, z0, x1, y1, z1;
+                    load_point(min(k0, n - 1), x0, y0, z0);
+                    load_point(min(k1, n - 1), x1, y1, z1);
+                    const bool h0 = k0 < n && !(d2_fma_pattern(qx, qy, qz, x0, y0, z0) > thr);
+                    const bool h1 = k1 < n && !(d2_fma_pattern(qx, qy, qz, x1, y1, z1) > thr);
+                    const unsigned b0 = __ballot_sync(kFullMask, h0), b1 = __ballot_sync(kFullMask, h1);
+                    if (b0 | b1) {
+                        const int r0 = cnt + __popc(b0 & lt_mask);
+                        const int c1 = cnt + __popc(b0);
+                        const int r1 = c1 + __popc(b1 & lt_mask);
+                        if (h0 && r0 < nsample) s_hits[warp][r0] = k0;
+                        if (h1 && r1 < nsample) s_hits[warp][r1] = k1;
+                        cnt = min(c1 + __popc(b1), nsample);
+                    }
+                }
+            } else {
+                for (int base = 0; base < n && cnt < nsample; base += 32) {
+                    const int k = base + lane;
+                    bool hit = false;
+                    float x = 0.f, y = 0.f, z = 0.f;
+                    if (k < n) {
+                        load_point(k, x, y, z);
+                        hit = !(d2_fma_pattern(qx, qy, qz, x, y, z) > thr);
+                    }
+                    const unsigned bal = __ballot_sync(kFullMask, hit);
+                    if (bal) {
+                        const int r = cnt + __popc(bal & lt_mask);
+                        if (hit && r < nsample) emit(r, k, x, y, z);
+                        if (hit && r == 0) s_first[warp] = make_float4(x, y, z, __int_as_float(k));
+                        cnt = min(cnt + __popc(bal), nsample);
+                    }
+                }
+            }
+            if (buffered) {
+                __syncwarp();
+                for (int r = lane; r < cnt; r += 32) {
+                    const int k = s_hits[warp][r];
+                    float x, y, z;
+                    load_point(k, x, y, z);
+                    emit(r, k, x, y, z);
+                    if (r == 0) s_first[warp] = make_float4(x, y, z, __int_as_float(k));
                 }
             }
         }
@@ -421,6 +473,7 @@ static int launch_ball_group(int b, int n, int m, float radius, float thr, int n
     static BgOnce once;
     size_t dyn = bg_smem_bytes(n);
     if (dyn > kBgSmemMax) return (int)cudaErrorInvalidValue;
+    if (bg_dual_layout(n)) dyn += (size_t)n * 16;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return (int)e;

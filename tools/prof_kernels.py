@@ -26,6 +26,9 @@ if case == "layer_cfg2":
     x = T(W.cloud_uniform(32, 4096, 100)); run(lambda: sample_group(1024, 0.1, 32, x, center=False))
 elif case == "layer_cfg4":
     x = T(W.cloud_duplicates(16, 8192, 100)); run(lambda: sample_group(1024, 0.1, 32, x, center=False))
+elif case == "bg_cfg3":
+    from pointnet2_b200.sa_layer import ball_group
+    x = T(W.cloud_surface(32, 1024, 100)); q = x[:, :512].contiguous(); run(lambda: ball_group(0.4, 128, x, q, center=True))
 elif case == "layer_cfg3":
     x = T(W.cloud_surface(32, 1024, 100)); run(lambda: sample_group(512, 0.2, 32, x, center=False))
 elif case in ("concat64", "concat320"):
