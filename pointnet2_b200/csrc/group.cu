@@ -145,22 +145,41 @@ group_rows_kernel(int n, int c, int nsample, unsigned rows_per_cloud, const floa
     const int* __restrict__ cidx = idx + cloud_row0;
     const float* __restrict__ cpts = points ? points + (size_t)cloud * n * c : nullptr;
     const float* __restrict__ cxyz = HAS_XYZ ? xyz + (size_t)cloud * n * 3 : nullptr;
-    for (unsigned r = warp * RPW + sub; r < rows_per_cloud; r += warps * RPW) {
-        const int a = __ldg(cidx + r);
-        float* __restrict__ dst = out + (cloud_row0 + r) * w;
-        if (HAS_XYZ) {
-            if (g < 3) {
+    // R rows per lane group and trip, U words per row and lane in flight: what limits these copies is bytes in
+    // flight per SM (measured: 32 KB/SM -> 3.5 TB/s, 64 KB/SM -> 5.5 TB/s for the same gather), so all R*U loads of a
+    // trip are issued before the first store
+    constexpr int R = 2, U = 4;  // measured at C = 320 + 3: R = 2: 58 / 94 / 172 us (38 registers); R = 4: 66 / 103 / 180 us (58 registers)
+    for (unsigned r0 = (warp * RPW + sub) * R; r0 < rows_per_cloud; r0 += warps * RPW * R) {
+        const float* __restrict__ src[R];
+        float* __restrict__ d[R];
+        bool ok[R];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const unsigned r = r0 + rr;
+            ok[rr] = r < rows_per_cloud;
+            const int a = ok[rr] ? __ldg(cidx + r) : 0;
+            float* __restrict__ dst = out + (cloud_row0 + r) * w;
+            src[rr] = cpts ? cpts + (size_t)a * c : nullptr;
+            d[rr] = dst + feat_lo;
+            if (HAS_XYZ && ok[rr] && g < 3) {
                 const size_t ctr = (size_t)cloud * (rows_per_cloud / (unsigned)nsample) + r / (unsigned)nsample;  // global centroid index
                 const float v = __fsub_rn(__ldg(cxyz + (size_t)a * 3 + g), __ldg(new_xyz + ctr * 3 + g));
                 __stcs(dst + xyz_lo + g, v);
                 if (grouped_xyz) __stcs(grouped_xyz + (cloud_row0 + r) * 3 + g, v);
             }
         }
-        if (c > 0) {
-            const float* __restrict__ src = cpts + (size_t)a * c;
-            float* __restrict__ d = dst + feat_lo;
-#pragma unroll 4
-            for (int l = g; l < c; l += LPR) __stcs(d + l, __ldg(src + l));
+        for (int l0 = g; l0 < c; l0 += LPR * U) {
+            float v[R][U];
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (ok[rr] && l0 + u * LPR < c) v[rr][u] = __ldg(src[rr] + l0 + u * LPR);
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (ok[rr] && l0 + u * LPR < c) __stcs(d[rr] + l0 + u * LPR, v[rr][u]);
         }
     }
 }
@@ -318,9 +337,8 @@ static int launch_group_rows(int b, int n, int c, int m, int nsample, const floa
         return finish_launch();
     }
     if (HAS_XYZ && c >= 8 && c <= 64 && c % 4 == 0 && aligned16(points) && aligned16(out)) {
-        // vectorised tail (see group_concat_vec_kernel).  Measured (profiles/r2_report.json): it wins at C = 64 (30.7 against
-        // 34.8 us, cfg4 SA256) and loses to the plain row kernel below from C = 128 up (C = 320: 125 against 103 us), so
-        // only narrow rows take it
+        // vectorised tail (see group_concat_vec_kernel).  Measured: it wins at C = 64 (30.7 against 35.6 us, cfg4 SA256) and
+        // loses to the row kernel below from C = 128 up (C = 320 + 3, S = 64: 125 against 94 us), so only narrow rows take it
         const int c4 = c / 4;
         const int lpr = c4 <= 8 ? 8 : (c4 <= 16 ? 16 : 32);
         constexpr int R = 2;
@@ -337,7 +355,7 @@ static int launch_group_rows(int b, int n, int c, int m, int nsample, const floa
         return finish_launch();
     }
     const int lpr = w <= 4 ? 4 : (w <= 8 ? 8 : (w <= 16 ? 16 : 32));
-    const unsigned rows_per_block = (kCopyThreads / 32) * (32 / lpr);
+    const unsigned rows_per_block = (kCopyThreads / 32) * (32 / lpr) * 2;  // R = 2 rows per lane group and trip
     unsigned gx = (rpc + rows_per_block - 1) / rows_per_block;
     const unsigned cap = (148u * 32u + b - 1) / b;  // enough CTAs to fill the machine, then grid-stride
     if (gx > cap) gx = cap;
