@@ -15,8 +15,9 @@
 //     broken by original index.  Only two kinds of elements can ever move or be selected: the k
 //     elements that start at positions < k (set A) and the k smallest of the rest under
 //     (value, position) (set B) — every other element keeps its position and always loses to an
-//     unselected member of B.  So the kernel (1) scans the row once, keeping A and a sorted top-k
-//     list B in shared memory, then (2) replays the k rounds on those <= 2k elements with their
+//     unselected member of B.  So the kernel (1) scans the row once, keeping A in shared memory and
+//     a sorted top-k list B in registers (one entry per lane and register: an insertion is a few
+//     ballots and shuffles), then (2) replays the k rounds on those <= 2k elements with their
 //     current positions.  The result equals the first k columns of selection_sort_gpu exactly.
 //
 // One warp per query; the data points of the query's cloud are staged through shared-memory tiles
@@ -32,6 +33,7 @@ constexpr int kKnnWarps = kKnnThreads / 32;
 constexpr int kKnnTile = 1024;  // data points per shared-memory tile
 constexpr int kKnnMaxK = 128;
 
+template <int KC>  // registers per lane that hold the sorted list B: k <= 32 * KC
 __global__ void __launch_bounds__(kKnnThreads)
 knn_kernel(int n, int m, int k, const float* __restrict__ xyz1, const float* __restrict__ xyz2, float* __restrict__ val,
            int* __restrict__ idx) {
@@ -56,12 +58,19 @@ knn_kernel(int n, int m, int k, const float* __restrict__ xyz1, const float* __r
     float* __restrict__ wv = s_wv[warp];
     int* __restrict__ wo = s_wo[warp];
     int* __restrict__ wp = s_wp[warp];
-    float* __restrict__ bv = wv + k;  // the sorted list B
-    int* __restrict__ bo = wo + k;
+    // the sorted list B lives in REGISTERS while the row is scanned: entry e = register e/32 of lane e%32.  An insertion
+    // is a handful of ballots and shuffles (no shared memory, no __syncwarp): round 2's first version kept B in shared
+    // memory and spent most of its time in the read-sync-write shifts (1.02 ms at 32 x 1024 x 4096, k = 32).
+    float bv[KC];
+    int bo[KC];
+#pragma unroll
+    for (int c = 0; c < KC; ++c) {
+        bv[c] = INFINITY;
+        bo[c] = 0;
+    }
     const int ka = min(k, n);       // |A|
     int nb = 0;                     // |B| so far (<= k)
     float tau = INFINITY;           // B full: its largest value; a later position must be strictly smaller to enter
-    const unsigned lt_mask = (1u << lane) - 1u;
 
     for (int base = 0; base < n; base += kKnnTile) {
         const int tn = min(kKnnTile, n - base);
@@ -95,40 +104,49 @@ knn_kernel(int n, int m, int k, const float* __restrict__ xyz1, const float* __r
                 if (nb == k && !(dv < tau)) continue;  // tau may have dropped since the ballot (warp-uniform)
                 // insertion point: after every entry with value <= dv (an equal value at an earlier position stays ahead)
                 int ins = 0;
-                for (int c = 0; c < nb; c += 32) {
-                    const int e = c + lane;
-                    ins += __popc(__ballot_sync(kFullMask, e < nb && bv[e] <= dv));
-                }
-                const int last = min(nb, k - 1);  // highest slot that stays (the k-th entry falls off when full)
-                // shift [ins, last) one slot up: read, sync, write
-                for (int c = ((last - 1) / 32) * 32; last > ins && c >= (ins / 32) * 32; c -= 32) {
-                    const int e = c + lane;
-                    float tv = 0.f;
-                    int to = 0;
-                    const bool mv = e >= ins && e < last;
-                    if (mv) {
-                        tv = bv[e];
-                        to = bo[e];
+#pragma unroll
+                for (int c = 0; c < KC; ++c) ins += __popc(__ballot_sync(kFullMask, 32 * c + lane < nb && bv[c] <= dv));
+                // shift the entries from `ins` on one slot up (the k-th falls off a full list), highest register first
+#pragma unroll
+                for (int c = KC - 1; c >= 0; --c) {
+                    float upv = __shfl_up_sync(kFullMask, bv[c], 1);
+                    int upo = __shfl_up_sync(kFullMask, bo[c], 1);
+                    if (c > 0) {  // lane 0 takes the last entry of the register below
+                        const float cv = __shfl_sync(kFullMask, bv[c - 1], 31);
+                        const int co = __shfl_sync(kFullMask, bo[c - 1], 31);
+                        if (lane == 0) {
+                            upv = cv;
+                            upo = co;
+                        }
                     }
-                    __syncwarp();
-                    if (mv) {
-                        bv[e + 1] = tv;
-                        bo[e + 1] = to;
+                    const int e = 32 * c + lane;
+                    if (e > ins) {
+                        bv[c] = upv;
+                        bo[c] = upo;
+                    } else if (e == ins) {
+                        bv[c] = dv;
+                        bo[c] = dpos;
                     }
-                    __syncwarp();
-                }
-                __syncwarp();  // every lane's reads of the list above are done before the slot is written
-                if (lane == 0) {
-                    bv[ins] = dv;
-                    bo[ins] = dpos;
                 }
                 if (nb < k) ++nb;
-                __syncwarp();
-                if (nb == k) tau = bv[k - 1];
+                if (nb == k) {  // the k-th entry: register (k-1)/32 of lane (k-1)%32
+                    float t = bv[0];
+#pragma unroll
+                    for (int c = 1; c < KC; ++c)
+                        if ((k - 1) / 32 == c) t = bv[c];
+                    tau = __shfl_sync(kFullMask, t, (k - 1) & 31);
+                }
             }
         }
     }
     if (!valid) return;
+#pragma unroll
+    for (int c = 0; c < KC; ++c) {
+        if (32 * c + lane < nb) {
+            wv[k + 32 * c + lane] = bv[c];
+            wo[k + 32 * c + lane] = bo[c];
+        }
+    }
     __syncwarp();
 
     // ---- phase 2: replay the selection sort on W = A ∪ B -------------------------------------------
@@ -189,7 +207,9 @@ int pn2_knn_point(int b, int n, int m, int k, const float* xyz1, const float* xy
     if (b == 0 || m == 0) return 0;
     if (!xyz1 || !xyz2 || !val || !idx || b > 65535) return (int)cudaErrorInvalidValue;
     dim3 grid((m + kKnnWarps - 1) / kKnnWarps, b, 1);
-    knn_kernel<<<grid, kKnnThreads, 0, as_stream(stream)>>>(n, m, k, xyz1, xyz2, val, idx);
+    if (k <= 32) knn_kernel<1><<<grid, kKnnThreads, 0, as_stream(stream)>>>(n, m, k, xyz1, xyz2, val, idx);
+    else if (k <= 64) knn_kernel<2><<<grid, kKnnThreads, 0, as_stream(stream)>>>(n, m, k, xyz1, xyz2, val, idx);
+    else knn_kernel<4><<<grid, kKnnThreads, 0, as_stream(stream)>>>(n, m, k, xyz1, xyz2, val, idx);
     return finish_launch();
 }
 
