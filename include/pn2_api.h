@@ -40,12 +40,13 @@ extern "C" {
  * inp (b,n,3) f32; out (b,m) i32.  out[:,0] = 0; selection order and tie-break identical to the
  * reference kernel (:105-170): argmax of the running min squared distance under
  * (value desc, k mod 512 asc, k asc).  `temp` is the reference's (32,n) float scratch
- * (tf_sampling_g.cu:202).  Clouds of up to 262144 points keep the running minimum in registers and
- * never touch it (temp may be NULL); larger clouds take the reference's global-scratch layout and
- * need pn2_fps_scratch_bytes(b, n) bytes there (cudaErrorInvalidValue if temp is NULL then). */
+ * (tf_sampling_g.cu:202).  Clouds of up to 425984 points (16 CTAs x 512 threads x 52 points) keep the
+ * running minimum in registers and never touch it (temp may be NULL); larger clouds take the reference's
+ * global-scratch layout and need pn2_fps_scratch_bytes(b, n) bytes there (cudaErrorInvalidValue if temp
+ * is NULL then). */
 int pn2_fps(int b, int n, int m, const float* inp, float* temp, int* out, void* stream);
 
-/* Bytes of `temp` pn2_fps / pn2_fps_gather need for (b, n): 0 up to n = 262144, else
+/* Bytes of `temp` pn2_fps / pn2_fps_gather need for (b, n): 0 up to n = 425984, else
  * min(b,32)*n*sizeof(float). */
 size_t pn2_fps_scratch_bytes(int b, int n);
 

@@ -386,6 +386,182 @@ fps_cluster_kernel(int n, int m, int log2c, const float* __restrict__ xyz, int* 
 }
 
 // =================================================================================================
+// Clusters for the largest clouds (8 x 262 144 points on one GPU).  B200 keeps only SEVEN 16-CTA
+// clusters resident when each CTA needs an SM of its own (cudaOccupancyMaxActiveClusters,
+// profiles/r2_fps_cluster_occupancy.txt), so eight such clouds ran as two waves.  Smaller clusters are
+// co-resident but then a CTA has to hold more points than fit when every point also sits in shared
+// memory.  Here the PR register-resident points per thread are NOT copied to shared memory — the
+// shared memory holds only the P-PR streamed points per thread — which makes the capacity of an SM
+// registers + shared memory (T = 512: 16 + 36 points per thread = 26 624 points) and lets clusters of
+// any size 2..16 (C*T is a multiple of 512 for every C) take 262 144 points with 10-12 CTAs.
+// The price: the CTA's candidate coordinates can no longer be looked up by warp 0.  Instead every
+// warp reduces the CTA's per-warp keys (as the single-CTA kernel does), the warp that owns the
+// winning thread is the sender, and the winning lane takes the coordinates from its own registers
+// (a select chain over PR entries, issued by that one warp) or from its own shared-memory column.
+// =================================================================================================
+template <int P, int T, int PR>
+__global__ void __launch_bounds__(T, 1)
+fps_cluster_big_kernel(int n, int m, int C, const float* __restrict__ xyz, int* __restrict__ idx_out,
+                       float* __restrict__ new_xyz) {
+    static_assert(T % 512 == 0, "every thread's points must share one reference slot for any cluster size");
+    static_assert(PR < P && (P - PR) % 4 == 0, "streamed points come in groups of four");
+    constexpr int NW = T / 32;
+    constexpr int NG = (P - PR) / 4;
+    __shared__ uint2 s_keys[2][32];
+    __shared__ __align__(16) uint4 s_xa[2][16];   // per peer: (key lo, key hi, x bits, y bits)
+    __shared__ __align__(4) unsigned s_xz[2][16];  // per peer: z bits
+    __shared__ __align__(8) unsigned long long s_mbar[2];
+    // streamed points only: float4 groups [(g*3 + c)*T + t], .x..w = point PR + 4g + u of thread t
+    extern __shared__ __align__(16) float s_pts[];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned rank = cluster_ctarank();
+    const int cloud = blockIdx.x / C;
+    const float* __restrict__ pts = xyz + (size_t)cloud * n * 3;
+    int* __restrict__ out = idx_out + (size_t)cloud * m;
+    float* __restrict__ oxyz = new_xyz ? new_xyz + (size_t)cloud * m * 3 : nullptr;
+
+    if (tid == 0) {
+        mbar_init(smem_addr(&s_mbar[0]), 1);
+        mbar_init(smem_addr(&s_mbar[1]), 1);
+        fence_mbar_init_cluster();
+    }
+
+    float px[PR], py[PR], pz[PR], td[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const long long k = (long long)tid + (long long)T * (rank + (long long)C * j);
+        float x = 0.f, y = 0.f, z = 0.f, t = -1.0f;
+        if (k < n) {
+            x = pts[3 * k + 0];
+            y = pts[3 * k + 1];
+            z = pts[3 * k + 2];
+            t = 1e38f;
+        }
+        td[j] = t;
+        if (j < PR) {
+            px[j] = x;
+            py[j] = y;
+            pz[j] = z;
+        } else {
+            const int g = (j - PR) >> 2, u = (j - PR) & 3;
+            s_pts[(((g * 3 + 0) * T + tid) << 2) + u] = x;
+            s_pts[(((g * 3 + 1) * T + tid) << 2) + u] = y;
+            s_pts[(((g * 3 + 2) * T + tid) << 2) + u] = z;
+        }
+    }
+
+    float x1 = pts[0], y1 = pts[1], z1 = pts[2];
+    if (rank == 0 && tid == 0) {
+        out[0] = 0;
+        if (oxyz) {
+            oxyz[0] = x1;
+            oxyz[1] = y1;
+            oxyz[2] = z1;
+        }
+    }
+    cluster_sync_all();  // every peer's mbarriers are initialised before anyone targets them
+
+    const unsigned mbar0 = smem_addr(&s_mbar[0]), mbar1 = smem_addr(&s_mbar[1]);
+    const float4* __restrict__ s4 = reinterpret_cast<const float4*>(s_pts);
+    const unsigned uc = (unsigned)C;
+
+    for (int it = 1; it < m; ++it) {
+        const int q = it - 1, buf = q & 1;
+        const unsigned parity = (unsigned)(q >> 1) & 1u;
+        const unsigned mbar = buf ? mbar1 : mbar0;
+        if (tid == 0) mbar_arrive_expect_tx(mbar, 20u * uc);
+
+        float best;
+        int bj;
+        fps_step<PR, 1, P>(px, py, pz, td, x1, y1, z1, best, bj);
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            const float4 X = s4[(g * 3 + 0) * T + tid], Y = s4[(g * 3 + 1) * T + tid], Z = s4[(g * 3 + 2) * T + tid];
+            const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = PR + 4 * g + u;
+                const float d = d2_fma_pattern(xs[u], ys[u], zs[u], x1, y1, z1);
+                const float d2 = fminf(d, td[j]);
+                td[j] = d2;
+                if (d2 > best) {
+                    best = d2;
+                    bj = j;
+                }
+            }
+        }
+        unsigned myhi = 0u, mylo = 0u;
+        if (best >= 0.0f) {
+            myhi = __float_as_uint(best);
+            mylo = ~tb_encode((unsigned)(tid + T * (rank + uc * bj)));
+        }
+        unsigned hi = myhi, lo = mylo;
+        warp_max_pair(hi, lo);
+        if (lane == 0) s_keys[buf][warp] = make_uint2(lo, hi);
+        __syncthreads();
+        // every warp reduces the CTA's keys; the warp whose entry is the maximum sends (all-zero keys: warp 0)
+        const uint2 e = (lane < NW) ? s_keys[buf][lane] : make_uint2(0u, 0u);
+        unsigned ch = e.y, cl = e.x;
+        warp_max_pair(ch, cl);
+        const unsigned wmask = __ballot_sync(0xffffffffu, lane < NW && e.x == cl && e.y == ch);
+        if (warp == __ffs((int)wmask) - 1) {
+            const unsigned lmask = __ballot_sync(0xffffffffu, mylo == cl && myhi == ch);
+            const int wl = __ffs((int)lmask) - 1;  // the winning thread's lane (keys are unique unless all are zero)
+            float cx = 0.f, cy = 0.f, cz = 0.f;
+#pragma unroll
+            for (int j = 0; j < PR; ++j)
+                if (bj == j) {
+                    cx = px[j];
+                    cy = py[j];
+                    cz = pz[j];
+                }
+            if (bj >= PR) {
+                const int g = (bj - PR) >> 2, u = (bj - PR) & 3;
+                cx = s_pts[(((g * 3 + 0) * T + tid) << 2) + u];
+                cy = s_pts[(((g * 3 + 1) * T + tid) << 2) + u];
+                cz = s_pts[(((g * 3 + 2) * T + tid) << 2) + u];
+            }
+            cx = __shfl_sync(0xffffffffu, cx, wl);
+            cy = __shfl_sync(0xffffffffu, cy, wl);
+            cz = __shfl_sync(0xffffffffu, cz, wl);
+            const unsigned ul = (unsigned)lane;
+            if (ul < uc) {
+                st_async_v4(mapa_shared(smem_addr(&s_xa[buf][rank]), ul), cl, ch, __float_as_uint(cx), __float_as_uint(cy),
+                            mapa_shared(mbar, ul));
+            } else if (ul < 2u * uc) {
+                st_async_u32(mapa_shared(smem_addr(&s_xz[buf][rank]), ul - uc), __float_as_uint(cz), mapa_shared(mbar, ul - uc));
+            }
+        }
+        mbar_wait_parity_cluster(mbar, parity);
+        unsigned kh = 0u, kl = 0u;
+        if ((unsigned)lane < uc) {
+            const uint2 kk = *reinterpret_cast<const uint2*>(&s_xa[buf][lane]);
+            kl = kk.x;
+            kh = kk.y;
+        }
+        unsigned gh = kh, gl = kl;
+        warp_max_pair(gh, gl);
+        const int old = (int)tb_decode(~gl);
+        const unsigned omask = __ballot_sync(0xffffffffu, (unsigned)lane < uc && kl == gl && kh == gh);
+        const int wr = __ffs((int)omask) - 1;  // the CTA that owns the winner
+        const uint4 wa = s_xa[buf][wr];
+        x1 = __uint_as_float(wa.z);
+        y1 = __uint_as_float(wa.w);
+        z1 = __uint_as_float(s_xz[buf][wr]);
+        if (rank == 0 && tid == 0) {
+            out[it] = old;
+            if (oxyz) {
+                oxyz[3 * it + 0] = x1;
+                oxyz[3 * it + 1] = y1;
+                oxyz[3 * it + 2] = z1;
+            }
+        }
+    }
+    cluster_sync_all();  // no CTA may exit while a peer can still write into its shared memory
+}
+
+// =================================================================================================
 // Any-size fallback: running minimum in caller-provided global scratch (32*n floats, the
 // reference's own requirement, tf_sampling_g.cu:202), grid of <= 32 CTAs looping over clouds.
 // =================================================================================================
@@ -572,6 +748,58 @@ static int cluster_capacity(int C) {
     return num;
 }
 
+template <int P, int T, int PR>
+static cudaLaunchConfig_t big_config(int C, int clusters, cudaLaunchAttribute* attr, cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)clusters * (unsigned)C, 1, 1);
+    cfg.blockDim = dim3(T, 1, 1);
+    cfg.dynamicSmemBytes = (size_t)3 * (P - PR) * T * sizeof(float);
+    cfg.stream = st;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cfg;
+}
+
+template <int P, int T, int PR>
+static int launch_cluster_big(int C, int b, int n, int m, const float* inp, int* out, float* new_xyz, cudaStream_t st) {
+    static AttrOnce once;
+    auto kern = fps_cluster_big_kernel<P, T, PR>;
+    cudaLaunchAttribute attr[1];
+    cudaLaunchConfig_t cfg = big_config<P, T, PR>(C, b, attr, st);
+    if (cfg.dynamicSmemBytes > 226 * 1024) return (int)cudaErrorInvalidValue;
+    cudaError_t e = ensure_attrs(once, kern, cfg.dynamicSmemBytes, true);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaLaunchKernelEx(&cfg, kern, n, m, C, inp, out, new_xyz);
+    count_launch();
+    if (e != cudaSuccess) return (int)e;
+    return (int)cudaGetLastError();
+}
+
+template <int P, int T, int PR>
+static int cluster_big_capacity(int C) {
+    static std::atomic<int> cache[17][64];  // [C][device]; 0 = not asked yet
+    int dev = 0;
+    if (C < 2 || C > 16 || cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+    const int hit = cache[C][dev].load(std::memory_order_relaxed);
+    if (hit) return hit > 0 ? hit : 0;
+    static AttrOnce once;
+    auto kern = fps_cluster_big_kernel<P, T, PR>;
+    cudaLaunchAttribute attr[1];
+    cudaLaunchConfig_t cfg = big_config<P, T, PR>(C, 148, attr, nullptr);
+    if (cfg.dynamicSmemBytes > 226 * 1024 || ensure_attrs(once, kern, cfg.dynamicSmemBytes, true) != cudaSuccess) return 0;
+    int num = 0;
+    if (cudaOccupancyMaxActiveClusters(&num, kern, &cfg) != cudaSuccess) {
+        (void)cudaGetLastError();
+        num = 0;
+    }
+    cache[C][dev].store(num > 0 ? num : -1, std::memory_order_relaxed);
+    return num;
+}
+
 struct FpsPlan {
     int threads, ppt, cluster;  // cluster == 0: global-scratch fallback; 1: single CTA; >= 2: thread-block cluster
     int pr;                     // cluster kernels: points per thread with register-resident coordinates (== ppt: all)
@@ -597,7 +825,7 @@ static FpsPlan plan_fps(int b, int n) {
         p.threads = (int)(ov >> 40);
         p.ppt = (int)((ov >> 20) & 0xfffff);
         p.cluster = (int)(ov & 0xfffff) - 64;
-        p.pr = (p.ppt >= 32 && p.threads >= 512) ? 16 : p.ppt;
+        p.pr = (p.ppt >= 32 && p.threads >= 512) ? 16 : p.ppt;  // ppt > 32: the register + shared-memory kernel
         return p;
     }
     // single CTA, register-resident (cluster = 1).  Measured on B200 (profiles/r1_fps_sweep*.json):
@@ -647,10 +875,32 @@ static FpsPlan plan_fps(int b, int n) {
         const int cap = fps_cluster_capacity(p.threads, p.ppt, p.cluster);
         if (cap == 0 || cap >= b) return p;
     }
-    if (first.cluster) return first;  // nothing fits at once: widest cluster, several waves
-    FpsPlan p;
-    // widest cluster regardless of co-residency
-    if (pick(((long long)n + 15) / 16, 16, p)) return p;
+    // No power-of-two cluster keeps all b clouds resident (B200 holds seven clusters of 11-16 CTAs, eleven of 10,
+    // fifteen of 7-9: profiles/r2_fps_cluster_occupancy.txt), or none holds the cloud at all (n > 262 144).
+    // Candidates: the widest power-of-two clusters in several waves, and the register + shared-memory kernel
+    // (up to 512*52 points per CTA, any cluster size).  Cost model fitted to profiles/r2_fps_sweep_large.json and
+    // r2_fps_cluster_big.json: a step costs 0.3 us + 0.07 us per 1000 point slots of a CTA; waves run back to back.
+    FpsPlan best{0, 0, 0, 0};
+    double best_cost = 1e30;
+    auto consider = [&](const FpsPlan& p) {
+        const int cap = fps_cluster_capacity(p.threads, p.ppt, p.cluster);
+        const int waves = cap > 0 ? (b + cap - 1) / cap : 1;
+        double cost = waves * (0.3 + 0.07e-3 * (double)p.threads * p.ppt);
+        if (cap > 0 && (long long)cap * p.cluster > 148) cost *= 1.3;  // CTAs of a wave share SMs (measured: 0.59 -> 0.77 us)
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = p;
+        }
+    };
+    if (first.cluster) consider(first);
+    FpsPlan widest;
+    if (pick(((long long)n + 15) / 16, 16, widest)) consider(widest);
+    for (int C = 16; C >= 2; --C) {
+        const long long per = ((long long)n + C - 1) / C;
+        if (per > 512LL * 52) break;
+        consider({512, per <= 512LL * 44 ? 44 : (per <= 512LL * 48 ? 48 : 52), C, 16});
+    }
+    if (best.cluster) return best;
     return {1024, 0, 0, 0};
 }
 
@@ -701,6 +951,13 @@ int fps_dispatch(int b, int n, int m, const float* inp, float* temp, int* out, f
         PN2_TRY_CTA(8, 1024)
         return (int)cudaErrorInvalidValue;
     }
+    if (plan.cluster >= 2 && plan.ppt > 32) {  // register + shared-memory kernel, any cluster size
+        if (plan.cluster > 16 || plan.threads != 512) return (int)cudaErrorInvalidValue;
+        if (plan.ppt == 44) return launch_cluster_big<44, 512, 16>(plan.cluster, b, n, m, inp, out, new_xyz, st);
+        if (plan.ppt == 48) return launch_cluster_big<48, 512, 12>(plan.cluster, b, n, m, inp, out, new_xyz, st);
+        if (plan.ppt == 52) return launch_cluster_big<52, 512, 16>(plan.cluster, b, n, m, inp, out, new_xyz, st);
+        return (int)cudaErrorInvalidValue;
+    }
     if (plan.cluster >= 2) {
         if (plan.cluster > 16 || (plan.cluster & (plan.cluster - 1))) return (int)cudaErrorInvalidValue;
         if (((long long)plan.cluster * plan.threads) % 512 != 0) return (int)cudaErrorInvalidValue;
@@ -734,6 +991,9 @@ int fps_dispatch(int b, int n, int m, const float* inp, float* temp, int* out, f
 #define PN2_CAP_CLU(PP, TT, PRR) \
     if (ppt == PP && threads == TT) return cluster_capacity<PP, TT, PRR>(cluster);
 int fps_cluster_capacity(int threads, int ppt, int cluster) {
+    if (threads == 512 && ppt == 44) return cluster_big_capacity<44, 512, 16>(cluster);
+    if (threads == 512 && ppt == 48) return cluster_big_capacity<48, 512, 12>(cluster);
+    if (threads == 512 && ppt == 52) return cluster_big_capacity<52, 512, 16>(cluster);
     if (cluster < 2 || cluster > 16 || (cluster & (cluster - 1))) return 0;
     PN2_CAP_CLU(4, 128, 4)
     PN2_CAP_CLU(8, 128, 8)

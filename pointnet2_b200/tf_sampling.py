@@ -75,7 +75,7 @@ def farthest_point_sample(npoint: int, inp: torch.Tensor) -> torch.Tensor:
         return out
     lib = _lib.load()
     with on_device(inp):
-        # clouds beyond the cluster kernels' capacity (n > 262144) need the reference's own
+        # clouds beyond the cluster kernels' capacity (n > 425984) need the reference's own
         # (32, n) float scratch (tf_sampling.cpp:115); the library says how much
         tb = int(lib.pn2_fps_scratch_bytes(b, n))
         temp = torch.empty(tb, dtype=torch.uint8, device=inp.device) if tb else None

@@ -58,6 +58,24 @@ def test_large_fps_matches_reference_kernel(dev, gen, b, n, m):
     assert torch.equal(fi, ref) and torch.equal(fx, O.refcuda_gather_point(x, ref))
 
 
+def test_eight_clouds_of_262144_points_run_as_co_resident_clusters(dev):
+    """8 x 262 144 points: no power-of-two cluster size keeps eight clusters resident on B200 (seven 16-CTA clusters
+    fit), so the planner must pick the register + shared-memory kernel with a smaller cluster — and the picks must
+    be the ones the one-cloud-at-a-time plan (16-CTA clusters, validated against the reference kernel above) makes."""
+    import ctypes
+    lib = _lib.load()
+    b, n, m = 8, 262144, 48
+    t, pp, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    assert lib.pn2_fps_plan(b, n, ctypes.byref(t), ctypes.byref(pp), ctypes.byref(c)) == 0
+    assert c.value >= 2 and t.value * pp.value * c.value >= n
+    assert lib.pn2_fps_cluster_capacity(t.value, pp.value, c.value) >= b, "planned clusters are not co-resident"
+    x = T(np.concatenate([W.cloud_duplicates(4, n, 131), W.cloud_uniform(4, n, 132)]), dev)
+    idx, new_xyz = farthest_point_sample_and_gather(m, x)
+    for i in range(b):
+        one_idx, one_xyz = farthest_point_sample_and_gather(m, x[i:i + 1].contiguous())
+        assert torch.equal(idx[i:i + 1], one_idx) and torch.equal(new_xyz[i:i + 1], one_xyz)
+
+
 # ---- cfg4: the whole FP stack at B = 16 (tf_interpolate.cpp:60-127) ------------------------------------------
 @needs_refcpu
 def test_cfg4_fp_stack_matches_reference_cpu_functions(dev):

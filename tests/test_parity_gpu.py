@@ -47,7 +47,9 @@ def test_fps_matches_oracle(dev, gen, b, n, m):
 FPS_VARIANTS = [(512, 2, 2), (512, 1, 4), (512, 4, 2), (512, 8, 4), (1024, 2, 2), (512, 2, 8),
                 (512, 1, 16), (512, 16, 2), (512, 32, 2), (1024, 4, 1), (512, 8, 1), (512, 16, 1),
                 (256, 2, 2), (256, 8, 4), (256, 32, 2), (128, 4, 4), (128, 16, 8), (128, 32, 16), (256, 16, 16),
-                (128, 2, 1), (128, 8, 1), (128, 32, 1), (256, 2, 1), (256, 4, 1), (256, 16, 1), (256, 32, 1)]
+                (128, 2, 1), (128, 8, 1), (128, 32, 1), (256, 2, 1), (256, 4, 1), (256, 16, 1), (256, 32, 1),
+                # register + shared-memory cluster kernel (points per thread > 32), any cluster size incl. non-powers of two
+                (512, 44, 2), (512, 44, 3), (512, 44, 12), (512, 44, 16), (512, 48, 5), (512, 48, 11), (512, 48, 13), (512, 52, 10), (512, 52, 7)]
 
 
 @pytest.mark.parametrize("cfg", FPS_VARIANTS)
@@ -70,7 +72,8 @@ def test_fps_every_kernel_variant_matches_oracle(dev, cfg, gen):
 
 
 @pytest.mark.parametrize("cfg,n", [((512, 32, 16), 262144), ((512, 32, 16), 262143), ((512, 32, 2), 32768), ((256, 32, 16), 131072),
-                                   ((128, 32, 16), 65536), ((256, 16, 16), 65536), ((256, 32, 8), 65536)])
+                                   ((128, 32, 16), 65536), ((256, 16, 16), 65536), ((256, 32, 8), 65536),
+                                   ((512, 44, 12), 262144), ((512, 48, 11), 262144), ((512, 44, 3), 67584), ((512, 48, 7), 172032), ((512, 52, 10), 266240)])
 def test_fps_cluster_variants_at_full_capacity(dev, cfg, n):
     """The cluster kernels with EVERY per-thread slot occupied (the 512x32 variant had only
     been forced on n <= 5997, i.e. 31 of its 32 points per thread were padding).  Duplicate-heavy

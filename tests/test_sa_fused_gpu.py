@@ -14,7 +14,7 @@ from pointnet2_b200 import _lib, workloads as W
 from pointnet2_b200.host import SetAbstractionHost
 from pointnet2_b200.sa_layer import SetAbstractionDevice, ball_group, sample_group, sample_group_msg
 from pointnet2_b200.tf_grouping import group_point, query_ball_point
-from pointnet2_b200.tf_sampling import farthest_point_sample, gather_point
+from pointnet2_b200.tf_sampling import farthest_point_sample, farthest_point_sample_and_gather, gather_point
 
 pytestmark = pytest.mark.gpu
 
@@ -223,10 +223,10 @@ def test_ball_group_nan_query_and_empty_rows(dev):
 
 # ------------------------------------------------------------------------------------------- C-ABI robustness
 def test_fps_gather_and_host_layer_beyond_the_cluster_capacity(dev):
-    """n > 262144 takes the global-scratch kernel: pn2_fps_gather and pn2_sa_layer_host must serve
-    it (round 1 passed temp = NULL and returned cudaErrorInvalidValue)."""
+    """n > 16 * 512 * 52 = 425 984 takes the global-scratch kernel: pn2_fps_gather and pn2_sa_layer_host must
+    serve it (round 1 passed temp = NULL and returned cudaErrorInvalidValue)."""
     lib = _lib.load()
-    b, n, m = 2, 262145 + 300, 8
+    b, n, m = 2, 425984 + 300, 8
     xyz = W.cloud_uniform(b, n, 65)
     want = O.oracle_fps(m, xyz)
     x = T(xyz, dev)
@@ -247,6 +247,19 @@ def test_fps_gather_and_host_layer_beyond_the_cluster_capacity(dev):
     oi, oc = O.oracle_query_ball_point(0.01, 4, xyz, new_xyz)
     np.testing.assert_array_equal(idx, oi)
     np.testing.assert_array_equal(cnt, oc)
+
+
+def test_fps_between_262144_and_425984_points_needs_no_scratch(dev):
+    """Clouds beyond the 16 x 16 384 points of the all-in-shared-memory clusters are held in registers + shared
+    memory (fps_cluster_big_kernel): no scratch, same picks as the CPU restatement."""
+    lib = _lib.load()
+    b, n, m = 2, 300001, 24
+    assert int(lib.pn2_fps_scratch_bytes(b, n)) == 0
+    xyz = np.concatenate([W.cloud_uniform(1, n, 67), W.cloud_duplicates(1, n, 68)])
+    want = O.oracle_fps(m, xyz)
+    fi, fx = farthest_point_sample_and_gather(m, T(xyz, dev))
+    np.testing.assert_array_equal(fi.cpu().numpy(), want)
+    np.testing.assert_array_equal(fx.cpu().numpy(), O.oracle_gather_point(xyz, want))
 
 
 def test_host_layer_idx_only_mode(dev):

@@ -11,3 +11,8 @@ for t, p in [(128, 4), (128, 8), (128, 16), (128, 32), (256, 2), (256, 4), (256,
     for c in (2, 4, 8, 16):
         k = lib.pn2_fps_cluster_capacity(t, p, c)
         print(f"{t:5d} {p:3d} {c:4d} {3*p*t*4/1024:7.1f} {k:5d} {k*c:5d}")
+print("# register + shared-memory cluster kernel (fps_cluster_big_kernel), any cluster size")
+for t, p in [(512, 44), (512, 48), (512, 52)]:
+    for c in range(2, 17):
+        k = lib.pn2_fps_cluster_capacity(t, p, c)
+        print(f"{t:5d} {p:3d} {c:4d} {3*(p-(12 if p == 48 else 16))*t*4/1024:7.1f} {k:5d} {k*c:5d}")

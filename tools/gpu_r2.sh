@@ -28,6 +28,11 @@ for stage in "$@"; do
       timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_ref_r2.json 2> gpurun_out/bench_ref_r2.err; head -c 600 gpurun_out/bench_ref_r2.json ;;
     report)
       timeout 1200 python bench.py --report gpurun_out/report_r2.json > gpurun_out/report_r2.log 2>&1; tail -3 gpurun_out/report_r2.log ;;
+    fpsbig)
+      timeout 900 python -m pytest tests/test_parity_gpu.py tests/test_full_size_parity_gpu.py tests/test_sa_fused_gpu.py -x -q -m gpu -k "fps or clouds" 2>&1 | tail -5
+      timeout 120 python tools/cluster_occupancy.py > gpurun_out/fps_cluster_occupancy.txt 2>&1; tail -32 gpurun_out/fps_cluster_occupancy.txt
+      timeout 600 python tools/fps_cluster_bench.py 2>&1 | tail -40
+      timeout 60 tools/experiments/cluster_probe > gpurun_out/cluster_probe.txt 2>&1; grep -A9 "^launch" gpurun_out/cluster_probe.txt | head -70 ;;
     sweep)
       PN2_SWEEP_LARGE=1 timeout 900 python bench.py --fps-sweep > gpurun_out/fps_sweep_large.log 2>&1; cp gpurun_out/fps_sweep.json gpurun_out/fps_sweep_large_r2.json 2>/dev/null; tail -3 gpurun_out/fps_sweep_large.log ;;
     launches)
