@@ -380,6 +380,7 @@ ball_group_kernel(int n, int m, float radius, float thr, int nsample, const floa
             // entries per store instruction — storing hit by hit costs 4 sparsely populated store instructions per
             // 32 points scanned, which made dense balls slower here than in the grid walk.
             const bool buffered = nsample <= kBgHitCap;
+            __syncwarp();  // an overflowed grid walk left entries in s_hits that other lanes overwrite below
             auto load_point = [&](int k, float& x, float& y, float& z) {
                 if (use_grid && !dual) {
                     x = __ldg(pts + 3 * (size_t)k);

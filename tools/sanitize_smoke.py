@@ -14,7 +14,7 @@ nx, npts, idx, gx = sample_and_group(64, 0.3, 16, xyz, f)
 npts.sum().backward()
 up = pointnet_fp_module(xyz, nx, None, npts.max(dim=2).values.detach())
 _ = pointnet_sa_module_msg(xyz, f.detach(), 32, [0.2, 0.4], [8, 16])
-for cfg in [(128, 32, 1), (128, 8, 4), (256, 8, 2), (512, 32, 2)]:
+for cfg in [(128, 32, 1), (128, 8, 4), (256, 8, 2), (512, 32, 2), (512, 44, 3), (512, 52, 5)]:
     lib.pn2_set_fps_config(*cfg)
     farthest_point_sample(40, xyz)
 lib.pn2_set_fps_config(0, 0, 0)
