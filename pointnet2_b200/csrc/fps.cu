@@ -141,7 +141,7 @@ fps_cta_kernel(int n, int m, const float* __restrict__ xyz, int* __restrict__ id
     constexpr int NW = T / 32;
     constexpr int D = (T >= 512) ? 1 : 512 / T;
     __shared__ uint2 s_keys[2][32];
-    extern __shared__ float s_xyz[];
+    extern __shared__ __align__(16) float s_xyz[];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cloud = blockIdx.x;
@@ -149,11 +149,44 @@ fps_cta_kernel(int n, int m, const float* __restrict__ xyz, int* __restrict__ id
     int* __restrict__ out = idx_out + (size_t)cloud * m;
     float* __restrict__ oxyz = new_xyz ? new_xyz + (size_t)cloud * m * 3 : nullptr;
 
+    // The cloud comes in as 16-byte loads, up to 12 per thread in flight before the first one is consumed, and the
+    // sentinel fill with its fence runs under them.  (Measured against the 4-byte copy loop this replaces: 0.3 us of
+    // the 332 us kernel at cfg2 — the prologue is not where the time goes; kept because it is the shorter chain.)
+    const int total = 3 * n;
+    const bool vec = (reinterpret_cast<size_t>(pts) & 15) == 0;  // always when n % 4 == 0
+    const int nv = vec ? (total >> 2) : 0;
+    const float4* __restrict__ p4 = reinterpret_cast<const float4*>(pts);
+    float4* __restrict__ s4 = reinterpret_cast<float4*>(s_xyz);
+    constexpr int LB = 12;
+    float4 v[LB];
+#pragma unroll
+    for (int u = 0; u < LB; ++u) {
+        const int e = u * T + tid;
+        if (e < nv) v[u] = __ldg(p4 + e);
+    }
     if (sentinel) {  // CTA-uniform
         for (int e = tid; e < m; e += T) out[e] = -1;
         __threadfence();  // the fill is performed device-wide before the dependent grid may start
     }
-    for (int e = tid; e < 3 * n; e += T) s_xyz[e] = pts[e];
+#pragma unroll
+    for (int u = 0; u < LB; ++u) {
+        const int e = u * T + tid;
+        if (e < nv) s4[e] = v[u];
+    }
+    for (int base = LB * T; base < nv; base += LB * T) {
+#pragma unroll
+        for (int u = 0; u < LB; ++u) {
+            const int e = base + u * T + tid;
+            if (e < nv) v[u] = __ldg(p4 + e);
+        }
+#pragma unroll
+        for (int u = 0; u < LB; ++u) {
+            const int e = base + u * T + tid;
+            if (e < nv) s4[e] = v[u];
+        }
+    }
+#pragma unroll 8
+    for (int e = (nv << 2) + tid; e < total; e += T) s_xyz[e] = pts[e];
     __syncthreads();
     if (sentinel) pdl_launch_dependents();
     const float* __restrict__ src = s_xyz;

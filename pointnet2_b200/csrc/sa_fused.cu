@@ -234,9 +234,16 @@ ball_group_kernel(int n, int m, float radius, float thr, int nsample, const floa
                 if (lane == 0) pts_cnt[(size_t)cloud * m + q] = -1;
                 continue;
             }
-            qx = __ldg(pts + 3 * (size_t)qi);
-            qy = __ldg(pts + 3 * (size_t)qi + 1);
-            qz = __ldg(pts + 3 * (size_t)qi + 2);
+            if (!use_grid || dual) {  // an index-ordered copy of the cloud is in shared memory: no L2 round trip
+                const float4 c = use_grid ? s_orig[qi] : s_pts[qi];
+                qx = c.x;
+                qy = c.y;
+                qz = c.z;
+            } else {
+                qx = __ldg(pts + 3 * (size_t)qi);
+                qy = __ldg(pts + 3 * (size_t)qi + 1);
+                qz = __ldg(pts + 3 * (size_t)qi + 2);
+            }
         } else {
             const float* qp = xyz2 + ((size_t)cloud * m + q) * 3;
             qx = __ldg(qp);
