@@ -64,7 +64,18 @@ def case_fps(rs):
     m = min(m, 600)
     kind, xyz = cloud(rs, b, n)
     p = dict(op="fps", b=b, n=n, m=m, kind=kind)
-    idx, new_xyz = farthest_point_sample_and_gather(m, T(xyz))
+    forced = None
+    if rs.random_sample() < 0.25:  # force the register + shared-memory cluster kernel at a random cluster size (2..16)
+        ppt = int(rs.choice([44, 48, 52]))
+        cmin = max(2, -(-n // (512 * ppt)))
+        forced = (512, ppt, int(rs.randint(cmin, 17)))
+        p["forced"] = forced
+        _lib.load().pn2_set_fps_config(*forced)
+    try:
+        idx, new_xyz = farthest_point_sample_and_gather(m, T(xyz))
+    finally:
+        if forced:
+            _lib.load().pn2_set_fps_config(0, 0, 0)
     want = O.oracle_fps(m, xyz)
     ok = np.array_equal(N(idx), want) and np.array_equal(N(new_xyz), O.oracle_gather_point(xyz, want))
     ok = ok and np.array_equal(N(gather_point(T(xyz), idx)), N(new_xyz))
