@@ -33,6 +33,44 @@ constexpr int kKnnWarps = kKnnThreads / 32;
 constexpr int kKnnTile = 1024;  // data points per shared-memory tile
 constexpr int kKnnMaxK = 128;
 
+// Ascending bitonic sort of 32*E 64-bit keys held E per lane (element i = register i/32 of lane i%32; E a power of 2).
+template <int E>
+__device__ __forceinline__ void bitonic_sort_u64(unsigned long long (&key)[E], int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32 * E; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 32) {  // partner in the same lane, another register
+                const int js = stride >> 5;
+#pragma unroll
+                for (int j = 0; j < E; ++j) {
+                    if ((j & js) == 0) {
+                        const bool up = (((32 * j) & size) == 0);
+                        const unsigned long long x = key[j], y = key[j | js];
+                        const bool sw = up ? (x > y) : (x < y);
+                        key[j] = sw ? y : x;
+                        key[j | js] = sw ? x : y;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < E; ++j) {
+                    const int i = 32 * j + lane;
+                    const unsigned long long other = __shfl_xor_sync(kFullMask, key[j], stride);
+                    const bool up = ((i & size) == 0), lower = ((lane & stride) == 0);
+                    const bool keep_min = (up == lower);  // the lower element of an ascending pair keeps the minimum
+                    key[j] = (keep_min == (other < key[j])) ? other : key[j];
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ float knn_dist(float x, float y, float z, float qx, float qy, float qz) {
+    const float dx = __fsub_rn(x, qx), dy = __fsub_rn(y, qy), dz = __fsub_rn(z, qz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
 template <int KC>  // registers per lane that hold the sorted list B: k <= 32 * KC
 __global__ void __launch_bounds__(kKnnThreads)
 knn_kernel(int n, int m, int k, const float* __restrict__ xyz1, const float* __restrict__ xyz2, float* __restrict__ val,
@@ -72,6 +110,62 @@ knn_kernel(int n, int m, int k, const float* __restrict__ xyz1, const float* __r
     int nb = 0;                     // |B| so far (<= k)
     float tau = INFINITY;           // B full: its largest value; a later position must be strictly smaller to enter
 
+    // set A: positions 0..k-1 keep their own slot (straight from global memory: at most 128 points)
+    if (valid)
+        for (int pos = lane; pos < ka; pos += 32) {
+            const float* s = data + (size_t)pos * 3;
+            wv[pos] = knn_dist(__ldg(s), __ldg(s + 1), __ldg(s + 2), qx, qy, qz);
+            wo[pos] = pos;
+        }
+
+    // one candidate group (32 consecutive positions, ascending): insert every lane of `cand` into the sorted list
+    auto insert_group = [&](unsigned cand, float d, int pos0) {
+        while (cand) {  // ascending position
+            const int src = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const float dv = __shfl_sync(kFullMask, d, src);
+            const int dpos = pos0 + src;
+            if (nb == k && !(dv < tau)) continue;  // tau may have dropped since the ballot (warp-uniform)
+            // insertion point: after every entry with value <= dv (an equal value at an earlier position stays ahead)
+            int ins = 0;
+#pragma unroll
+            for (int c = 0; c < KC; ++c) ins += __popc(__ballot_sync(kFullMask, 32 * c + lane < nb && bv[c] <= dv));
+            // shift the entries from `ins` on one slot up (the k-th falls off a full list), highest register first
+#pragma unroll
+            for (int c = KC - 1; c >= 0; --c) {
+                float upv = __shfl_up_sync(kFullMask, bv[c], 1);
+                int upo = __shfl_up_sync(kFullMask, bo[c], 1);
+                if (c > 0) {  // lane 0 takes the last entry of the register below
+                    const float cv = __shfl_sync(kFullMask, bv[c - 1], 31);
+                    const int co = __shfl_sync(kFullMask, bo[c - 1], 31);
+                    if (lane == 0) {
+                        upv = cv;
+                        upo = co;
+                    }
+                }
+                const int e = 32 * c + lane;
+                if (e > ins) {
+                    bv[c] = upv;
+                    bo[c] = upo;
+                } else if (e == ins) {
+                    bv[c] = dv;
+                    bo[c] = dpos;
+                }
+            }
+            if (nb < k) ++nb;
+            if (nb == k) {  // the k-th entry: register (k-1)/32 of lane (k-1)%32
+                float t = bv[0];
+#pragma unroll
+                for (int c = 1; c < KC; ++c)
+                    if ((k - 1) / 32 == c) t = bv[c];
+                tau = __shfl_sync(kFullMask, t, (k - 1) & 31);
+            }
+        }
+    };
+
+    // candidates for B: positions >= k that beat the current k-th best (strictly, once B is full).  ncu (k = 32,
+    // n = 4096): the kernel is issue-bound (91 % issue-active) and this loop was 27 % of its instructions at 44 per
+    // 32 points — now two groups per trip and nothing about set A inside.
     for (int base = 0; base < n; base += kKnnTile) {
         const int tn = min(kKnnTile, n - base);
         __syncthreads();  // previous tile consumed
@@ -83,60 +177,17 @@ knn_kernel(int n, int m, int k, const float* __restrict__ xyz1, const float* __r
         }
         __syncthreads();
         if (!valid) continue;
-        for (int p0 = 0; p0 < tn; p0 += 32) {
-            const int p = p0 + lane, pos = base + p;
-            float d = INFINITY;
-            if (p < tn) {
-                const float dx = __fsub_rn(s_x[p], qx), dy = __fsub_rn(s_y[p], qy), dz = __fsub_rn(s_z[p], qz);
-                d = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            }
-            if (pos < ka) {  // set A: positions 0..k-1 keep their own slot
-                wv[pos] = d;
-                wo[pos] = pos;
-            }
-            // candidates for B: positions >= k that beat the current k-th best (strictly, once B is full)
-            unsigned cand = __ballot_sync(kFullMask, p < tn && pos >= k && (nb < k || d < tau));
-            while (cand) {  // ascending position
-                const int src = __ffs(cand) - 1;
-                cand &= cand - 1;
-                const float dv = __shfl_sync(kFullMask, d, src);
-                const int dpos = base + p0 + src;
-                if (nb == k && !(dv < tau)) continue;  // tau may have dropped since the ballot (warp-uniform)
-                // insertion point: after every entry with value <= dv (an equal value at an earlier position stays ahead)
-                int ins = 0;
-#pragma unroll
-                for (int c = 0; c < KC; ++c) ins += __popc(__ballot_sync(kFullMask, 32 * c + lane < nb && bv[c] <= dv));
-                // shift the entries from `ins` on one slot up (the k-th falls off a full list), highest register first
-#pragma unroll
-                for (int c = KC - 1; c >= 0; --c) {
-                    float upv = __shfl_up_sync(kFullMask, bv[c], 1);
-                    int upo = __shfl_up_sync(kFullMask, bo[c], 1);
-                    if (c > 0) {  // lane 0 takes the last entry of the register below
-                        const float cv = __shfl_sync(kFullMask, bv[c - 1], 31);
-                        const int co = __shfl_sync(kFullMask, bo[c - 1], 31);
-                        if (lane == 0) {
-                            upv = cv;
-                            upo = co;
-                        }
-                    }
-                    const int e = 32 * c + lane;
-                    if (e > ins) {
-                        bv[c] = upv;
-                        bo[c] = upo;
-                    } else if (e == ins) {
-                        bv[c] = dv;
-                        bo[c] = dpos;
-                    }
-                }
-                if (nb < k) ++nb;
-                if (nb == k) {  // the k-th entry: register (k-1)/32 of lane (k-1)%32
-                    float t = bv[0];
-#pragma unroll
-                    for (int c = 1; c < KC; ++c)
-                        if ((k - 1) / 32 == c) t = bv[c];
-                    tau = __shfl_sync(kFullMask, t, (k - 1) & 31);
-                }
-            }
+        for (int p0 = max(0, k - base); p0 < tn; p0 += 64) {
+            const int pa = p0 + lane, pb = pa + 32;
+            float d0 = INFINITY, d1 = INFINITY;
+            if (pa < tn) d0 = knn_dist(s_x[pa], s_y[pa], s_z[pa], qx, qy, qz);
+            if (pb < tn) d1 = knn_dist(s_x[pb], s_y[pb], s_z[pb], qx, qy, qz);
+            const bool open = nb < k;
+            // a NaN distance beyond position k-1 is never "less than" anything: the selection sort cannot pick it
+            const unsigned c0 = __ballot_sync(kFullMask, pa < tn && (open ? d0 == d0 : d0 < tau));
+            const unsigned c1 = __ballot_sync(kFullMask, pb < tn && (open ? d1 == d1 : d1 < tau));
+            if (c0) insert_group(c0, d0, base + p0);
+            if (c1) insert_group(c1, d1, base + p0 + 32);  // insert_group re-checks every candidate against the current tau
         }
     }
     if (!valid) return;
@@ -151,23 +202,83 @@ knn_kernel(int n, int m, int k, const float* __restrict__ xyz1, const float* __r
 
     // ---- phase 2: replay the selection sort on W = A ∪ B -------------------------------------------
     const int nw = k + nb;  // slots [ka, k) are empty when n < k (then nb == 0)
+    float* __restrict__ oval = val + ((size_t)cloud * m + q) * k;
+    int* __restrict__ oidx = idx + ((size_t)cloud * m + q) * k;
+    // Fast path (ncu: the k-round replay below was 28 % of the kernel's instructions).  Sort W by value once.  If the
+    // k + 1 smallest values of W are finite and pairwise different, every round of the selection sort has a unique
+    // minimum — the next value in sorted order, wherever the swaps have moved it — so the sorted prefix IS the
+    // result.  Any tie (or inf / NaN distance) among them takes the exact replay.
+    if (ka == k) {
+        constexpr int E = 2 * KC;
+        unsigned long long key[E];
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const int e = 32 * j + lane;
+            key[j] = e < nw ? (((unsigned long long)__float_as_uint(wv[e]) << 32) | (unsigned)wo[e]) : ~0ull;
+        }
+        bitonic_sort_u64<E>(key, lane);
+        bool bad = false;
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const int e = 32 * j + lane;
+            const unsigned hi = (unsigned)(key[j] >> 32);
+            unsigned nxt = __shfl_down_sync(kFullMask, hi, 1);
+            if (j + 1 < E) {
+                const unsigned first_of_next = __shfl_sync(kFullMask, (unsigned)(key[(j + 1 < E) ? j + 1 : j] >> 32), 0);
+                if (lane == 31) nxt = first_of_next;
+            } else if (lane == 31) {
+                nxt = 0xffffffffu;
+            }
+            if (e < k && (hi >= 0x7f800000u || (e + 1 < nw && hi == nxt))) bad = true;
+            if (e < nw && (hi & 0x7fffffffu) > 0x7f800000u) bad = true;  // a NaN anywhere in W is selected by POSITION (v[s] starts as the minimum)
+        }
+        if (!__any_sync(kFullMask, bad)) {
+#pragma unroll
+            for (int j = 0; j < E; ++j) {
+                const int e = 32 * j + lane;
+                if (e < k) {
+                    oval[e] = __uint_as_float((unsigned)(key[j] >> 32));
+                    oidx[e] = (int)(unsigned)key[j];
+                }
+            }
+            return;
+        }
+    }
     for (int e = lane; e < nw; e += 32) wp[e] = (e < ka || e >= k) ? wo[e] : 0x7fffffff;
     if (ka < k)
         for (int e = ka + lane; e < k; e += 32) wv[e] = INFINITY;
     __syncwarp();
-    float* __restrict__ oval = val + ((size_t)cloud * m + q) * k;
-    int* __restrict__ oidx = idx + ((size_t)cloud * m + q) * k;
     for (int s = 0; s < ka; ++s) {
-        // first minimum over the elements at positions >= s, by (value, current position)
+        // first minimum over the elements at positions >= s, by (value, current position).  The reference starts
+        // from min = v[s] and replaces it by strict '<' (tf_grouping_g.cu:98-108): a NaN sitting AT position s is
+        // never replaced, a NaN anywhere else is never taken.
         float bestv = INFINITY;
         int bestp = 0x7fffffff, beste = -1;
         for (int e = lane; e < nw; e += 32) {
             const int pe = wp[e];
             const float ve = wv[e];
-            if (pe >= s && pe != 0x7fffffff && (beste < 0 || ve < bestv || (ve == bestv && pe < bestp))) {
+            const bool nan_at_s = (pe == s) && (ve != ve);
+            const bool usable = (ve == ve) || nan_at_s;
+            if (pe >= s && pe != 0x7fffffff && usable && (beste < 0 || nan_at_s || ve < bestv || (ve == bestv && pe < bestp))) {
                 bestv = ve;
                 bestp = pe;
                 beste = e;
+            }
+        }
+        {   // a NaN at position s wins outright
+            const unsigned nan_lanes = __ballot_sync(kFullMask, beste >= 0 && bestp == s && bestv != bestv);
+            if (nan_lanes) {
+                const int src = __ffs(nan_lanes) - 1;
+                bestv = __shfl_sync(kFullMask, bestv, src);
+                bestp = s;
+                beste = __shfl_sync(kFullMask, beste, src);
+                if (lane == 0) {
+                    wp[beste] = s;
+                    oval[s] = bestv;
+                    oidx[s] = wo[beste];
+                }
+                __syncwarp();
+                continue;
             }
         }
 #pragma unroll

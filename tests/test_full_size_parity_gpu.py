@@ -133,6 +133,25 @@ def test_knn_point_matches_reference_composite(dev, gen, b, n, m, k):
         knn_point(n + 1, x1, x2)
 
 
+@pytest.mark.parametrize("k", [4, 32, 48])
+def test_knn_point_with_nan_and_inf_points_matches_the_selection_sort(dev, k):
+    """Non-finite distances: the selection sort starts every round from min = v[s] and replaces it by strict '<'
+    (tf_grouping_g.cu:98-108), so a NaN at a position < k is output in its own round and a NaN anywhere else is
+    never taken; inf is an ordinary (largest) value.  Checked against the CPU restatement of the composite."""
+    b, n, m = 3, 300, 40
+    xyz = W.cloud_uniform(b, n, 123)
+    xyz[0, 2, 1] = np.nan      # inside the first k positions
+    xyz[0, 150, 0] = np.nan    # beyond them
+    xyz[1, 1, 2] = np.inf
+    xyz[1, 200, 0] = -np.inf
+    xyz[2, k + 1, 0] = np.nan  # among the first candidates of the top-k list
+    q = W.cloud_uniform(b, m, 124)
+    val, idx = knn_point(k, T(xyz, dev), T(q, dev))
+    wv, wi = O.oracle_knn_point(k, xyz, q)
+    np.testing.assert_array_equal(idx.cpu().numpy(), wi)
+    np.testing.assert_array_equal(val.cpu().numpy(), wv)
+
+
 @needs_refcuda
 def test_knn_point_full_size_matches_reference_composite(dev):
     """(32, 1024, 4096, k = 32) — cfg2's shape, in 4 slices of 8 clouds so that the reference's
