@@ -16,7 +16,7 @@
 //     elements that start at positions < k (set A) and the k smallest of the rest under
 //     (value, position) (set B) — every other element keeps its position and always loses to an
 //     unselected member of B.  So the kernel (1) scans the row once, keeping A in shared memory and
-//     a sorted top-k list B in registers (one entry per lane and register: an insertion is a few
+//     a top-k list B in registers (one entry per lane and register, unsorted: an insertion is a few
 //     ballots and shuffles), then (2) replays the k rounds on those <= 2k elements with their
 //     current positions.  The result equals the first k columns of selection_sort_gpu exactly.
 //
@@ -71,12 +71,12 @@ __device__ __forceinline__ float knn_dist(float x, float y, float z, float qx, f
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
-template <int KC>  // registers per lane that hold the sorted list B: k <= 32 * KC
+template <int KC>  // registers per lane that hold the list B: k <= 32 * KC
 __global__ void __launch_bounds__(kKnnThreads)
 knn_kernel(int n, int m, int k, const float* __restrict__ xyz1, const float* __restrict__ xyz2, float* __restrict__ val,
            int* __restrict__ idx) {
     __shared__ float s_x[kKnnTile], s_y[kKnnTile], s_z[kKnnTile];
-    // per warp: W[0..k) = set A (positions 0..k-1), W[k..2k) = set B (sorted ascending by (value, position))
+    // per warp: W[0..k) = set A (positions 0..k-1), W[k..2k) = set B (in no particular order)
     __shared__ float s_wv[kKnnWarps][2 * kKnnMaxK];
     __shared__ int s_wo[kKnnWarps][2 * kKnnMaxK];  // original index
     __shared__ int s_wp[kKnnWarps][2 * kKnnMaxK];  // current position (phase 2)
@@ -96,9 +96,9 @@ knn_kernel(int n, int m, int k, const float* __restrict__ xyz1, const float* __r
     float* __restrict__ wv = s_wv[warp];
     int* __restrict__ wo = s_wo[warp];
     int* __restrict__ wp = s_wp[warp];
-    // the sorted list B lives in REGISTERS while the row is scanned: entry e = register e/32 of lane e%32.  An insertion
-    // is a handful of ballots and shuffles (no shared memory, no __syncwarp): round 2's first version kept B in shared
-    // memory and spent most of its time in the read-sync-write shifts (1.02 ms at 32 x 1024 x 4096, k = 32).
+    // the list B lives in REGISTERS while the row is scanned: entry e = register e/32 of lane e%32 (no shared memory,
+    // no __syncwarp): round 2's first version kept a sorted B in shared memory and spent most of its time in the
+    // read-sync-write shifts (1.02 ms at 32 x 1024 x 4096, k = 32).
     float bv[KC];
     int bo[KC];
 #pragma unroll
@@ -118,47 +118,47 @@ knn_kernel(int n, int m, int k, const float* __restrict__ xyz1, const float* __r
             wo[pos] = pos;
         }
 
-    // one candidate group (32 consecutive positions, ascending): insert every lane of `cand` into the sorted list
+    // B's current maximum under (value, position) — the entry a better candidate evicts — and tau, its value
+    int ev_pos = -1;
+    auto find_max = [&]() {
+        unsigned loc = 0u;  // distances are non-negative and never NaN here: unsigned order of the bits == float order
+#pragma unroll
+        for (int c = 0; c < KC; ++c)
+            if (32 * c + lane < k) loc = max(loc, __float_as_uint(bv[c]));
+        const unsigned mx = __reduce_max_sync(kFullMask, loc);
+        int lp = -1;
+#pragma unroll
+        for (int c = 0; c < KC; ++c)
+            if (32 * c + lane < k && __float_as_uint(bv[c]) == mx) lp = max(lp, bo[c]);
+        ev_pos = __reduce_max_sync(kFullMask, lp);  // among equal values the latest position goes first
+        tau = __uint_as_float(mx);
+    };
+    // one candidate group (32 consecutive positions, ascending): offer every lane of `cand` to the list.  B is kept
+    // UNSORTED (phase 2 sorts W anyway): while it is open a candidate is appended, afterwards it replaces the current
+    // maximum, and two redux.sync find the next one — ~20 instructions whatever k is (the sorted list this replaces
+    // shifted KC registers per insertion: 35 instructions at k <= 32, ~70 at k = 128, 35 % of the kernel at k = 32).
     auto insert_group = [&](unsigned cand, float d, int pos0) {
         while (cand) {  // ascending position
             const int src = __ffs(cand) - 1;
             cand &= cand - 1;
             const float dv = __shfl_sync(kFullMask, d, src);
             const int dpos = pos0 + src;
-            if (nb == k && !(dv < tau)) continue;  // tau may have dropped since the ballot (warp-uniform)
-            // insertion point: after every entry with value <= dv (an equal value at an earlier position stays ahead)
-            int ins = 0;
+            if (nb < k) {
 #pragma unroll
-            for (int c = 0; c < KC; ++c) ins += __popc(__ballot_sync(kFullMask, 32 * c + lane < nb && bv[c] <= dv));
-            // shift the entries from `ins` on one slot up (the k-th falls off a full list), highest register first
-#pragma unroll
-            for (int c = KC - 1; c >= 0; --c) {
-                float upv = __shfl_up_sync(kFullMask, bv[c], 1);
-                int upo = __shfl_up_sync(kFullMask, bo[c], 1);
-                if (c > 0) {  // lane 0 takes the last entry of the register below
-                    const float cv = __shfl_sync(kFullMask, bv[c - 1], 31);
-                    const int co = __shfl_sync(kFullMask, bo[c - 1], 31);
-                    if (lane == 0) {
-                        upv = cv;
-                        upo = co;
+                for (int c = 0; c < KC; ++c)
+                    if (32 * c + lane == nb) {
+                        bv[c] = dv;
+                        bo[c] = dpos;
                     }
-                }
-                const int e = 32 * c + lane;
-                if (e > ins) {
-                    bv[c] = upv;
-                    bo[c] = upo;
-                } else if (e == ins) {
-                    bv[c] = dv;
-                    bo[c] = dpos;
-                }
-            }
-            if (nb < k) ++nb;
-            if (nb == k) {  // the k-th entry: register (k-1)/32 of lane (k-1)%32
-                float t = bv[0];
+                if (++nb == k) find_max();
+            } else if (dv < tau) {  // tau may have dropped since the ballot (warp-uniform)
 #pragma unroll
-                for (int c = 1; c < KC; ++c)
-                    if ((k - 1) / 32 == c) t = bv[c];
-                tau = __shfl_sync(kFullMask, t, (k - 1) & 31);
+                for (int c = 0; c < KC; ++c)
+                    if (bo[c] == ev_pos && 32 * c + lane < k) {
+                        bv[c] = dv;
+                        bo[c] = dpos;
+                    }
+                find_max();
             }
         }
     };
