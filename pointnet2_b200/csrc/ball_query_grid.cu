@@ -358,8 +358,13 @@ int pn2_query_ball_point_ws(int b, int n, int m, float radius, int nsample, cons
     // clouds that fit the shared-memory grid of sa_fused.cu (n <= 9700): one launch that builds the grid in shared
     // memory and serves the queries from it — faster than build + query + brute-force back to back from n = 2048 up
     // (profiles/r2_report.json: cfg2[U] 0.035 against 0.050 ms, cfg4 SA1024 0.051 against 0.093); no workspace needed
-    if (g_bq_mode == 0 && n >= kGridMinN && pn2_ball_group_fits(n) && thr >= 0.0f)
-        return pn2_ball_group(b, n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt, nullptr, 0, stream);
+    if (g_bq_mode == 0 && n >= kGridMinN && pn2_ball_group_fits(n) && thr >= 0.0f) {
+        // ... when there are queries enough to pay for the grids (every CTA builds its own): below ~4096 queries the
+        // packed brute-force kernel is ahead (r2_report.json, cfg4 SA1024 at B = 2: 2048 queries x 8192 points,
+        // 0.0246 ms against 0.0287)
+        if ((long long)b * m >= 4096) return pn2_ball_group(b, n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt, nullptr, 0, stream);
+        return pn2_query_ball_point(b, n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt, stream);
+    }
     if (g_bq_mode == 1 || !workspace || need == 0 || workspace_bytes < need || thr < 0.0f || b > 65535)
         return pn2_query_ball_point(b, n, m, radius, nsample, xyz1, xyz2, idx, pts_cnt, stream);
     int rc = pn2_ball_grid_build(b, n, radius, nsample, xyz1, workspace, workspace_bytes, stream);
