@@ -13,15 +13,12 @@ from ._tensor import on_device, ptr, require_cuda, same_device, stream_ptr
 
 
 def query_ball_point(radius: float, nsample: int, xyz1: torch.Tensor, xyz2: torch.Tensor):
-    """
-    Input:
-        radius: float32, ball search radius
-        nsample: int32, number of points selected in each ball region
-        xyz1: (batch_size, ndataset, 3) float32 array, input points
-        xyz2: (batch_size, npoint, 3) float32 array, query points
-    Output:
-        idx: (batch_size, npoint, nsample) int32 array, indices to input points
-        pts_cnt: (batch_size, npoint) int32 array, number of unique points in each local region
+    """For every query centre, the first ``nsample`` data points (ascending index) closer than ``radius``.
+
+    Arguments: ``radius`` of the ball; ``nsample`` row length; ``xyz1`` float32 (B, N, 3), the cloud that is
+    searched; ``xyz2`` float32 (B, M, 3), the ball centres.
+    Returns ``idx`` int32 (B, M, nsample) — positions in ``xyz1``, short rows padded with their first hit — and
+    ``pts_cnt`` int32 (B, M), how many distinct hits each row holds.
     Reference: tf_grouping.py:8-20 -> QueryBallPointGpuOp (tf_grouping.cpp:67-106) ->
     query_ball_point_gpu (tf_grouping_g.cu:3-36).  Rows with no point in the ball (undefined in the
     reference) come back as zeros with pts_cnt 0.
@@ -61,13 +58,12 @@ def query_ball_point(radius: float, nsample: int, xyz1: torch.Tensor, xyz2: torc
 
 
 def select_top_k(k: int, dist: torch.Tensor):
-    """
-    Input:
-        k: int32, number of k SMALLEST elements selected
-        dist: (b,m,n) float32 array, distance matrix, m query points, n dataset points
-    Output:
-        idx: (b,m,n) int32 array, first k in n are indices to the top k
-        dist_out: (b,m,n) float32 array, first k in n are the top k
+    """k rounds of selection sort along the last axis of a distance matrix.
+
+    Arguments: ``k`` — how many of the smallest entries to bring to the front; ``dist`` float32 (B, M, N), one row
+    of N distances per query.
+    Returns ``(idx, dist_out)``, both (B, M, N): columns [0, k) hold the k smallest distances in ascending order and
+    their original column numbers, the remaining columns the reference's swapped-around tail.
     Reference: tf_grouping.py:22-31 -> SelectionSortGpuOp (tf_grouping.cpp:110-139) ->
     selection_sort_gpu (tf_grouping_g.cu:83-123).
     """
@@ -119,12 +115,10 @@ class _GroupPoint(torch.autograd.Function):
 
 
 def group_point(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
-    """
-    Input:
-        points: (batch_size, ndataset, channel) float32 array, points to sample from
-        idx: (batch_size, npoint, nsample) int32 array, indices to points
-    Output:
-        out: (batch_size, npoint, nsample, channel) float32 array, values sampled from points
+    """Row gather: ``out[b, j, s, :] = points[b, idx[b, j, s], :]``.
+
+    Arguments: ``points`` float32 (B, N, C), the rows to pick from; ``idx`` int32 (B, M, S), row numbers into
+    ``points``.  Returns float32 (B, M, S, C).  Differentiable in ``points``.
     Reference: tf_grouping.py:33-41 -> group_point_gpu (tf_grouping_g.cu:40-57); gradient
     tf_grouping.py:42-46 -> group_point_grad_gpu (:61-78).
     """
@@ -141,14 +135,11 @@ def group_point(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
 
 
 def knn_point(k: int, xyz1: torch.Tensor, xyz2: torch.Tensor):
-    """
-    Input:
-        k: int32, number of k in k-nn search
-        xyz1: (batch_size, ndataset, c) float32 array, input points
-        xyz2: (batch_size, npoint, c) float32 array, query points
-    Output:
-        val: (batch_size, npoint, k) float32 array, L2 distances
-        idx: (batch_size, npoint, k) int32 array, indices to input points
+    """The k nearest data points of every query point, by squared Euclidean distance.
+
+    Arguments: ``k`` neighbours per query; ``xyz1`` float32 (B, N, c), the cloud that is searched; ``xyz2`` float32
+    (B, M, c), the queries.  Returns ``val`` float32 (B, M, k), the squared distances in ascending order, and
+    ``idx`` int32 (B, M, k), the matching positions in ``xyz1``.
     Reference: tf_grouping.py:48-73.  The reference builds the (b,m,n) matrix of squared distances
     sum((xyz1 - xyz2)**2, -1) and runs select_top_k on it; for 3-D points and k <= 128 this runs one
     tiled top-k kernel instead (pn2_knn_point: no matrix), whose val / idx equal the first k columns

@@ -15,13 +15,11 @@ from ._tensor import on_device, ptr, require_cuda, same_device, stream_ptr
 
 
 def three_nn(xyz1: torch.Tensor, xyz2: torch.Tensor):
-    """
-    Input:
-        xyz1: (b,n,3) float32 array, unknown points
-        xyz2: (b,m,3) float32 array, known points
-    Output:
-        dist: (b,n,3) float32 array, distances to known points   [SQUARED, ascending]
-        idx: (b,n,3) int32 array, indices to known points
+    """The three nearest known points of every unknown point.
+
+    ``xyz1`` float32 (B, n, 3): the points that need values; ``xyz2`` float32 (B, m, 3): the points that carry them.
+    Returns ``dist`` float32 (B, n, 3) — SQUARED distances, ascending — and ``idx`` int32 (B, n, 3), positions in
+    ``xyz2``.
     Reference: tf_interpolate.py:8-17 -> ThreeNNOp (tf_interpolate.cpp:157-187) -> threenn_cpu (:60-103).
     """
     xyz1 = require_cuda(xyz1, "xyz1", torch.float32)
@@ -94,13 +92,10 @@ class _ThreeInterpolate(torch.autograd.Function):
 
 
 def three_interpolate(points: torch.Tensor, idx: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
-    """
-    Input:
-        points: (b,m,c) float32 array, known points
-        idx: (b,n,3) int32 array, indices to known points
-        weight: (b,n,3) float32 array, weights on known points
-    Output:
-        out: (b,n,c) float32 array, interpolated point values
+    """Weighted sum of three feature rows: ``out[b, i, :] = sum_t weight[b, i, t] * points[b, idx[b, i, t], :]``.
+
+    ``points`` float32 (B, m, c): features of the known points; ``idx`` int32 and ``weight`` float32, both (B, n, 3),
+    as produced from three_nn.  Returns float32 (B, n, c).  Differentiable in ``points``.
     Reference: tf_interpolate.py:19-28 -> threeinterpolate_cpu (tf_interpolate.cpp:107-127);
     gradient :29-34 -> threeinterpolate_grad_cpu (:131-153).
     """

@@ -6,7 +6,7 @@ reference registers a gradient: gather_point w.r.t. ``inp`` (tf_sampling.py:43-4
 farthest_point_sample has none (ops.NoGradient, :57).
 
 ``prob_sample`` (tf_sampling.py:13-21) is outside the set-abstraction path (only the
-module's __main__ demo calls it) and is not provided.
+module's __main__ demo calls it); it is provided for completeness and kept out of every measurement.
 """
 from __future__ import annotations
 
@@ -22,12 +22,10 @@ def _check_xyz(t: torch.Tensor, name: str, op: str) -> None:
 
 
 def prob_sample(inp: torch.Tensor, inpr: torch.Tensor) -> torch.Tensor:
-    """
-    input:
-        batch_size * ncategory float32   (unnormalised probabilities)
-        batch_size * npoints   float32   (uniform draws in [0,1])
-    returns:
-        batch_size * npoints   int32     (sampled category per draw)
+    """Inverse-CDF sampling: one category per uniform draw.
+
+    ``inp`` float32 (B, K): non-negative, unnormalised weights of K categories; ``inpr`` float32 (B, M): draws in
+    [0, 1].  Returns int32 (B, M), the category each draw falls into.
     Reference: tf_sampling.py:13-21 -> ProbSampleGpuOp (tf_sampling.cpp:66-92) ->
     probsampleLauncher (tf_sampling_g.cu:198-201): cumulative sum, then the first index whose
     cumulative sum reaches inpr * total.  No gradient (ops.NoGradient, tf_sampling.py:22).
@@ -53,12 +51,9 @@ def prob_sample(inp: torch.Tensor, inpr: torch.Tensor) -> torch.Tensor:
 
 
 def farthest_point_sample(npoint: int, inp: torch.Tensor) -> torch.Tensor:
-    """
-    input:
-        int32
-        batch_size * ndataset * 3   float32
-    returns:
-        batch_size * npoint         int32
+    """Farthest point sampling: ``npoint`` picks per cloud, each the point farthest from everything picked so far.
+
+    ``inp`` float32 (B, N, 3).  Returns int32 (B, npoint), positions in ``inp``; the first pick is point 0.
     Reference: tf_sampling.py:48-56 -> FarthestPointSampleGpuOp (tf_sampling.cpp:95-123) ->
     farthestpointsamplingKernel (tf_sampling_g.cu:105-170).  Deterministic, starts at index 0.
     """
@@ -139,12 +134,9 @@ class _GatherPoint(torch.autograd.Function):
 
 
 def gather_point(inp: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
-    """
-    input:
-        batch_size * ndataset * 3   float32
-        batch_size * npoints        int32
-    returns:
-        batch_size * npoints * 3    float32
+    """Row gather of coordinates: ``out[b, j, :] = inp[b, idx[b, j], :]``.
+
+    ``inp`` float32 (B, N, 3); ``idx`` int32 (B, M).  Returns float32 (B, M, 3).  Differentiable in ``inp``.
     Reference: tf_sampling.py:29-37 -> gatherpointKernel (tf_sampling_g.cu:172-181);
     gradient tf_sampling.py:43-47 -> scatteraddpointKernel (:183-192).
     """
