@@ -122,6 +122,177 @@ __device__ __forceinline__ void fps_step(const float (&px)[P], const float (&py)
 // as soon as every CTA of this grid has got here (SASS: PREEXIT).  A no-op for ordinary launches.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// ---- packed FP32x2 arithmetic (SASS FADD2 / FMUL2 / FFMA2): two points per instruction, each half
+// rounded to nearest on its own, so bit-identical to d2_fma_pattern on either half --------------------
+__device__ __forceinline__ unsigned long long f2_pack(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// ---- a thread's points in SCAN order --------------------------------------------------------------
+// Register slot e of thread t holds point k = t + j(e)*T, with j(e) running through the thread's points in the
+// reference's tie-break order (slot k mod 512 ascending, then k ascending; see fps_step).  The tie-break word of
+// that point splits into the thread's own part tb_encode(t) and a compile-time constant tbj(e) with disjoint bits.
+template <int P, int T>
+struct ScanOrder {
+    static constexpr int D = (T >= 512) ? 1 : 512 / T;
+    static constexpr int DD = (D < P) ? D : P;
+    static constexpr int Q = P / DD;                 // points per slot residue
+    static constexpr int GS = (Q >= 4) ? 4 : Q;      // scan-order neighbours per search group
+    __host__ __device__ static constexpr int j_of(int e) { return (e % Q) * DD + e / Q; }
+    __host__ __device__ static constexpr unsigned tbj(int e) {
+        return ((((unsigned)(j_of(e) * T)) & 511u) << 23) | (((unsigned)(j_of(e) * T)) >> 9);
+    }
+    // tbj(GS*a + u) == tbj(GS*a) | tbj(u) for every group a and in-group position u (checked at compile time)
+    __host__ __device__ static constexpr bool separable() {
+        for (int a = 0; a < P / GS; ++a)
+            for (int u = 0; u < GS; ++u)
+                if (tbj(GS * a + u) != (tbj(GS * a) | tbj(u)) || (u && (tbj(GS * a) & tbj(u)))) return false;
+        return true;
+    }
+};
+
+// ---- the M-step chain of fps_cta_kernel, restructured around what binds it ---------------------------
+// The plain chain (fps_step) spends 10 instructions per point and step: 6 on the FMA pipe (3 FADD, FMUL, 2 FFMA)
+// and 4 on the half-rate ALU pipe (FMNMX, FSETP, FSEL, SEL: the running (value, position) maximum).  With two
+// warps per scheduler the ALU pipe and the issue slot are both ~full during the update (SASS: 213 instructions per
+// warp and step, 83 of them ALU).  This form keeps the arithmetic bit-identical and cuts both:
+//   * the 6 distance operations run as packed FP32x2 (two scan-order neighbours per instruction);
+//   * the update tracks VALUES only — groups of GS scan-order neighbours are reduced with 3-input maxima
+//     (FMNMX3) — and the position of the first maximum is recovered afterwards: first group whose maximum equals
+//     the thread's maximum, then first equal leaf inside it.  "First in scan order among equals" is exactly
+//     what the strict '>' scan of fps_step selects, so the key is the same word for word;
+//   * a thread without points (t >= n) contributes the all-zero key through its precomputed tie-break part
+//     instead of a test per step; the floor 0 of the maximum replaces the `best >= 0` guard.
+// SASS (P = 16, T = 256): 143 instructions per warp and step, 53 on the ALU pipe.
+template <int P, int T>
+__device__ __forceinline__ void fps_chain_packed(int n, int m, const float* __restrict__ src, int* __restrict__ out,
+                                                 float* __restrict__ oxyz, uint2 (&s_keys)[2][32]) {
+    using SO = ScanOrder<P, T>;
+    constexpr int GS = SO::GS, G = P / GS, H = P / 2;
+    static_assert(P % 2 == 0 && P % GS == 0 && SO::Q % GS == 0, "packed pairs and whole search groups");
+    static_assert(SO::separable(), "group and in-group tie-break constants must OR together");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    unsigned long long X[H], Y[H], Z[H];
+    float td[P];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        float c[2][3];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int e = 2 * h + u;
+            const int k = tid + SO::j_of(e) * T;
+            c[u][0] = c[u][1] = c[u][2] = 0.0f;
+            td[e] = -1.0f;  // padding: below the floor of the maximum, never equal to it
+            if (k < n) {
+                c[u][0] = src[3 * k + 0];
+                c[u][1] = src[3 * k + 1];
+                c[u][2] = src[3 * k + 2];
+                td[e] = 1e38f;
+            }
+        }
+        X[h] = f2_pack(c[0][0], c[1][0]);
+        Y[h] = f2_pack(c[0][1], c[1][1]);
+        Z[h] = f2_pack(c[0][2], c[1][2]);
+    }
+    // tie-break part of this thread; all ones for a thread without points, so that its key is (0, 0)
+    const unsigned tp = (tid < n) ? tb_encode((unsigned)tid) : 0xffffffffu;
+
+    float x1 = src[0], y1 = src[1], z1 = src[2];
+    if (tid == 0) {
+        if (oxyz) {
+            oxyz[0] = x1;
+            oxyz[1] = y1;
+            oxyz[2] = z1;
+        }
+        out[0] = 0;
+    }
+    // key slots of warps that do not exist stay (0, 0): the cross-warp reduction reads all 32 without a test
+    if (tid < 64) (&s_keys[0][0])[tid] = make_uint2(0u, 0u);
+    __syncthreads();
+
+    for (int it = 1; it < m; ++it) {
+        const unsigned long long X1 = f2_pack(x1, x1), Y1 = f2_pack(y1, y1), Z1 = f2_pack(z1, z1);
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            const unsigned long long dx = f2_sub(X[h], X1), dy = f2_sub(Y[h], Y1), dz = f2_sub(Z[h], Z1);
+            const unsigned long long d = f2_fma(dz, dz, f2_fma(dx, dx, f2_mul(dy, dy)));  // d2_fma_pattern on both halves
+            float d0, d1;
+            f2_unpack(d, d0, d1);
+            td[2 * h] = fminf(d0, td[2 * h]);
+            td[2 * h + 1] = fminf(d1, td[2 * h + 1]);
+        }
+        // running minima are never NaN (fminf drops a NaN distance) and never -0, so == and the unsigned order of
+        // the float bits are exact
+        float g[G];
+#pragma unroll
+        for (int a = 0; a < G; ++a) {
+            float v = td[GS * a];
+#pragma unroll
+            for (int u = 1; u < GS; ++u) v = fmaxf(v, td[GS * a + u]);
+            g[a] = v;
+        }
+        float mx = 0.0f;
+#pragma unroll
+        for (int a = 0; a < G; ++a) mx = fmaxf(mx, g[a]);
+        // first group in scan order that attains mx (a thread with points always has one), then the first leaf in it
+        float s[GS];
+#pragma unroll
+        for (int u = 0; u < GS; ++u) s[u] = td[GS * (G - 1) + u];
+        unsigned cg = SO::tbj(GS * (G - 1));
+#pragma unroll
+        for (int a = G - 2; a >= 0; --a) {
+            const bool q = (g[a] == mx);
+#pragma unroll
+            for (int u = 0; u + 1 < GS; ++u) s[u] = q ? td[GS * a + u] : s[u];
+            cg = q ? SO::tbj(GS * a) : cg;
+        }
+        unsigned cu = SO::tbj(GS - 1);
+#pragma unroll
+        for (int u = GS - 2; u >= 0; --u) cu = (s[u] == mx) ? SO::tbj(u) : cu;
+        unsigned hi = __float_as_uint(mx), lo = ~(tp | cg | cu);
+        warp_max_pair(hi, lo);
+        const int buf = it & 1;
+        s_keys[buf][warp] = make_uint2(lo, hi);  // every lane holds the warp's key: one same-address store, no test
+        __syncthreads();
+        const uint2 e = s_keys[buf][lane];
+        unsigned gh = e.y, gl = e.x;
+        warp_max_pair(gh, gl);
+        const int old = (int)tb_decode(~gl);
+        x1 = src[3 * old + 0];
+        y1 = src[3 * old + 1];
+        z1 = src[3 * old + 2];
+        if (tid == 0) {
+            if (oxyz) {
+                oxyz[3 * it + 0] = x1;
+                oxyz[3 * it + 1] = y1;
+                oxyz[3 * it + 2] = z1;
+            }
+            out[it] = old;
+        }
+    }
+}
+
 // =================================================================================================
 // One CTA per cloud.  Thread t owns points k = t + j*T (j < P).  When T is a multiple of 512 all of
 // a thread's points share the reference slot k mod 512 and the in-thread strict '>' scan in
@@ -133,7 +304,8 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // programmatic launch completion, so a dependent grid that polls idx_out for non-negative entries
 // (sa_fused.cu) can consume the picks while this chain is still running — no fence in the loop.
 // =================================================================================================
-template <int P, int T>
+// V = 0: the plain chain (fps_step); V = 1: fps_chain_packed.  Same prologue, same outputs bit for bit.
+template <int P, int T, int V = 0>
 __global__ void __launch_bounds__(T, 1)
 fps_cta_kernel(int n, int m, const float* __restrict__ xyz, int* __restrict__ idx_out,
                float* __restrict__ new_xyz, int sentinel) {
@@ -191,6 +363,9 @@ fps_cta_kernel(int n, int m, const float* __restrict__ xyz, int* __restrict__ id
     if (sentinel) pdl_launch_dependents();
     const float* __restrict__ src = s_xyz;
 
+    if constexpr (V == 1) {
+        fps_chain_packed<P, T>(n, m, src, out, oxyz, s_keys);
+    } else {
     float px[P], py[P], pz[P], td[P];
 #pragma unroll
     for (int j = 0; j < P; ++j) {
@@ -245,6 +420,7 @@ fps_cta_kernel(int n, int m, const float* __restrict__ xyz, int* __restrict__ id
             out[it] = old;
         }
     }
+    }  // V == 0
 }
 
 // =================================================================================================
@@ -667,6 +843,11 @@ fps_global_kernel(int b, int n, int m, const float* __restrict__ xyz, float* __r
 // several host threads always see a consistent (threads, points/thread, cluster) triple.
 static std::atomic<unsigned long long> g_fps_cfg{0ull};  // threads << 40 | ppt << 20 | (cluster + 64); 0 = built-in plan
 static std::once_flag g_fps_env_once;
+// Which chain the single-CTA kernel runs where both exist (points per thread >= 8): 1 = fps_chain_packed,
+// 0 = the plain fps_step chain.  PN2_FPS_PACKED=0/1 overrides the built-in choice; an override plan with
+// cluster = -1 / -2 (pn2_set_fps_config, PN2_FPS_CFG) forces the plain / packed chain for that plan.
+constexpr int kFpsPackedDefault = 0;
+static std::atomic<int> g_fps_packed{kFpsPackedDefault};
 
 static unsigned long long pack_cfg(int threads, int ppt, int cluster) {
     if (threads <= 0) return 0ull;
@@ -696,10 +877,10 @@ static cudaError_t ensure_attrs(AttrOnce& once, K kern, size_t dyn, bool nonport
     return cudaSuccess;
 }
 
-template <int P, int T>
+template <int P, int T, int V>
 static int launch_cta(int b, int n, int m, const float* inp, int* out, float* new_xyz, int sentinel, cudaStream_t st) {
     static AttrOnce once;
-    auto kern = fps_cta_kernel<P, T>;
+    auto kern = fps_cta_kernel<P, T, V>;
     // the opt-in is set for the largest cloud this instantiation can serve, so one call per device is enough
     size_t dyn = (size_t)n * 3 * sizeof(float);
     if (dyn > 200 * 1024) return (int)cudaErrorInvalidValue;
@@ -836,6 +1017,7 @@ static int cluster_big_capacity(int C) {
 struct FpsPlan {
     int threads, ppt, cluster;  // cluster == 0: global-scratch fallback; 1: single CTA; >= 2: thread-block cluster
     int pr;                     // cluster kernels: points per thread with register-resident coordinates (== ppt: all)
+    int packed = 0;             // single CTA: 1 = fps_chain_packed where it is instantiated (ppt >= 8)
 };
 
 static int pow2_floor(int v) {
@@ -851,7 +1033,10 @@ static FpsPlan plan_fps(int b, int n) {
         const char* e = getenv("PN2_FPS_CFG");
         int t = 0, pp = 0, c = 0;
         if (e && sscanf(e, "%d,%d,%d", &t, &pp, &c) == 3) g_fps_cfg.store(pack_cfg(t, pp, c), std::memory_order_relaxed);
+        const char* pk = getenv("PN2_FPS_PACKED");
+        if (pk && (pk[0] == '0' || pk[0] == '1') && pk[1] == 0) g_fps_packed.store(pk[0] - '0', std::memory_order_relaxed);
     });
+    const int packed = g_fps_packed.load(std::memory_order_relaxed);
     const unsigned long long ov = g_fps_cfg.load(std::memory_order_relaxed);
     if (ov) {
         FpsPlan p;
@@ -859,19 +1044,24 @@ static FpsPlan plan_fps(int b, int n) {
         p.ppt = (int)((ov >> 20) & 0xfffff);
         p.cluster = (int)(ov & 0xfffff) - 64;
         p.pr = (p.ppt >= 32 && p.threads >= 512) ? 16 : p.ppt;  // ppt > 32: the register + shared-memory kernel
+        p.packed = packed;
+        if (p.cluster == -1 || p.cluster == -2) {  // single CTA with the chain named explicitly
+            p.packed = (p.cluster == -2) ? 1 : 0;
+            p.cluster = 1;
+        }
         return p;
     }
     // single CTA, register-resident (cluster = 1).  Measured on B200 (profiles/r1_fps_sweep*.json):
     // few warps with many points each win at every size (4-8 warps; e.g. N=4096: 8 warps x 16 points
     // 0.313 us/step, 16 x 8: 0.410, 32 x 4: 0.501) — the step is bound by the ALU pipe, the per-warp
     // replicated reduction code and barrier latency, all of which shrink with fewer warps.
-    if (n <= 128) return {128, 1, 1, 1};
-    if (n <= 256) return {128, 2, 1, 2};
-    if (n <= 512) return {256, 2, 1, 2};
-    if (n <= 1024) return {128, 8, 1, 8};
-    if (n <= 2048) return {128, 16, 1, 16};
-    if (n <= 4096) return {256, 16, 1, 16};
-    if (n <= 8192) return {256, 32, 1, 32};
+    if (n <= 128) return {128, 1, 1, 1, packed};
+    if (n <= 256) return {128, 2, 1, 2, packed};
+    if (n <= 512) return {256, 2, 1, 2, packed};
+    if (n <= 1024) return {128, 8, 1, 8, packed};
+    if (n <= 2048) return {128, 16, 1, 16, packed};
+    if (n <= 4096) return {256, 16, 1, 16, packed};
+    if (n <= 8192) return {256, 32, 1, 32, packed};
     // cluster: as many CTAs per cloud as keeps all clouds co-resident on the 148 SMs; inside each CTA
     // again few fat warps
     int cmax = pow2_floor(148 / (b > 148 ? 148 : b));
@@ -938,7 +1128,9 @@ static FpsPlan plan_fps(int b, int n) {
 }
 
 #define PN2_TRY_CTA(PP, TT) \
-    if (plan.ppt == PP && plan.threads == TT) return launch_cta<PP, TT>(b, n, m, inp, out, new_xyz, sentinel, st);
+    if (plan.ppt == PP && plan.threads == TT) return launch_cta<PP, TT, 0>(b, n, m, inp, out, new_xyz, sentinel, st);
+#define PN2_TRY_CTA_PACKED(PP, TT) \
+    if (plan.packed && plan.ppt == PP && plan.threads == TT) return launch_cta<PP, TT, 1>(b, n, m, inp, out, new_xyz, sentinel, st);
 #define PN2_TRY_CLU(PP, TT, PRR) \
     if (plan.ppt == PP && plan.threads == TT && plan.pr == PRR) \
         return launch_cluster<PP, TT, PRR>(plan.cluster, b, n, m, inp, out, new_xyz, st);
@@ -961,6 +1153,15 @@ int fps_dispatch(int b, int n, int m, const float* inp, float* temp, int* out, f
         if (cap < n) return (int)cudaErrorInvalidValue;
     }
     if (plan.cluster == 1) {
+        PN2_TRY_CTA_PACKED(8, 128)
+        PN2_TRY_CTA_PACKED(16, 128)
+        PN2_TRY_CTA_PACKED(32, 128)
+        PN2_TRY_CTA_PACKED(8, 256)
+        PN2_TRY_CTA_PACKED(16, 256)
+        PN2_TRY_CTA_PACKED(32, 256)
+        PN2_TRY_CTA_PACKED(8, 512)
+        PN2_TRY_CTA_PACKED(16, 512)
+        PN2_TRY_CTA_PACKED(8, 1024)
         PN2_TRY_CTA(1, 128)
         PN2_TRY_CTA(2, 128)
         PN2_TRY_CTA(4, 128)

@@ -48,6 +48,10 @@ FPS_VARIANTS = [(512, 2, 2), (512, 1, 4), (512, 4, 2), (512, 8, 4), (1024, 2, 2)
                 (512, 1, 16), (512, 16, 2), (512, 32, 2), (1024, 4, 1), (512, 8, 1), (512, 16, 1),
                 (256, 2, 2), (256, 8, 4), (256, 32, 2), (128, 4, 4), (128, 16, 8), (128, 32, 16), (256, 16, 16),
                 (128, 2, 1), (128, 8, 1), (128, 32, 1), (256, 2, 1), (256, 4, 1), (256, 16, 1), (256, 32, 1),
+                # single CTA with the chain named explicitly: cluster -1 = plain fps_step chain, -2 = packed FP32x2 chain with
+                # value-only tracking (every instantiation of it)
+                (128, 8, -2), (128, 16, -2), (128, 32, -2), (256, 8, -2), (256, 16, -2), (256, 32, -2), (512, 8, -2),
+                (512, 16, -2), (1024, 8, -2), (128, 8, -1), (256, 16, -1), (256, 32, -1), (512, 16, -1),
                 # register + shared-memory cluster kernel (points per thread > 32), any cluster size incl. non-powers of two
                 (512, 44, 2), (512, 44, 3), (512, 44, 12), (512, 44, 16), (512, 48, 5), (512, 48, 11), (512, 48, 13), (512, 52, 10), (512, 52, 7)]
 
@@ -59,7 +63,7 @@ def test_fps_every_kernel_variant_matches_oracle(dev, cfg, gen):
     (cluster 1), the DSMEM cluster exchange carrying key + coordinates (cluster >= 2) and the variant
     that streams half of the coordinates from shared memory (512 x 32) — on a cloud that fits it."""
     threads, ppt, cluster = cfg
-    cap = threads * ppt * cluster
+    cap = threads * ppt * max(cluster, 1)
     n = min(cap, 6000) - 3
     xyz = W.DISTRIBUTIONS[gen](2, n, 32)
     lib = _lib.load()
@@ -89,6 +93,53 @@ def test_fps_cluster_variants_at_full_capacity(dev, cfg, n):
         finally:
             lib.pn2_set_fps_config(0, 0, 0)
         want = O.oracle_fps(m, xyz)
+        np.testing.assert_array_equal(N(fi), want)
+        np.testing.assert_array_equal(N(fx), O.oracle_gather_point(xyz, want))
+
+
+@pytest.mark.skipif(not O.have_refcuda(), reason="oracle/_ref CUDA libraries did not travel")
+@pytest.mark.parametrize("chain", [-1, -2])
+@pytest.mark.parametrize("gen,b,n,m,threads,ppt", [("U", 8, 4096, 1024, 256, 16), ("D", 8, 4096, 1024, 256, 16),
+                                                   ("D", 4, 8192, 1024, 256, 32), ("S", 8, 2048, 700, 128, 16),
+                                                   ("D", 8, 1024, 1024, 128, 8), ("D", 2, 8192, 512, 1024, 8)])
+def test_fps_both_chains_match_the_reference_kernel(dev, chain, gen, b, n, m, threads, ppt):
+    """The plain and the packed chain of the single-CTA kernel against the rebuilt reference kernel at the planner's
+    own shapes, every per-thread slot occupied, on clouds with many exact ties (D)."""
+    xyz = T(W.DISTRIBUTIONS[gen](b, n, 35), dev)
+    ref = O.refcuda_fps(m, xyz)
+    lib = _lib.load()
+    lib.pn2_set_fps_config(threads, ppt, chain)
+    try:
+        fi, fx = farthest_point_sample_and_gather(m, xyz)
+    finally:
+        lib.pn2_set_fps_config(0, 0, 0)
+    assert torch.equal(fi, ref)
+    assert torch.equal(fx, O.refcuda_gather_point(xyz, ref))
+
+
+@pytest.mark.parametrize("chain", [-1, -2])
+def test_fps_chains_with_ties_everywhere_and_odd_sizes(dev, chain):
+    """All points coincide (every running minimum is 0 after the first pick: the tie-break alone decides every step),
+    a cloud with NaN / inf coordinates, and sizes that leave padding slots in the middle of the scan order."""
+    lib = _lib.load()
+    rs = np.random.RandomState(36)
+    clouds = [np.zeros((2, 2500, 3), np.float32) + np.float32(0.25),
+              np.repeat(rs.rand(2, 7, 3).astype(np.float32), 500, axis=1)[:, :3333],
+              W.cloud_uniform(2, 4093, 37), W.cloud_uniform(3, 1281, 38)]
+    bad = W.cloud_uniform(2, 3000, 39)
+    bad[0, 5] = np.nan
+    bad[1, 77, 1] = np.inf
+    bad[1, 900, 2] = -np.inf
+    clouds.append(bad)
+    for xyz in clouds:
+        n = xyz.shape[1]
+        threads, ppt = (256, 16) if n > 2048 else (128, 16)
+        lib.pn2_set_fps_config(threads, ppt, chain)
+        try:
+            fi, fx = farthest_point_sample_and_gather(200, T(xyz, dev))
+        finally:
+            lib.pn2_set_fps_config(0, 0, 0)
+        want = O.oracle_fps(200, xyz)
         np.testing.assert_array_equal(N(fi), want)
         np.testing.assert_array_equal(N(fx), O.oracle_gather_point(xyz, want))
 
