@@ -148,6 +148,14 @@ __device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsig
     return r;
 }
 
+// Lexicographic (max hi, then min lo) over the warp; every lane gets the result.
+__device__ __forceinline__ void warp_max_min_pair(unsigned& hi, unsigned& lo) {
+    const unsigned mh = __reduce_max_sync(kFullMask, hi);
+    const unsigned ml = __reduce_min_sync(kFullMask, hi == mh ? lo : 0xffffffffu);
+    hi = mh;
+    lo = ml;
+}
+
 // ---- a thread's points in SCAN order --------------------------------------------------------------
 // Register slot e of thread t holds point k = t + j(e)*T, with j(e) running through the thread's points in the
 // reference's tie-break order (slot k mod 512 ascending, then k ascending; see fps_step).  The tie-break word of
@@ -215,7 +223,9 @@ __device__ __forceinline__ void fps_chain_packed(int n, int m, const float* __re
         Y[h] = f2_pack(c[0][1], c[1][1]);
         Z[h] = f2_pack(c[0][2], c[1][2]);
     }
-    // tie-break part of this thread; all ones for a thread without points, so that its key is (0, 0)
+    // Keys of this chain are (value bits, tie-break word) reduced as max-then-MIN, i.e. the plain chain's
+    // (value, ~word) max-then-max without the two complements per step.  Tie-break part of this thread: all ones
+    // for a thread without points, so that its key (0, ~0) loses to every real point.
     const unsigned tp = (tid < n) ? tb_encode((unsigned)tid) : 0xffffffffu;
 
     float x1 = src[0], y1 = src[1], z1 = src[2];
@@ -227,10 +237,11 @@ __device__ __forceinline__ void fps_chain_packed(int n, int m, const float* __re
         }
         out[0] = 0;
     }
-    // key slots of warps that do not exist stay (0, 0): the cross-warp reduction reads all 32 without a test
-    if (tid < 64) (&s_keys[0][0])[tid] = make_uint2(0u, 0u);
+    // key slots of warps that do not exist stay (value 0, word ~0): the cross-warp reduction reads all 32 without a test
+    if (tid < 64) (&s_keys[0][0])[tid] = make_uint2(0xffffffffu, 0u);
     __syncthreads();
 
+#pragma unroll 2
     for (int it = 1; it < m; ++it) {
         const unsigned long long X1 = f2_pack(x1, x1), Y1 = f2_pack(y1, y1), Z1 = f2_pack(z1, z1);
 #pragma unroll
@@ -270,15 +281,15 @@ __device__ __forceinline__ void fps_chain_packed(int n, int m, const float* __re
         unsigned cu = SO::tbj(GS - 1);
 #pragma unroll
         for (int u = GS - 2; u >= 0; --u) cu = (s[u] == mx) ? SO::tbj(u) : cu;
-        unsigned hi = __float_as_uint(mx), lo = ~(tp | cg | cu);
-        warp_max_pair(hi, lo);
+        unsigned hi = __float_as_uint(mx), lo = tp | cg | cu;
+        warp_max_min_pair(hi, lo);
         const int buf = it & 1;
         s_keys[buf][warp] = make_uint2(lo, hi);  // every lane holds the warp's key: one same-address store, no test
         __syncthreads();
         const uint2 e = s_keys[buf][lane];
         unsigned gh = e.y, gl = e.x;
-        warp_max_pair(gh, gl);
-        const int old = (int)tb_decode(~gl);
+        warp_max_min_pair(gh, gl);
+        const int old = (int)tb_decode(gl);
         x1 = src[3 * old + 0];
         y1 = src[3 * old + 1];
         z1 = src[3 * old + 2];
