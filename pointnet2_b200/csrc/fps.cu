@@ -857,7 +857,7 @@ static std::once_flag g_fps_env_once;
 // Which chain the single-CTA kernel runs where both exist (points per thread >= 8): 1 = fps_chain_packed,
 // 0 = the plain fps_step chain.  PN2_FPS_PACKED=0/1 overrides the built-in choice; an override plan with
 // cluster = -1 / -2 (pn2_set_fps_config, PN2_FPS_CFG) forces the plain / packed chain for that plan.
-constexpr int kFpsPackedDefault = 0;
+constexpr int kFpsPackedDefault = 1;
 static std::atomic<int> g_fps_packed{kFpsPackedDefault};
 
 static unsigned long long pack_cfg(int threads, int ppt, int cluster) {
