@@ -179,6 +179,39 @@ struct ScanOrder {
     }
 };
 
+// Value-only maximum (floored at 0) of P running minima held in ascending tie-break order, and the position of the
+// FIRST leaf that attains it: first group of four whose maximum equals the maximum, then the first equal leaf inside
+// it — what a strict '>' scan from -1 over the same order selects whenever the maximum is >= 0.  Padding leaves
+// carry -1 and never equal it; if no leaf does (a thread without points) the position is P-1 and the caller's
+// tie-break part masks the key.
+template <int P>
+__device__ __forceinline__ void value_argmax_first(const float (&td)[P], float& mx, int& pos) {
+    static_assert(P % 4 == 0, "groups of four");
+    constexpr int G = P / 4;
+    float g[G];
+#pragma unroll
+    for (int a = 0; a < G; ++a) g[a] = fmaxf(fmaxf(fmaxf(td[4 * a], td[4 * a + 1]), td[4 * a + 2]), td[4 * a + 3]);
+    float m = 0.0f;
+#pragma unroll
+    for (int a = 0; a < G; ++a) m = fmaxf(m, g[a]);
+    float s0 = td[4 * (G - 1)], s1 = td[4 * (G - 1) + 1], s2 = td[4 * (G - 1) + 2];
+    int pg = 4 * (G - 1);
+#pragma unroll
+    for (int a = G - 2; a >= 0; --a) {
+        const bool q = (g[a] == m);
+        s0 = q ? td[4 * a] : s0;
+        s1 = q ? td[4 * a + 1] : s1;
+        s2 = q ? td[4 * a + 2] : s2;
+        pg = q ? 4 * a : pg;
+    }
+    int pu = 3;
+    pu = (s2 == m) ? 2 : pu;
+    pu = (s1 == m) ? 1 : pu;
+    pu = (s0 == m) ? 0 : pu;
+    mx = m;
+    pos = pg | pu;
+}
+
 // ---- the M-step chain of fps_cta_kernel, restructured around what binds it ---------------------------
 // The plain chain (fps_step) spends 10 instructions per point and step: 6 on the FMA pipe (3 FADD, FMUL, 2 FFMA)
 // and 4 on the half-rate ALU pipe (FMNMX, FSETP, FSEL, SEL: the running (value, position) maximum).  With two
@@ -450,12 +483,16 @@ fps_cta_kernel(int n, int m, const float* __restrict__ xyz, int* __restrict__ id
 // from the shared-memory copy as 128-bit loads of 4 points per coordinate; the running minimum of
 // every point stays in registers.
 // =================================================================================================
-template <int P, int T, int PR>
+// V = 1 (P % 4 == 0): the per-thread update of fps_chain_packed — packed FP32x2 distances, value-only maximum,
+// position by value_argmax_first; a thread's points are already in tie-break order here (one slot per thread), and
+// the tie-break word of point j is tb_encode(t + T*rank) | j << (log2(C*T) - 9).  The exchange is unchanged.
+template <int P, int T, int PR, int V = 0>
 __global__ void __launch_bounds__(T, 1)
 fps_cluster_kernel(int n, int m, int log2c, const float* __restrict__ xyz, int* __restrict__ idx_out,
                    float* __restrict__ new_xyz) {
     static_assert(T % 512 == 0 || 512 % T == 0, "T must divide or be a multiple of 512");
     static_assert(PR == P || (PR % 4 == 0 && P % 4 == 0 && PR < P), "streamed points come in groups of four");
+    static_assert(V == 0 || (P % 4 == 0 && PR % 2 == 0), "the packed update works on pairs and groups of four");
     constexpr int NW = T / 32;
     constexpr bool STREAM = PR < P;
     __shared__ uint2 s_keys[2][32];
@@ -504,6 +541,23 @@ fps_cluster_kernel(int n, int m, int log2c, const float* __restrict__ xyz, int* 
             pz[j] = z;
         }
     }
+    // V == 1: the register-resident coordinates as packed pairs (the scalar copies above are then dead)
+    constexpr int HR = (V == 1) ? PR / 2 : 1;
+    unsigned long long X2[HR], Y2[HR], Z2[HR];
+    unsigned tpc = 0u, jshift = 0u;
+    if constexpr (V == 1) {
+#pragma unroll
+        for (int h = 0; h < HR; ++h) {
+            X2[h] = f2_pack(px[2 * h], px[2 * h + 1]);
+            Y2[h] = f2_pack(py[2 * h], py[2 * h + 1]);
+            Z2[h] = f2_pack(pz[2 * h], pz[2 * h + 1]);
+        }
+        const unsigned base = (unsigned)tid + (unsigned)T * rank;  // this thread's point j = 0
+        tpc = (base < (unsigned)n) ? tb_encode(base) : 0xffffffffu;  // all ones: a thread without points sends key (0, 0)
+        unsigned log2t = 0;
+        while ((1u << log2t) < (unsigned)T) ++log2t;
+        jshift = (unsigned)log2c + log2t - 9u;  // C*T is a multiple of 512 (checked by the dispatcher)
+    }
 
     float x1 = pts[0], y1 = pts[1], z1 = pts[2];
     if (rank == 0 && tid == 0) {
@@ -526,6 +580,43 @@ fps_cluster_kernel(int n, int m, int log2c, const float* __restrict__ xyz, int* 
         const unsigned mbar = buf ? mbar1 : mbar0;
         if (tid == 0) mbar_arrive_expect_tx(mbar, 20u * C);
 
+        unsigned hi = 0u, lo = 0u;
+        if constexpr (V == 1) {
+            const unsigned long long X1 = f2_pack(x1, x1), Y1 = f2_pack(y1, y1), Z1 = f2_pack(z1, z1);
+#pragma unroll
+            for (int h = 0; h < PR / 2; ++h) {
+                const unsigned long long dx = f2_sub(X2[h], X1), dy = f2_sub(Y2[h], Y1), dz = f2_sub(Z2[h], Z1);
+                const unsigned long long d = f2_fma(dz, dz, f2_fma(dx, dx, f2_mul(dy, dy)));
+                float d0, d1;
+                f2_unpack(d, d0, d1);
+                td[2 * h] = fminf(d0, td[2 * h]);
+                td[2 * h + 1] = fminf(d1, td[2 * h + 1]);
+            }
+            if constexpr (STREAM) {
+#pragma unroll
+                for (int g = PR / 4; g < P / 4; ++g) {
+                    const float4 X = s4[(g * 3 + 0) * T + tid], Y = s4[(g * 3 + 1) * T + tid], Z = s4[(g * 3 + 2) * T + tid];
+                    const unsigned long long xa = f2_pack(X.x, X.y), xb = f2_pack(X.z, X.w), ya = f2_pack(Y.x, Y.y),
+                                             yb = f2_pack(Y.z, Y.w), za = f2_pack(Z.x, Z.y), zb = f2_pack(Z.z, Z.w);
+                    const unsigned long long dxa = f2_sub(xa, X1), dya = f2_sub(ya, Y1), dza = f2_sub(za, Z1);
+                    const unsigned long long dxb = f2_sub(xb, X1), dyb = f2_sub(yb, Y1), dzb = f2_sub(zb, Z1);
+                    const unsigned long long da = f2_fma(dza, dza, f2_fma(dxa, dxa, f2_mul(dya, dya)));
+                    const unsigned long long db = f2_fma(dzb, dzb, f2_fma(dxb, dxb, f2_mul(dyb, dyb)));
+                    float d0, d1, d2, d3;
+                    f2_unpack(da, d0, d1);
+                    f2_unpack(db, d2, d3);
+                    td[4 * g + 0] = fminf(d0, td[4 * g + 0]);
+                    td[4 * g + 1] = fminf(d1, td[4 * g + 1]);
+                    td[4 * g + 2] = fminf(d2, td[4 * g + 2]);
+                    td[4 * g + 3] = fminf(d3, td[4 * g + 3]);
+                }
+            }
+            float mx;
+            int pos;
+            value_argmax_first<P>(td, mx, pos);
+            hi = __float_as_uint(mx);
+            lo = ~(tpc | ((unsigned)pos << jshift));
+        } else {
         float best;
         int bj;
         fps_step<PR, 1, P>(px, py, pz, td, x1, y1, z1, best, bj);  // the PR register-resident points
@@ -547,11 +638,11 @@ fps_cluster_kernel(int n, int m, int log2c, const float* __restrict__ xyz, int* 
                 }
             }
         }
-        unsigned hi = 0u, lo = 0u;
         if (best >= 0.0f) {
             hi = __float_as_uint(best);
             lo = ~tb_encode((unsigned)(tid + T * (rank + C * bj)));
         }
+        }  // V == 0
         warp_max_pair(hi, lo);
         if (lane == 0) s_keys[buf][warp] = make_uint2(lo, hi);
         __syncthreads();
@@ -619,12 +710,15 @@ fps_cluster_kernel(int n, int m, int log2c, const float* __restrict__ xyz, int* 
 // winning thread is the sender, and the winning lane takes the coordinates from its own registers
 // (a select chain over PR entries, issued by that one warp) or from its own shared-memory column.
 // =================================================================================================
-template <int P, int T, int PR>
+// V = 1: packed update + value_argmax_first, as in fps_cluster_kernel; the tie-break word of point j is
+// tb_encode(t + T*rank) + j*(C*T/512) (C*T is a multiple of 512 for every C because T is).
+template <int P, int T, int PR, int V = 0>
 __global__ void __launch_bounds__(T, 1)
 fps_cluster_big_kernel(int n, int m, int C, const float* __restrict__ xyz, int* __restrict__ idx_out,
                        float* __restrict__ new_xyz) {
     static_assert(T % 512 == 0, "every thread's points must share one reference slot for any cluster size");
     static_assert(PR < P && (P - PR) % 4 == 0, "streamed points come in groups of four");
+    static_assert(V == 0 || (P % 4 == 0 && PR % 4 == 0), "the packed update works on pairs and groups of four");
     constexpr int NW = T / 32;
     constexpr int NG = (P - PR) / 4;
     __shared__ uint2 s_keys[2][32];
@@ -670,6 +764,21 @@ fps_cluster_big_kernel(int n, int m, int C, const float* __restrict__ xyz, int* 
             s_pts[(((g * 3 + 2) * T + tid) << 2) + u] = z;
         }
     }
+    // V == 1: the register-resident coordinates as packed pairs (the scalar copies above are then dead)
+    constexpr int HR = (V == 1) ? PR / 2 : 1;
+    unsigned long long X2[HR], Y2[HR], Z2[HR];
+    unsigned tpc = 0u, jstep = 0u;
+    if constexpr (V == 1) {
+#pragma unroll
+        for (int h = 0; h < HR; ++h) {
+            X2[h] = f2_pack(px[2 * h], px[2 * h + 1]);
+            Y2[h] = f2_pack(py[2 * h], py[2 * h + 1]);
+            Z2[h] = f2_pack(pz[2 * h], pz[2 * h + 1]);
+        }
+        const unsigned base = (unsigned)tid + (unsigned)T * rank;  // this thread's point j = 0
+        tpc = (base < (unsigned)n) ? tb_encode(base) : 0xffffffffu;  // all ones: a thread without points sends key (0, 0)
+        jstep = (unsigned)C * (unsigned)(T / 512);                   // k >> 9 grows by this per j; base >> 9 < jstep
+    }
 
     float x1 = pts[0], y1 = pts[1], z1 = pts[2];
     if (rank == 0 && tid == 0) {
@@ -692,8 +801,44 @@ fps_cluster_big_kernel(int n, int m, int C, const float* __restrict__ xyz, int* 
         const unsigned mbar = buf ? mbar1 : mbar0;
         if (tid == 0) mbar_arrive_expect_tx(mbar, 20u * uc);
 
+        int bj = 0;
+        unsigned myhi = 0u, mylo = 0u;
+        if constexpr (V == 1) {
+            const unsigned long long X1 = f2_pack(x1, x1), Y1 = f2_pack(y1, y1), Z1 = f2_pack(z1, z1);
+#pragma unroll
+            for (int h = 0; h < PR / 2; ++h) {
+                const unsigned long long dx = f2_sub(X2[h], X1), dy = f2_sub(Y2[h], Y1), dz = f2_sub(Z2[h], Z1);
+                const unsigned long long d = f2_fma(dz, dz, f2_fma(dx, dx, f2_mul(dy, dy)));
+                float d0, d1;
+                f2_unpack(d, d0, d1);
+                td[2 * h] = fminf(d0, td[2 * h]);
+                td[2 * h + 1] = fminf(d1, td[2 * h + 1]);
+            }
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const float4 X = s4[(g * 3 + 0) * T + tid], Y = s4[(g * 3 + 1) * T + tid], Z = s4[(g * 3 + 2) * T + tid];
+                const unsigned long long xa = f2_pack(X.x, X.y), xb = f2_pack(X.z, X.w), ya = f2_pack(Y.x, Y.y),
+                                         yb = f2_pack(Y.z, Y.w), za = f2_pack(Z.x, Z.y), zb = f2_pack(Z.z, Z.w);
+                const unsigned long long dxa = f2_sub(xa, X1), dya = f2_sub(ya, Y1), dza = f2_sub(za, Z1);
+                const unsigned long long dxb = f2_sub(xb, X1), dyb = f2_sub(yb, Y1), dzb = f2_sub(zb, Z1);
+                const unsigned long long da = f2_fma(dza, dza, f2_fma(dxa, dxa, f2_mul(dya, dya)));
+                const unsigned long long db = f2_fma(dzb, dzb, f2_fma(dxb, dxb, f2_mul(dyb, dyb)));
+                float d0, d1, d2, d3;
+                f2_unpack(da, d0, d1);
+                f2_unpack(db, d2, d3);
+                const int j = PR + 4 * g;
+                td[j + 0] = fminf(d0, td[j + 0]);
+                td[j + 1] = fminf(d1, td[j + 1]);
+                td[j + 2] = fminf(d2, td[j + 2]);
+                td[j + 3] = fminf(d3, td[j + 3]);
+            }
+            float mx;
+            value_argmax_first<P>(td, mx, bj);
+            myhi = __float_as_uint(mx);
+            mylo = ~(tpc + (unsigned)bj * jstep);  // tpc all ones (no points): the sum wraps to bj*jstep - 1, masked below
+            if (tpc == 0xffffffffu) mylo = 0u;
+        } else {
         float best;
-        int bj;
         fps_step<PR, 1, P>(px, py, pz, td, x1, y1, z1, best, bj);
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
@@ -711,11 +856,11 @@ fps_cluster_big_kernel(int n, int m, int C, const float* __restrict__ xyz, int* 
                 }
             }
         }
-        unsigned myhi = 0u, mylo = 0u;
         if (best >= 0.0f) {
             myhi = __float_as_uint(best);
             mylo = ~tb_encode((unsigned)(tid + T * (rank + uc * bj)));
         }
+        }  // V == 0
         unsigned hi = myhi, lo = mylo;
         warp_max_pair(hi, lo);
         if (lane == 0) s_keys[buf][warp] = make_uint2(lo, hi);
@@ -729,6 +874,25 @@ fps_cluster_big_kernel(int n, int m, int C, const float* __restrict__ xyz, int* 
             const unsigned lmask = __ballot_sync(0xffffffffu, mylo == cl && myhi == ch);
             const int wl = __ffs((int)lmask) - 1;  // the winning thread's lane (keys are unique unless all are zero)
             float cx = 0.f, cy = 0.f, cz = 0.f;
+            if constexpr (V == 1) {
+#pragma unroll
+                for (int h = 0; h < PR / 2; ++h) {
+                    float a0, a1, b0, b1, c0, c1;
+                    f2_unpack(X2[h], a0, a1);
+                    f2_unpack(Y2[h], b0, b1);
+                    f2_unpack(Z2[h], c0, c1);
+                    if (bj == 2 * h) {
+                        cx = a0;
+                        cy = b0;
+                        cz = c0;
+                    }
+                    if (bj == 2 * h + 1) {
+                        cx = a1;
+                        cy = b1;
+                        cz = c1;
+                    }
+                }
+            } else {
 #pragma unroll
             for (int j = 0; j < PR; ++j)
                 if (bj == j) {
@@ -736,6 +900,7 @@ fps_cluster_big_kernel(int n, int m, int C, const float* __restrict__ xyz, int* 
                     cy = py[j];
                     cz = pz[j];
                 }
+            }
             if (bj >= PR) {
                 const int g = (bj - PR) >> 2, u = (bj - PR) & 3;
                 cx = s_pts[(((g * 3 + 0) * T + tid) << 2) + u];
@@ -859,6 +1024,10 @@ static std::once_flag g_fps_env_once;
 // cluster = -1 / -2 (pn2_set_fps_config, PN2_FPS_CFG) forces the plain / packed chain for that plan.
 constexpr int kFpsPackedDefault = 1;
 static std::atomic<int> g_fps_packed{kFpsPackedDefault};
+// The same choice for the cluster kernels (points per thread a multiple of 4): PN2_FPS_PACKED_CLUSTER=0/1; an override
+// plan names the chain in the two low bits of `threads` (T is a multiple of 128): +1 = packed, +2 = plain.
+constexpr int kFpsPackedClusterDefault = 0;
+static std::atomic<int> g_fps_packed_cluster{kFpsPackedClusterDefault};
 
 static unsigned long long pack_cfg(int threads, int ppt, int cluster) {
     if (threads <= 0) return 0ull;
@@ -908,10 +1077,10 @@ static int launch_cta(int b, int n, int m, const float* inp, int* out, float* ne
     return finish_launch();
 }
 
-template <int P, int T, int PR>
+template <int P, int T, int PR, int V>
 static int launch_cluster(int C, int b, int n, int m, const float* inp, int* out, float* new_xyz, cudaStream_t st) {
     static AttrOnce once;
-    auto kern = fps_cluster_kernel<P, T, PR>;
+    auto kern = fps_cluster_kernel<P, T, PR, V>;
     const size_t dyn = (size_t)3 * P * T * sizeof(float);
     if (dyn > 200 * 1024) return (int)cudaErrorInvalidValue;
     cudaError_t e = ensure_attrs(once, kern, dyn, true);
@@ -940,7 +1109,7 @@ static int launch_cluster(int C, int b, int n, int m, const float* inp, int* out
 // planner must keep every cloud's cluster co-resident — a cluster that has to wait for a second wave
 // doubles the time of the whole call (measured: 8 clouds x 16-CTA clusters with 196 KB of shared
 // memory per CTA run as two waves on B200, profiles/r2_fps_cluster_occupancy.txt).
-template <int P, int T, int PR>
+template <int P, int T, int PR, int V>
 static int cluster_capacity(int C) {
     static std::atomic<int> cache[5][64];  // [log2 C][device]; 0 = not asked yet
     int log2c = 0;
@@ -950,7 +1119,7 @@ static int cluster_capacity(int C) {
     const int hit = cache[log2c][dev].load(std::memory_order_relaxed);
     if (hit) return hit > 0 ? hit : 0;
     static AttrOnce once;
-    auto kern = fps_cluster_kernel<P, T, PR>;
+    auto kern = fps_cluster_kernel<P, T, PR, V>;
     const size_t dyn = (size_t)3 * P * T * sizeof(float);
     if (dyn > 200 * 1024 || ensure_attrs(once, kern, dyn, true) != cudaSuccess) return 0;
     cudaLaunchConfig_t cfg = {};
@@ -989,10 +1158,10 @@ static cudaLaunchConfig_t big_config(int C, int clusters, cudaLaunchAttribute* a
     return cfg;
 }
 
-template <int P, int T, int PR>
+template <int P, int T, int PR, int V>
 static int launch_cluster_big(int C, int b, int n, int m, const float* inp, int* out, float* new_xyz, cudaStream_t st) {
     static AttrOnce once;
-    auto kern = fps_cluster_big_kernel<P, T, PR>;
+    auto kern = fps_cluster_big_kernel<P, T, PR, V>;
     cudaLaunchAttribute attr[1];
     cudaLaunchConfig_t cfg = big_config<P, T, PR>(C, b, attr, st);
     if (cfg.dynamicSmemBytes > 226 * 1024) return (int)cudaErrorInvalidValue;
@@ -1004,7 +1173,7 @@ static int launch_cluster_big(int C, int b, int n, int m, const float* inp, int*
     return (int)cudaGetLastError();
 }
 
-template <int P, int T, int PR>
+template <int P, int T, int PR, int V>
 static int cluster_big_capacity(int C) {
     static std::atomic<int> cache[17][64];  // [C][device]; 0 = not asked yet
     int dev = 0;
@@ -1012,7 +1181,7 @@ static int cluster_big_capacity(int C) {
     const int hit = cache[C][dev].load(std::memory_order_relaxed);
     if (hit) return hit > 0 ? hit : 0;
     static AttrOnce once;
-    auto kern = fps_cluster_big_kernel<P, T, PR>;
+    auto kern = fps_cluster_big_kernel<P, T, PR, V>;
     cudaLaunchAttribute attr[1];
     cudaLaunchConfig_t cfg = big_config<P, T, PR>(C, 148, attr, nullptr);
     if (cfg.dynamicSmemBytes > 226 * 1024 || ensure_attrs(once, kern, cfg.dynamicSmemBytes, true) != cudaSuccess) return 0;
@@ -1037,7 +1206,7 @@ static int pow2_floor(int v) {
     return p;
 }
 
-int fps_cluster_capacity(int threads, int ppt, int cluster);
+int fps_cluster_capacity(int threads, int ppt, int cluster, int packed);
 
 static FpsPlan plan_fps(int b, int n) {
     std::call_once(g_fps_env_once, [] {  // PN2_FPS_CFG="threads,points_per_thread,cluster": profiling/tuning override
@@ -1046,16 +1215,23 @@ static FpsPlan plan_fps(int b, int n) {
         if (e && sscanf(e, "%d,%d,%d", &t, &pp, &c) == 3) g_fps_cfg.store(pack_cfg(t, pp, c), std::memory_order_relaxed);
         const char* pk = getenv("PN2_FPS_PACKED");
         if (pk && (pk[0] == '0' || pk[0] == '1') && pk[1] == 0) g_fps_packed.store(pk[0] - '0', std::memory_order_relaxed);
+        const char* pc = getenv("PN2_FPS_PACKED_CLUSTER");
+        if (pc && (pc[0] == '0' || pc[0] == '1') && pc[1] == 0) g_fps_packed_cluster.store(pc[0] - '0', std::memory_order_relaxed);
     });
     const int packed = g_fps_packed.load(std::memory_order_relaxed);
+    const int packed_cluster = g_fps_packed_cluster.load(std::memory_order_relaxed);
     const unsigned long long ov = g_fps_cfg.load(std::memory_order_relaxed);
     if (ov) {
         FpsPlan p;
         p.threads = (int)(ov >> 40);
         p.ppt = (int)((ov >> 20) & 0xfffff);
         p.cluster = (int)(ov & 0xfffff) - 64;
+        const int chain = p.threads & 3;  // cluster plans: chain named in the low bits of `threads`
+        p.threads &= ~3;
         p.pr = (p.ppt >= 32 && p.threads >= 512) ? 16 : p.ppt;  // ppt > 32: the register + shared-memory kernel
-        p.packed = packed;
+        p.packed = (p.cluster >= 2) ? packed_cluster : packed;
+        if (chain == 1) p.packed = 1;
+        if (chain == 2) p.packed = 0;
         if (p.cluster == -1 || p.cluster == -2) {  // single CTA with the chain named explicitly
             p.packed = (p.cluster == -2) ? 1 : 0;
             p.cluster = 1;
@@ -1078,21 +1254,21 @@ static FpsPlan plan_fps(int b, int n) {
     int cmax = pow2_floor(148 / (b > 148 ? 148 : b));
     if (cmax > 16) cmax = 16;
     if (cmax < 2) cmax = 2;
-    auto pick = [](long long per, int C, FpsPlan& out) -> bool {
+    auto pick = [packed_cluster](long long per, int C, FpsPlan& out) -> bool {
         const int t = (C >= 4) ? 128 : 256;  // C*T must be a multiple of 512
         const int pmin = (t == 128) ? 4 : 2;
         for (int pp = pmin; pp <= 32; pp *= 2) {
             if (per <= (long long)t * pp) {
-                out = {t, pp, C, pp};
+                out = {t, pp, C, pp, packed_cluster};
                 return true;
             }
         }
         if (per <= 256LL * 32) {
-            out = {256, 32, C, 32};
+            out = {256, 32, C, 32, packed_cluster};
             return true;
         }
         if (per <= 512LL * 32) {
-            out = {512, 32, C, 16};  // half of the coordinates in registers, half streamed from shared memory
+            out = {512, 32, C, 16, packed_cluster};  // half of the coordinates in registers, half streamed from shared memory
             return true;
         }
         return false;
@@ -1106,7 +1282,7 @@ static FpsPlan plan_fps(int b, int n) {
         if (first.cluster == 0) first = p;
         // every cloud's cluster must be resident at once: a cluster left for a second wave doubles the call
         // (0 = capacity unknown, e.g. no device yet: take the plan)
-        const int cap = fps_cluster_capacity(p.threads, p.ppt, p.cluster);
+        const int cap = fps_cluster_capacity(p.threads, p.ppt, p.cluster, p.packed);
         if (cap == 0 || cap >= b) return p;
     }
     // No power-of-two cluster keeps all b clouds resident (B200 holds seven clusters of 11-16 CTAs, eleven of 10,
@@ -1117,7 +1293,7 @@ static FpsPlan plan_fps(int b, int n) {
     FpsPlan best{0, 0, 0, 0};
     double best_cost = 1e30;
     auto consider = [&](const FpsPlan& p) {
-        const int cap = fps_cluster_capacity(p.threads, p.ppt, p.cluster);
+        const int cap = fps_cluster_capacity(p.threads, p.ppt, p.cluster, p.packed);
         const int waves = cap > 0 ? (b + cap - 1) / cap : 1;
         double cost = waves * (0.3 + 0.07e-3 * (double)p.threads * p.ppt);
         if (cap > 0 && (long long)cap * p.cluster > 148) cost *= 1.3;  // CTAs of a wave share SMs (measured: 0.59 -> 0.77 us)
@@ -1132,7 +1308,7 @@ static FpsPlan plan_fps(int b, int n) {
     for (int C = 16; C >= 2; --C) {
         const long long per = ((long long)n + C - 1) / C;
         if (per > 512LL * 52) break;
-        consider({512, per <= 512LL * 44 ? 44 : (per <= 512LL * 48 ? 48 : 52), C, 16});
+        consider({512, per <= 512LL * 44 ? 44 : (per <= 512LL * 48 ? 48 : 52), C, 16, packed_cluster});
     }
     if (best.cluster) return best;
     return {1024, 0, 0, 0};
@@ -1144,7 +1320,10 @@ static FpsPlan plan_fps(int b, int n) {
     if (plan.packed && plan.ppt == PP && plan.threads == TT) return launch_cta<PP, TT, 1>(b, n, m, inp, out, new_xyz, sentinel, st);
 #define PN2_TRY_CLU(PP, TT, PRR) \
     if (plan.ppt == PP && plan.threads == TT && plan.pr == PRR) \
-        return launch_cluster<PP, TT, PRR>(plan.cluster, b, n, m, inp, out, new_xyz, st);
+        return launch_cluster<PP, TT, PRR, 0>(plan.cluster, b, n, m, inp, out, new_xyz, st);
+#define PN2_TRY_CLU_PACKED(PP, TT, PRR) \
+    if (plan.packed && plan.ppt == PP && plan.threads == TT && plan.pr == PRR) \
+        return launch_cluster<PP, TT, PRR, 1>(plan.cluster, b, n, m, inp, out, new_xyz, st);
 
 bool fps_single_cta(int b, int n) { return plan_fps(b, n).cluster == 1; }
 
@@ -1198,14 +1377,33 @@ int fps_dispatch(int b, int n, int m, const float* inp, float* temp, int* out, f
     }
     if (plan.cluster >= 2 && plan.ppt > 32) {  // register + shared-memory kernel, any cluster size
         if (plan.cluster > 16 || plan.threads != 512) return (int)cudaErrorInvalidValue;
-        if (plan.ppt == 44) return launch_cluster_big<44, 512, 16>(plan.cluster, b, n, m, inp, out, new_xyz, st);
-        if (plan.ppt == 48) return launch_cluster_big<48, 512, 12>(plan.cluster, b, n, m, inp, out, new_xyz, st);
-        if (plan.ppt == 52) return launch_cluster_big<52, 512, 16>(plan.cluster, b, n, m, inp, out, new_xyz, st);
+        if (plan.packed) {
+            if (plan.ppt == 44) return launch_cluster_big<44, 512, 16, 1>(plan.cluster, b, n, m, inp, out, new_xyz, st);
+            if (plan.ppt == 48) return launch_cluster_big<48, 512, 12, 1>(plan.cluster, b, n, m, inp, out, new_xyz, st);
+            if (plan.ppt == 52) return launch_cluster_big<52, 512, 16, 1>(plan.cluster, b, n, m, inp, out, new_xyz, st);
+        }
+        if (plan.ppt == 44) return launch_cluster_big<44, 512, 16, 0>(plan.cluster, b, n, m, inp, out, new_xyz, st);
+        if (plan.ppt == 48) return launch_cluster_big<48, 512, 12, 0>(plan.cluster, b, n, m, inp, out, new_xyz, st);
+        if (plan.ppt == 52) return launch_cluster_big<52, 512, 16, 0>(plan.cluster, b, n, m, inp, out, new_xyz, st);
         return (int)cudaErrorInvalidValue;
     }
     if (plan.cluster >= 2) {
         if (plan.cluster > 16 || (plan.cluster & (plan.cluster - 1))) return (int)cudaErrorInvalidValue;
         if (((long long)plan.cluster * plan.threads) % 512 != 0) return (int)cudaErrorInvalidValue;
+        PN2_TRY_CLU_PACKED(4, 128, 4)
+        PN2_TRY_CLU_PACKED(8, 128, 8)
+        PN2_TRY_CLU_PACKED(16, 128, 16)
+        PN2_TRY_CLU_PACKED(32, 128, 32)
+        PN2_TRY_CLU_PACKED(4, 256, 4)
+        PN2_TRY_CLU_PACKED(8, 256, 8)
+        PN2_TRY_CLU_PACKED(16, 256, 16)
+        PN2_TRY_CLU_PACKED(32, 256, 32)
+        PN2_TRY_CLU_PACKED(4, 512, 4)
+        PN2_TRY_CLU_PACKED(8, 512, 8)
+        PN2_TRY_CLU_PACKED(16, 512, 16)
+        PN2_TRY_CLU_PACKED(32, 512, 16)
+        PN2_TRY_CLU_PACKED(4, 1024, 4)
+        PN2_TRY_CLU_PACKED(8, 1024, 8)
         PN2_TRY_CLU(4, 128, 4)
         PN2_TRY_CLU(8, 128, 8)
         PN2_TRY_CLU(16, 128, 16)
@@ -1234,12 +1432,33 @@ int fps_dispatch(int b, int n, int m, const float* inp, float* temp, int* out, f
 }
 
 #define PN2_CAP_CLU(PP, TT, PRR) \
-    if (ppt == PP && threads == TT) return cluster_capacity<PP, TT, PRR>(cluster);
-int fps_cluster_capacity(int threads, int ppt, int cluster) {
-    if (threads == 512 && ppt == 44) return cluster_big_capacity<44, 512, 16>(cluster);
-    if (threads == 512 && ppt == 48) return cluster_big_capacity<48, 512, 12>(cluster);
-    if (threads == 512 && ppt == 52) return cluster_big_capacity<52, 512, 16>(cluster);
+    if (ppt == PP && threads == TT) return cluster_capacity<PP, TT, PRR, 0>(cluster);
+#define PN2_CAP_CLU_PACKED(PP, TT, PRR) \
+    if (packed && ppt == PP && threads == TT) return cluster_capacity<PP, TT, PRR, 1>(cluster);
+int fps_cluster_capacity(int threads, int ppt, int cluster, int packed) {
+    if (packed) {
+        if (threads == 512 && ppt == 44) return cluster_big_capacity<44, 512, 16, 1>(cluster);
+        if (threads == 512 && ppt == 48) return cluster_big_capacity<48, 512, 12, 1>(cluster);
+        if (threads == 512 && ppt == 52) return cluster_big_capacity<52, 512, 16, 1>(cluster);
+    }
+    if (threads == 512 && ppt == 44) return cluster_big_capacity<44, 512, 16, 0>(cluster);
+    if (threads == 512 && ppt == 48) return cluster_big_capacity<48, 512, 12, 0>(cluster);
+    if (threads == 512 && ppt == 52) return cluster_big_capacity<52, 512, 16, 0>(cluster);
     if (cluster < 2 || cluster > 16 || (cluster & (cluster - 1))) return 0;
+    PN2_CAP_CLU_PACKED(4, 128, 4)
+    PN2_CAP_CLU_PACKED(8, 128, 8)
+    PN2_CAP_CLU_PACKED(16, 128, 16)
+    PN2_CAP_CLU_PACKED(32, 128, 32)
+    PN2_CAP_CLU_PACKED(4, 256, 4)
+    PN2_CAP_CLU_PACKED(8, 256, 8)
+    PN2_CAP_CLU_PACKED(16, 256, 16)
+    PN2_CAP_CLU_PACKED(32, 256, 32)
+    PN2_CAP_CLU_PACKED(4, 512, 4)
+    PN2_CAP_CLU_PACKED(8, 512, 8)
+    PN2_CAP_CLU_PACKED(16, 512, 16)
+    PN2_CAP_CLU_PACKED(32, 512, 16)
+    PN2_CAP_CLU_PACKED(4, 1024, 4)
+    PN2_CAP_CLU_PACKED(8, 1024, 8)
     PN2_CAP_CLU(4, 128, 4)
     PN2_CAP_CLU(8, 128, 8)
     PN2_CAP_CLU(16, 128, 16)
@@ -1266,7 +1485,9 @@ int fps_cluster_capacity(int threads, int ppt, int cluster) {
 extern "C" {
 
 int pn2_fps_cluster_capacity(int threads, int points_per_thread, int cluster) {
-    return pn2::fps_cluster_capacity(threads, points_per_thread, cluster);
+    const int chain = threads & 3;  // as in pn2_set_fps_config: +1 packed chain, +2 plain chain, +0 the built-in choice
+    const int packed = chain == 1 ? 1 : (chain == 2 ? 0 : pn2::g_fps_packed_cluster.load(std::memory_order_relaxed));
+    return pn2::fps_cluster_capacity(threads & ~3, points_per_thread, cluster, packed);
 }
 
 int pn2_fps(int b, int n, int m, const float* inp, float* temp, int* out, void* stream) {

@@ -52,6 +52,10 @@ FPS_VARIANTS = [(512, 2, 2), (512, 1, 4), (512, 4, 2), (512, 8, 4), (1024, 2, 2)
                 # value-only tracking (every instantiation of it)
                 (128, 8, -2), (128, 16, -2), (128, 32, -2), (256, 8, -2), (256, 16, -2), (256, 32, -2), (512, 8, -2),
                 (512, 16, -2), (1024, 8, -2), (128, 8, -1), (256, 16, -1), (256, 32, -1), (512, 16, -1),
+                # cluster kernels with the chain named in the low bits of `threads`: +1 = packed update, +2 = plain
+                (129, 4, 4), (129, 16, 8), (129, 32, 16), (257, 4, 2), (257, 8, 4), (257, 32, 2), (257, 16, 16), (513, 4, 2),
+                (513, 8, 4), (513, 16, 2), (513, 32, 2), (1025, 4, 2), (1025, 8, 4), (513, 44, 2), (513, 44, 3), (513, 48, 5),
+                (513, 48, 13), (513, 52, 7), (513, 52, 10), (130, 16, 8), (514, 32, 2), (514, 44, 3),
                 # register + shared-memory cluster kernel (points per thread > 32), any cluster size incl. non-powers of two
                 (512, 44, 2), (512, 44, 3), (512, 44, 12), (512, 44, 16), (512, 48, 5), (512, 48, 11), (512, 48, 13), (512, 52, 10), (512, 52, 7)]
 
@@ -63,7 +67,7 @@ def test_fps_every_kernel_variant_matches_oracle(dev, cfg, gen):
     (cluster 1), the DSMEM cluster exchange carrying key + coordinates (cluster >= 2) and the variant
     that streams half of the coordinates from shared memory (512 x 32) — on a cloud that fits it."""
     threads, ppt, cluster = cfg
-    cap = threads * ppt * max(cluster, 1)
+    cap = (threads & ~3) * ppt * max(cluster, 1)
     n = min(cap, 6000) - 3
     xyz = W.DISTRIBUTIONS[gen](2, n, 32)
     lib = _lib.load()
@@ -77,7 +81,11 @@ def test_fps_every_kernel_variant_matches_oracle(dev, cfg, gen):
 
 @pytest.mark.parametrize("cfg,n", [((512, 32, 16), 262144), ((512, 32, 16), 262143), ((512, 32, 2), 32768), ((256, 32, 16), 131072),
                                    ((128, 32, 16), 65536), ((256, 16, 16), 65536), ((256, 32, 8), 65536),
-                                   ((512, 44, 12), 262144), ((512, 48, 11), 262144), ((512, 44, 3), 67584), ((512, 48, 7), 172032), ((512, 52, 10), 266240)])
+                                   ((512, 44, 12), 262144), ((512, 48, 11), 262144), ((512, 44, 3), 67584), ((512, 48, 7), 172032), ((512, 52, 10), 266240),
+                                   # the same with the packed update (threads + 1)
+                                   ((513, 32, 16), 262144), ((513, 32, 2), 32768), ((257, 32, 16), 131072), ((129, 32, 16), 65536),
+                                   ((257, 16, 16), 65536), ((513, 44, 12), 262144), ((513, 48, 11), 262144), ((513, 44, 3), 67584),
+                                   ((513, 52, 10), 266240)])
 def test_fps_cluster_variants_at_full_capacity(dev, cfg, n):
     """The cluster kernels with EVERY per-thread slot occupied (the 512x32 variant had only
     been forced on n <= 5997, i.e. 31 of its 32 points per thread were padding).  Duplicate-heavy

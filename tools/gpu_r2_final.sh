@@ -5,10 +5,12 @@
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 echo "=== probe ($(date +%T))"
-timeout 240 python tools/fps_packed_probe.py 2>&1 | tee gpurun_out/fps_packed_probe.log | tail -14
+timeout 240 python tools/fps_packed_probe.py 2>&1 | tee gpurun_out/fps_packed_probe.log | tail -30
 dec=$(grep -o "DECISION packed=[01]" gpurun_out/fps_packed_probe.log | tail -1 | grep -o "[01]$")
+cdec=$(grep -o "DECISION_CLUSTER packed=[01]" gpurun_out/fps_packed_probe.log | tail -1 | grep -o "[01]$")
 export PN2_FPS_PACKED=${dec:-0}
-echo "PN2_FPS_PACKED=$PN2_FPS_PACKED" | tee gpurun_out/final_decision.txt
+export PN2_FPS_PACKED_CLUSTER=${cdec:-0}
+echo "PN2_FPS_PACKED=$PN2_FPS_PACKED PN2_FPS_PACKED_CLUSTER=$PN2_FPS_PACKED_CLUSTER" | tee gpurun_out/final_decision.txt
 echo "=== tests ($(date +%T))"
 timeout 600 python -m pytest tests -q -m gpu -x 2>&1 | tail -15 | tee gpurun_out/final_alltests.log
 echo "=== smoke ($(date +%T))"
