@@ -1026,7 +1026,7 @@ constexpr int kFpsPackedDefault = 1;
 static std::atomic<int> g_fps_packed{kFpsPackedDefault};
 // The same choice for the cluster kernels (points per thread a multiple of 4): PN2_FPS_PACKED_CLUSTER=0/1; an override
 // plan names the chain in the two low bits of `threads` (T is a multiple of 128): +1 = packed, +2 = plain.
-constexpr int kFpsPackedClusterDefault = 0;
+constexpr int kFpsPackedClusterDefault = 1;
 static std::atomic<int> g_fps_packed_cluster{kFpsPackedClusterDefault};
 
 static unsigned long long pack_cfg(int threads, int ppt, int cluster) {
