@@ -637,7 +637,12 @@ def run_b200_arm(args, cfg):
         pt, pp, pc = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         lib.pn2_fps_plan(b, n, ctypes.byref(pt), ctypes.byref(pp), ctypes.byref(pc))
         kinds = {1: "fps_cta_kernel", 0: "fps_global_kernel"}
-        fps_kernel = f"{kinds.get(pc.value, 'fps_cluster_kernel')}<{pp.value},{pt.value}>" + (f" cluster={pc.value}" if pc.value > 1 else "")
+        # chain of the sampling kernel: the packed FP32x2 / value-only update is the library's built-in choice wherever
+        # it is instantiated (>= 8 points per thread for one CTA per cloud, a multiple of 4 for clusters)
+        env_chain = os.environ.get("PN2_FPS_PACKED" if pc.value == 1 else "PN2_FPS_PACKED_CLUSTER", "1")
+        packed_chain = env_chain != "0" and (pp.value >= 8 if pc.value == 1 else (pc.value > 1 and pp.value % 4 == 0))
+        fps_kernel = (f"{kinds.get(pc.value, 'fps_cluster_kernel')}<{pp.value},{pt.value}{',1' if packed_chain else ''}>"
+                      + (f" cluster={pc.value}" if pc.value > 1 else "") + (" packed chain" if packed_chain else ""))
         peak, peak_kind = measured_peaks()
         fps_ms = statistics.mean(t_fps)
         fps_bytes = W.bytes_fps(b, n, m, with_new_xyz=True)
@@ -677,8 +682,10 @@ def run_b200_arm(args, cfg):
                          "note": "FPS is a serial chain of npoint argmax steps: latency/FP32-issue bound, not HBM bound; it is "
                                  f"{100 * fps_ms / step_ms:.0f} % of the step now that the ball query + grouping overlap it",
                          "secondary": {"point_pairs_per_s": b * (m - 1) * n / (fps_ms * 1e-3),
-                                       # 10 FP32/ALU instructions per point pair is the minimum for the exact
-                                       # arithmetic contract (SASS: 3 FADD, FMUL, 2 FFMA, FMNMX, FSETP, FSEL, SEL)
+                                       # normalised to the PLAIN chain's 10 scalar instructions per point pair
+                                       # (SASS: 3 FADD, FMUL, 2 FFMA, FMNMX, FSETP, FSEL, SEL) so that rounds compare; the
+                                       # packed chain issues ~5.5 per pair (3 FP32x2 halves, FMNMX, 0.6 of FMNMX3, search)
+                                       "fp32_issue_basis": "10 scalar instructions per point pair (plain chain); the packed chain issues ~5.5",
                                        "fp32_issue_frac_of_gpu": b * (m - 1) * n * 10 / (fps_ms * 1e-3) / (148 * 128 * 1.965e9),
                                        "fp32_issue_frac_of_occupied_sms": b * (m - 1) * n * 10 / (fps_ms * 1e-3) / (min(b, 148) * 128 * 1.965e9),
                                        "whole_layer_GBps": layer_bytes / (step_ms * 1e-3) / 1e9,

@@ -247,7 +247,12 @@ unsigned long long pn2_launch_count(void);
  * (largest float t with max(sqrtf(t),1e-20f) < radius; negative if no t qualifies) */
 float pn2_ball_threshold(float radius);
 /* tuning override for experiments: threads, points/thread, cluster size of the FPS kernel
- * (cluster 0 = global-scratch fallback); threads = 0 restores the built-in plan */
+ * (cluster 0 = global-scratch fallback); threads = 0 restores the built-in plan.
+ * The per-step update exists in two bit-identical forms — the plain scalar chain and the packed FP32x2 /
+ * value-only chain that is the built-in choice wherever it is instantiated (environment: PN2_FPS_PACKED=0/1 for
+ * one CTA per cloud, PN2_FPS_PACKED_CLUSTER=0/1 for clusters).  An override can name the chain: cluster = -1 /
+ * -2 = one CTA per cloud with the plain / packed chain; for cluster plans the two low bits of `threads`
+ * (threads is a multiple of 128): +1 = packed, +2 = plain. */
 void pn2_set_fps_config(int threads, int points_per_thread, int cluster);
 /* the kernel variant pn2_fps would launch for (b, n): threads per CTA, points per thread and
  * cluster size (1 = one CTA per cloud, >= 2 = thread-block cluster per cloud, 0 = global-scratch
