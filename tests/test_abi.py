@@ -54,6 +54,35 @@ def test_host_only_entry_points_work_without_gpu():
     assert lib.pn2_error_string(1)  # cudaErrorInvalidValue has a message
 
 
+def test_fps_plan_and_chain_override_codes_without_gpu():
+    """The single-CTA plans need no device; an override names the per-step chain (pn2_api.h: cluster -1 / -2, or
+    the two low bits of `threads` for cluster plans) without changing the plan that is reported."""
+    lib = _lib.load()
+
+    def plan(b, n):
+        t, p, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        assert lib.pn2_fps_plan(b, n, ctypes.byref(t), ctypes.byref(p), ctypes.byref(c)) == 0
+        return t.value, p.value, c.value
+
+    try:
+        lib.pn2_set_fps_config(0, 0, 0)
+        assert plan(32, 4096) == (256, 16, 1)    # cfg2: 8 warps x 16 points
+        assert plan(16, 8192) == (256, 32, 1)    # cfg4 SA1
+        assert plan(32, 1024) == (128, 8, 1)     # cfg3 layer 1
+        for t, p, c in ((256, 16, 1), (128, 32, 1), (512, 8, 1)):
+            assert t * p * c >= 4096
+        for chain in (-1, -2):
+            lib.pn2_set_fps_config(256, 16, chain)
+            assert plan(32, 4096) == (256, 16, 1)
+            assert plan(1, 100000) == (256, 16, 1)  # an override is taken as given, whatever n
+        for bits in (1, 2):
+            lib.pn2_set_fps_config(128 + bits, 32, 16)
+            assert plan(8, 65536) == (128, 32, 16)
+        assert lib.pn2_fps_plan(0, 4096, None, None, None) != 0
+    finally:
+        lib.pn2_set_fps_config(0, 0, 0)
+
+
 def test_argument_errors_are_reported_not_launched():
     lib = _lib.load()
     before = _lib.launch_count()
