@@ -17,7 +17,8 @@ WATCH = [("CREDUX", r"^CREDUX"), ("REDUX", r"^REDUX"), ("FADD2", r"^FADD2"), ("F
          ("PREEXIT(griddepcontrol.launch_dependents)", r"^PREEXIT"), ("ACQBULK(griddepcontrol.wait)", r"^ACQBULK"), ("BAR.SYNC", r"^BAR"), ("LDS.128", r"^LDS.*128"), ("LDS.64", r"^LDS.*64"), ("LDS", r"^LDS"), ("STS", r"^STS"),
          ("LDG.128", r"^LDG.*128"), ("STG.128", r"^STG.*128"), ("LDG", r"^LDG"), ("STG", r"^STG"), ("SHFL", r"^SHFL"), ("VOTE", r"^VOTE"),
          ("POPC", r"^POPC"), ("MUFU", r"^MUFU"), ("LDL", r"^LDL"), ("STL", r"^STL")]
-SHOW = ["fps_cta_kernel<16, 256, 0>", "fps_cta_kernel<16, 256, 1>", "fps_cta_kernel<32, 256, 1>", "fps_cluster_kernel<16, 128, 16>", "fps_cluster_kernel<32, 128, 32>", "fps_cluster_kernel<32, 512, 16>",
+SHOW = ["fps_cta_kernel<16, 256, 0>", "fps_cta_kernel<16, 256, 1>", "fps_cta_kernel<32, 256, 1>", "fps_cluster_kernel<16, 128, 16, 1>", "fps_cluster_kernel<32, 128, 32, 0>", "fps_cluster_kernel<32, 128, 32, 1>", "fps_cluster_kernel<32, 512, 16, 1>",
+        "fps_cluster_big_kernel<52, 512, 16, 0>", "fps_cluster_big_kernel<52, 512, 16, 1>",
         "ball_group_kernel", "knn_kernel", "ball_query_kernel<16>", "bq_grid_build_kernel", "bq_grid_query_kernel",
         "group_rows_vec4_kernel<32, 4>", "group_narrow_kernel<0>", "group_rows_kernel<32, true>", "group_concat_vec_kernel<16, 2>",
         "group_point_grad_vec4_kernel<unsigned int>", "three_nn_kernel", "fp_front_kernel<1>", "fp_front_kernel<8>",
